@@ -1,0 +1,46 @@
+"""Build libvgpmp_b200.so in-tree with nvcc for sm_100a (no torch, no JIT cache)."""
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+SRC = [PKG / "csrc" / n for n in ("cabi.cu", "kinematics.cu", "gp.cu")]
+HDR = [PKG / "csrc" / "common.cuh", PKG.parent / "include" / "vgpmp_b200.h"]
+LIB = PKG / "lib" / "libvgpmp_b200.so"
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--fmad=true", "-Xptxas", "-v"]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found: libvgpmp_b200.so cannot be built (there is no CPU fallback)")
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    return any(p.stat().st_mtime > t for p in SRC + HDR)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB
+    LIB.parent.mkdir(parents=True, exist_ok=True)
+    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB), *map(str, SRC)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    (PKG / "lib" / "build.log").write_text(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stderr[-4000:])
+    if verbose:
+        print(res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

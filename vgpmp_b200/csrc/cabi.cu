@@ -1,0 +1,330 @@
+// C-ABI of libvgpmp_b200.so: handle lifetime, workspace carving, argument checks, entry points.
+// Every entry point documents the reference interface it replaces in include/vgpmp_b200.h.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+namespace {
+
+std::string g_create_error;
+
+inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int fail(vgpmp_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+
+int check_cuda(vgpmp_handle* h, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return VGPMP_OK;
+  return fail(h, VGPMP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+  double* take(size_t n_doubles) {
+    double* r = reinterpret_cast<double*>(base + off);
+    off = align_up(off + n_doubles * sizeof(double));
+    return r;
+  }
+};
+
+GpScratch carve(void* ws, int D, const vgpmp_dims& d, size_t* total) {
+  const size_t Bp = d.num_problems, M = d.num_inducing, Mp = M + 2, N = d.num_timesteps, S = d.num_samples;
+  const size_t A = N + Mp;
+  Carver c(ws);
+  GpScratch g;
+  g.Lc = c.take(Bp * D * Mp * Mp);
+  g.Sfull = c.take(Bp * D * Mp * Mp);
+  g.kl_l = c.take(Bp * D);
+  g.kvec = c.take(Bp * D * (Mp + 4));
+  g.v = c.take(Bp * D * S * Mp);
+  g.f0 = c.take(Bp * D * S * A);
+  g.h0 = c.take(Bp * D * S * A);
+  g.f = c.take(Bp * S * N * D);
+  g.df = c.take(Bp * S * N * D);
+  g.logp = c.take(Bp * S * N);
+  *total = c.off;
+  return g;
+}
+
+int check_dims(vgpmp_handle* h, const vgpmp_dims* d) {
+  if (!h || !d) return fail(h, VGPMP_ERR_INVALID, "null handle or dims");
+  if (d->num_problems < 1 || d->num_inducing < 1 || d->num_timesteps < 1 || d->num_samples < 1 || d->num_bases < 1)
+    return fail(h, VGPMP_ERR_INVALID, "all dims must be >= 1");
+  if (d->num_inducing + 2 > VGPMP_MAX_MP) return fail(h, VGPMP_ERR_INVALID, "num_inducing + 2 must be <= 32");
+  if (d->num_timesteps + d->num_inducing + 2 > 768) return fail(h, VGPMP_ERR_INVALID, "num_timesteps + Mp must be <= 768");
+  if (d->num_samples >= (1 << 24)) return fail(h, VGPMP_ERR_INVALID, "num_samples must be < 2^24");
+  return VGPMP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vgpmp_version(void) { return "vgpmp_b200 0.1 (sm_100a, float64)"; }
+
+const char* vgpmp_last_error(const vgpmp_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+uint64_t vgpmp_launch_count(const vgpmp_handle* h) { return h ? h->launches : 0; }
+
+int vgpmp_create(vgpmp_handle** out, int device, const vgpmp_robot_desc* robot, const vgpmp_sdf_desc* sdf,
+                 const vgpmp_lik_desc* lik) {
+  if (!out || !robot || !sdf || !lik) return fail(nullptr, VGPMP_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (robot->dof < 1 || robot->dof > VGPMP_MAX_DOF) return fail(nullptr, VGPMP_ERR_INVALID, "dof must be in 1..8");
+  if (robot->num_spheres < 1 || robot->num_spheres > VGPMP_MAX_SPHERES)
+    return fail(nullptr, VGPMP_ERR_INVALID, "num_spheres must be in 1..64");
+  if (sdf->nx < 1 || sdf->ny < 1 || sdf->nz < 1 || !(sdf->delta > 0.0) || !sdf->data)
+    return fail(nullptr, VGPMP_ERR_INVALID, "bad SDF description");
+  if (!(lik->sigma_obs > 0.0)) return fail(nullptr, VGPMP_ERR_INVALID, "sigma_obs must be > 0");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, VGPMP_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(nullptr, VGPMP_ERR_INVALID, "device index out of range");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return fail(nullptr, VGPMP_ERR_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, VGPMP_ERR_NO_DEVICE, "this library holds sm_100a code only; device is sm_" +
+                                                  std::to_string(prop.major) + std::to_string(prop.minor));
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, VGPMP_ERR_CUDA, cudaGetErrorString(e));
+
+  vgpmp_handle* h = new (std::nothrow) vgpmp_handle();
+  if (!h) return fail(nullptr, VGPMP_ERR_INVALID, "out of host memory");
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  RobotDev& r = h->robot;
+  std::memset(&r, 0, sizeof(r));
+  r.dof = robot->dof; r.craig = robot->craig ? 1 : 0; r.num_spheres = robot->num_spheres;
+  for (int j = 0; j < r.dof; ++j) {
+    for (int k = 0; k < 3; ++k) r.dh[j][k] = robot->dh[3 * j + k];
+    r.cos_alpha[j] = std::cos(r.dh[j][2]);
+    r.sin_alpha[j] = std::sin(r.dh[j][2]);
+    r.twist[j] = robot->twist[j];
+    r.lo[j] = robot->limits_lo[j];
+    r.hi[j] = robot->limits_hi[j];
+  }
+  for (int i = 0; i < 12; ++i) r.base[i] = robot->base_pose[i];
+  int prev = 0;
+  for (int p = 0; p < r.num_spheres; ++p) {
+    const int fr = robot->sphere_frame[p];
+    if (fr < prev || fr > r.dof) {
+      delete h;
+      return fail(nullptr, VGPMP_ERR_INVALID, "sphere_frame must be non-decreasing and within 0..dof");
+    }
+    prev = fr;
+    r.sphere_frame[p] = fr;
+    for (int k = 0; k < 3; ++k) r.sphere_off[p][k] = robot->sphere_offsets[3 * p + k];
+    r.sphere_rad[p] = robot->sphere_radii[p];
+  }
+  h->lik.sigma_obs = lik->sigma_obs; h->lik.epsilon = lik->epsilon; h->lik.alpha = lik->alpha;
+  h->lik.jitter = lik->jitter;
+  for (int k = 0; k < 3; ++k) h->lik.offset[k] = lik->scene_offset[k];
+
+  const size_t cells = (size_t)sdf->nx * sdf->ny * sdf->nz;
+  if ((e = cudaMalloc(&h->grid_dev, cells * sizeof(double))) != cudaSuccess ||
+      (e = cudaMemcpy(h->grid_dev, sdf->data, cells * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) {
+    std::string msg = std::string("SDF upload: ") + cudaGetErrorString(e);
+    if (h->grid_dev) cudaFree(h->grid_dev);
+    delete h;
+    return fail(nullptr, VGPMP_ERR_CUDA, msg);
+  }
+  h->sdf.grid = h->grid_dev;
+  h->sdf.nx = sdf->nx; h->sdf.ny = sdf->ny; h->sdf.nz = sdf->nz;
+  for (int k = 0; k < 3; ++k) h->sdf.origin[k] = sdf->origin[k];
+  h->sdf.delta = sdf->delta;
+  *out = h;
+  return VGPMP_OK;
+}
+
+int vgpmp_destroy(vgpmp_handle* h) {
+  if (!h) return VGPMP_OK;
+  cudaSetDevice(h->device);
+  if (h->grid_dev) cudaFree(h->grid_dev);
+  delete h;
+  return VGPMP_OK;
+}
+
+size_t vgpmp_workspace_bytes(const vgpmp_handle* h, const vgpmp_dims* dims) {
+  if (!h || !dims) return 0;
+  size_t total = 0;
+  carve(nullptr, h->robot.dof, *dims, &total);
+  return total;
+}
+
+size_t vgpmp_draws_bytes(const vgpmp_dims* d, int dof) {
+  if (!d) return 0;
+  const size_t Bp = d->num_problems, D = dof, B = d->num_bases, S = d->num_samples, Mp = d->num_inducing + 2;
+  return align_up(Bp * D * B * D * 8) + align_up(Bp * D * B * 8) + align_up(Bp * D * S * B * 8) +
+         2 * align_up(Bp * D * S * Mp * 8);
+}
+
+int vgpmp_fk_frames(vgpmp_handle* h, const double* joints, double* frames, int64_t n, void* stream) {
+  if (!h || !joints || !frames || n < 0) return fail(h, VGPMP_ERR_INVALID, "fk_frames: bad argument");
+  return check_cuda(h, launch_fk_frames(h, joints, frames, n, (cudaStream_t)stream), "fk_frames");
+}
+
+int vgpmp_fk_spheres(vgpmp_handle* h, const double* joints, double* centres, int64_t n, void* stream) {
+  if (!h || !joints || !centres || n < 0) return fail(h, VGPMP_ERR_INVALID, "fk_spheres: bad argument");
+  return check_cuda(h, launch_fk_spheres(h, joints, centres, n, (cudaStream_t)stream), "fk_spheres");
+}
+
+int vgpmp_sdf_lookup(vgpmp_handle* h, const double* pts, double* dist, double* grad, int64_t n, void* stream) {
+  if (!h || !pts || !dist || n < 0) return fail(h, VGPMP_ERR_INVALID, "sdf_lookup: bad argument");
+  return check_cuda(h, launch_sdf_lookup(h, pts, dist, grad, n, (cudaStream_t)stream), "sdf_lookup");
+}
+
+int vgpmp_loglik_fwd_bwd(vgpmp_handle* h, const double* in, int squash, double upstream, double* logp, double* d_in,
+                         int64_t n, void* stream) {
+  if (!h || !in || !logp || n < 0) return fail(h, VGPMP_ERR_INVALID, "loglik_fwd_bwd: bad argument");
+  return check_cuda(h, launch_loglik(h, in, squash, upstream, logp, d_in, n, (cudaStream_t)stream), "loglik_fwd_bwd");
+}
+
+int vgpmp_kuu(vgpmp_handle* h, const double* Z, const double* lengthscales, const double* variances, double jitter,
+              double* K, int num_problems, int num_inducing, void* stream) {
+  if (!h || !Z || !lengthscales || !variances || !K || num_problems < 1 || num_inducing < 1 ||
+      num_inducing + 2 > VGPMP_MAX_MP)
+    return fail(h, VGPMP_ERR_INVALID, "kuu: bad argument");
+  return check_cuda(h, launch_kuu(h, Z, lengthscales, variances, jitter, K, num_problems, num_inducing,
+                                  (cudaStream_t)stream), "kuu");
+}
+
+int vgpmp_kuf(vgpmp_handle* h, const double* Z, const double* X, const double* lengthscales, const double* variances,
+              double* Kuf, int num_problems, int num_inducing, int num_points, void* stream) {
+  if (!h || !Z || !X || !lengthscales || !variances || !Kuf || num_problems < 1 || num_inducing < 1 || num_points < 1 ||
+      num_inducing + 2 > VGPMP_MAX_MP)
+    return fail(h, VGPMP_ERR_INVALID, "kuf: bad argument");
+  return check_cuda(h, launch_kuf(h, Z, X, lengthscales, variances, Kuf, num_problems, num_inducing, num_points,
+                                  (cudaStream_t)stream), "kuf");
+}
+
+int vgpmp_gp_prepare(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_params* p, double* Lc, double* q_sqrt_full,
+                     double* kl, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_dims(h, dims);
+  if (rc) return rc;
+  if (!p || !ws) return fail(h, VGPMP_ERR_INVALID, "gp_prepare: null params or workspace");
+  size_t need = 0;
+  GpScratch g = carve(ws, h->robot.dof, *dims, &need);
+  if (ws_bytes < need) return fail(h, VGPMP_ERR_WORKSPACE, "gp_prepare: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  rc = check_cuda(h, launch_gp_prepare(h, *dims, *p, Lc ? Lc : g.Lc, q_sqrt_full ? q_sqrt_full : g.Sfull, g.kl_l,
+                                       g.kvec, s), "gp_prepare");
+  if (rc || !kl) return rc;
+  // kl[p] = sum_l kl_l: reuse the ELBO reducer with an empty likelihood term
+  vgpmp_dims d0 = *dims;
+  d0.num_timesteps = 0;
+  return check_cuda(h, launch_elbo_reduce(h, d0, g.logp, g.kl_l, g.f0 /*scratch for -kl*/, kl, s), "kl_reduce");
+}
+
+int vgpmp_pathwise_sample(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_params* p, const vgpmp_draws* r,
+                          const double* Xq, int num_query, double* f, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_dims(h, dims);
+  if (rc) return rc;
+  if (!p || !r || !Xq || !f || !ws || num_query < 1) return fail(h, VGPMP_ERR_INVALID, "pathwise_sample: bad argument");
+  vgpmp_dims dq = *dims;
+  dq.num_timesteps = num_query;
+  if ((rc = check_dims(h, &dq))) return rc;
+  size_t need = 0;
+  GpScratch g = carve(ws, h->robot.dof, dq, &need);
+  if (ws_bytes < need) return fail(h, VGPMP_ERR_WORKSPACE, "pathwise_sample: workspace too small (size it with num_timesteps = num_query)");
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = check_cuda(h, launch_gp_prepare(h, dq, *p, g.Lc, g.Sfull, g.kl_l, g.kvec, s), "gp_prepare"))) return rc;
+  return check_cuda(h, launch_pathwise(h, dq, *p, *r, Xq, num_query, g.Lc, g.Sfull, f, nullptr, nullptr, nullptr, s),
+                    "pathwise_sample");
+}
+
+int vgpmp_elbo_fwd_bwd(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_params* p, const vgpmp_draws* r,
+                       double* elbo, const vgpmp_grads* gr, const vgpmp_aux* aux, void* ws, size_t ws_bytes,
+                       void* stream) {
+  int rc = check_dims(h, dims);
+  if (rc) return rc;
+  if (!p || !r || !elbo || !ws) return fail(h, VGPMP_ERR_INVALID, "elbo_fwd_bwd: bad argument");
+  size_t need = 0;
+  GpScratch g = carve(ws, h->robot.dof, *dims, &need);
+  if (ws_bytes < need) return fail(h, VGPMP_ERR_WORKSPACE, "elbo_fwd_bwd: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int D = h->robot.dof;
+  const int64_t ncfg = (int64_t)dims->num_problems * dims->num_samples * dims->num_timesteps;
+  double* f = (aux && aux->f) ? aux->f : g.f;
+  double* logp = (aux && aux->logp) ? aux->logp : g.logp;
+  const bool bwd = gr != nullptr;
+  if ((rc = check_cuda(h, launch_gp_prepare(h, *dims, *p, g.Lc, g.Sfull, g.kl_l, g.kvec, s), "gp_prepare"))) return rc;
+  if ((rc = check_cuda(h, launch_pathwise(h, *dims, *p, *r, p->X, dims->num_timesteps, g.Lc, g.Sfull, f,
+                                          bwd ? g.v : nullptr, bwd ? g.f0 : nullptr, bwd ? g.h0 : nullptr, s),
+                       "pathwise")))
+    return rc;
+  if ((rc = check_cuda(h, launch_loglik(h, f, 1, h->lik.alpha / (double)dims->num_samples, logp, bwd ? g.df : nullptr,
+                                        ncfg, s), "loglik")))
+    return rc;
+  if ((rc = check_cuda(h, launch_elbo_reduce(h, *dims, logp, g.kl_l, elbo, aux ? aux->kl : nullptr, s), "elbo_reduce")))
+    return rc;
+  if (bwd) {
+    GpScratch gs = g;
+    gs.f = f;
+    if ((rc = check_cuda(h, launch_gp_backward(h, *dims, *p, *r, gs, *gr, s), "gp_backward"))) return rc;
+  }
+  (void)D;
+  return VGPMP_OK;
+}
+
+int vgpmp_adam_step(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* st, const vgpmp_grads* g, void* stream) {
+  int rc = check_dims(h, dims);
+  if (rc) return rc;
+  if (!st || !g) return fail(h, VGPMP_ERR_INVALID, "adam_step: bad argument");
+  rc = check_cuda(h, launch_adam(h, *dims, *st, *g, (cudaStream_t)stream), "adam_step");
+  if (!rc) st->step += 1;
+  return rc;
+}
+
+int vgpmp_rng_fill(vgpmp_handle* h, const vgpmp_dims* dims, uint64_t seed, uint64_t iteration, int64_t problem_offset,
+                   int64_t sample_offset, double* omega, double* tau, double* w, double* eps_u, double* eps_j,
+                   void* stream) {
+  int rc = check_dims(h, dims);
+  if (rc) return rc;
+  if ((omega == nullptr) != (tau == nullptr) || (eps_u == nullptr) != (eps_j == nullptr))
+    return fail(h, VGPMP_ERR_INVALID, "rng_fill: omega/tau and eps_u/eps_j come in pairs");
+  return check_cuda(h, launch_rng_fill(h, *dims, seed, iteration, problem_offset, sample_offset, omega, tau, w, eps_u,
+                                       eps_j, (cudaStream_t)stream), "rng_fill");
+}
+
+int vgpmp_train_step_host(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* st, const double* query_latent,
+                          const double* Z, const double* X_host, double* X_dev, uint64_t seed, double* draws_ws,
+                          size_t draws_bytes, const vgpmp_grads* g, double* elbo_dev, double* loss_host, void* ws,
+                          size_t ws_bytes, void* stream) {
+  int rc = check_dims(h, dims);
+  if (rc) return rc;
+  if (!st || !query_latent || !Z || !X_host || !X_dev || !draws_ws || !g || !elbo_dev || !loss_host || !ws)
+    return fail(h, VGPMP_ERR_INVALID, "train_step_host: bad argument");
+  const int D = h->robot.dof;
+  if (draws_bytes < vgpmp_draws_bytes(dims, D)) return fail(h, VGPMP_ERR_WORKSPACE, "train_step_host: draws buffer too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t Bp = dims->num_problems, B = dims->num_bases, S = dims->num_samples, Mp = dims->num_inducing + 2;
+  if ((rc = check_cuda(h, cudaMemcpyAsync(X_dev, X_host, sizeof(double) * dims->num_timesteps * D, cudaMemcpyHostToDevice, s),
+                       "H2D X")))
+    return rc;
+  Carver c(draws_ws);
+  double* omega = c.take(Bp * D * B * D);
+  double* tau = c.take(Bp * D * B);
+  double* w = c.take(Bp * D * S * B);
+  double* eps_u = c.take(Bp * D * S * Mp);
+  double* eps_j = c.take(Bp * D * S * Mp);
+  if ((rc = vgpmp_rng_fill(h, dims, seed, (uint64_t)st->step, 0, 0, omega, tau, w, eps_u, eps_j, stream))) return rc;
+  vgpmp_params p{st->q_mu, st->q_sqrt, st->lengthscales, st->variances, query_latent, Z, X_dev};
+  vgpmp_draws r{omega, tau, w, eps_u, eps_j};
+  if ((rc = vgpmp_elbo_fwd_bwd(h, dims, &p, &r, elbo_dev, g, nullptr, ws, ws_bytes, stream))) return rc;
+  if ((rc = vgpmp_adam_step(h, dims, st, g, stream))) return rc;
+  if ((rc = check_cuda(h, cudaMemcpyAsync(loss_host, elbo_dev, sizeof(double) * Bp, cudaMemcpyDeviceToHost, s), "D2H loss")))
+    return rc;
+  if ((rc = check_cuda(h, cudaStreamSynchronize(s), "sync"))) return rc;
+  for (size_t i = 0; i < Bp; ++i) loss_host[i] = -loss_host[i];  // training_loss = -ELBO
+  return VGPMP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+// Internal declarations shared by the vgpmp_b200 translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/vgpmp_b200.h"
+
+#define VG_SQRT5 2.23606797749978969641
+
+// Robot constants passed BY VALUE as a kernel parameter: they land in the constant bank, and every
+// thread of a warp walks joints/spheres in lock-step, so each access is a uniform broadcast load.
+struct RobotDev {
+  int dof, craig, num_spheres, pad_;
+  double dh[VGPMP_MAX_DOF][3];      // d, a, alpha
+  double cos_alpha[VGPMP_MAX_DOF], sin_alpha[VGPMP_MAX_DOF];
+  double twist[VGPMP_MAX_DOF];
+  double lo[VGPMP_MAX_DOF], hi[VGPMP_MAX_DOF];
+  double base[12];                  // rows 0..2 of the 4x4 base pose
+  int sphere_frame[VGPMP_MAX_SPHERES];
+  double sphere_off[VGPMP_MAX_SPHERES][3];
+  double sphere_rad[VGPMP_MAX_SPHERES];
+};
+
+struct SdfDev {
+  const double* grid;  // [nx,ny,nz], z fastest
+  int nx, ny, nz, pad_;
+  double origin[3];
+  double delta;
+  double inv_2delta_unused;
+};
+
+struct LikDev {
+  double sigma_obs, epsilon, alpha, jitter;
+  double offset[3];
+};
+
+struct vgpmp_handle {
+  int device = 0;
+  int num_sms = 0;
+  RobotDev robot{};
+  SdfDev sdf{};
+  LikDev lik{};
+  double* grid_dev = nullptr;
+  uint64_t launches = 0;
+  std::string err;
+};
+
+// ---- launchers implemented in kinematics.cu -------------------------------------------------
+cudaError_t launch_fk_frames(vgpmp_handle* h, const double* joints, double* frames, int64_t n, cudaStream_t s);
+cudaError_t launch_fk_spheres(vgpmp_handle* h, const double* joints, double* centres, int64_t n, cudaStream_t s);
+cudaError_t launch_sdf_lookup(vgpmp_handle* h, const double* pts, double* dist, double* grad, int64_t n, cudaStream_t s);
+cudaError_t launch_loglik(vgpmp_handle* h, const double* in, int squash, double upstream, double* logp, double* d_in,
+                          int64_t n, cudaStream_t s);
+
+// ---- launchers implemented in gp.cu ---------------------------------------------------------
+struct GpScratch {  // carved from the caller's workspace by cabi.cu
+  double* Lc;      // [Bp,D,Mp,Mp]
+  double* Sfull;   // [Bp,D,Mp,Mp]
+  double* kl_l;    // [Bp,D]
+  double* kvec;    // [Bp,D,Mp+4]  saved b = Lc^-1 (mu - p_mu) and c = K22^-1 q
+  double* v;       // [Bp,D,S,Mp]
+  double* f0;      // [Bp,D,S,A]   prior draws at X then Zy
+  double* h0;      // [Bp,D,S,A]   d f0 / d lengthscale
+  double* f;       // [Bp,S,N,D]
+  double* df;      // [Bp,S,N,D]
+  double* logp;    // [Bp,S,N]
+};
+
+cudaError_t launch_kuu(vgpmp_handle* h, const double* Z, const double* ls, const double* var, double jitter, double* K,
+                       int Bp, int M, cudaStream_t s);
+cudaError_t launch_kuf(vgpmp_handle* h, const double* Z, const double* X, const double* ls, const double* var,
+                       double* Kuf, int Bp, int M, int N, cudaStream_t s);
+cudaError_t launch_gp_prepare(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, double* Lc, double* Sfull,
+                              double* kl_l, double* kvec, cudaStream_t s);
+cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
+                            const double* Xq, int Nq, const double* Lc, const double* Sfull, double* f, double* v,
+                            double* f0, double* h0, cudaStream_t s);
+cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
+                               const GpScratch& ws, const vgpmp_grads& g, cudaStream_t s);
+cudaError_t launch_elbo_reduce(vgpmp_handle* h, const vgpmp_dims& d, const double* logp, const double* kl_l,
+                               double* elbo, double* kl_out, cudaStream_t s);
+cudaError_t launch_adam(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_adam& st, const vgpmp_grads& g, cudaStream_t s);
+cudaError_t launch_rng_fill(vgpmp_handle* h, const vgpmp_dims& d, uint64_t seed, uint64_t iteration,
+                            int64_t problem_offset, int64_t sample_offset, double* omega, double* tau, double* w,
+                            double* eps_u, double* eps_j, cudaStream_t s);
+
+// Matern-5/2 radial profile and its derivative wrt r (GPflow Matern52.K_r).
+__host__ __device__ inline double vg_matern52(double r) {
+  const double a = VG_SQRT5 * r;
+  return (1.0 + a + (5.0 / 3.0) * r * r) * exp(-a);
+}
+__host__ __device__ inline double vg_matern52_dr(double r) {  // d/dr
+  const double a = VG_SQRT5 * r;
+  return -(5.0 / 3.0) * r * (1.0 + a) * exp(-a);
+}

@@ -1,0 +1,774 @@
+// Gaussian-process side of the vgpmp ELBO hot path (sm_100a, float64):
+//   Kuu / Kuf builds, Cholesky, q_sqrt un-whitening, endpoint-conditioned KL      (gp_prepare_kernel)
+//   random-Fourier prior + pathwise update -> latent trajectory samples             (pathwise_kernel)
+//   reverse pass to _q_mu, _q_sqrt, lengthscales, variances                         (gp_backward_kernel)
+//   ELBO assembly, Keras-Adam update, Philox draw generator.
+//
+// Reference semantics restated (files under /root/reference; GPflow / GPflowSampling are un-vendored):
+//   kernel_conditioning/multioutput/cond_kernel.py:17-25, cond_kernel.py:19-22   per-latent 1-D Matern-5/2
+//   covariances/multioutput/Kuus.py:42-53, Kufs.py:26-34, covariances/Kfus.py:36-42
+//   models/vgpmp.py:200-218 (q_mu / q_sqrt properties), :265-289 (elbo)
+//   kullback_leiblers/prior_kl.py:16-35 + gpflow.kullback_leiblers.gauss_kl (white)
+//   GPflowSampling random_fourier / PathwiseSVGP.generate_paths / exact_update
+//
+// One CTA per (problem, latent GP).  The inducing covariance is at most 32x32, so all dense algebra on it lives in
+// shared memory; triangular solves are warp-per-right-hand-side with the running vector in registers and the pivot
+// broadcast by shuffle.  Matrices in shared memory use a row stride of 33 doubles so that both row and column walks
+// are bank-conflict free.
+#include "common.cuh"
+
+namespace {
+
+constexpr int LDM = 33;          // shared-memory leading dimension of the Mp x Mp matrices
+constexpr int kST = 8;           // samples per register tile in the Fourier contraction
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ double zy_at(const double* __restrict__ Z, int D, int l, int m) {
+  return m == 0 ? 0.0 : (m == 1 ? 1.0 : Z[(size_t)(m - 2) * D + l]);  // Zy = [0; 1; Z]  inducing_variables.py:56-62
+}
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  // deterministic block reduction (fixed tree), result valid in every thread
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+
+// In-place Cholesky of the leading Mp x Mp block of A (lower), whole CTA cooperates.  Upper triangle zeroed.
+__device__ void chol_inplace(double* A, int Mp) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int k = 0; k < Mp; ++k) {
+    __syncthreads();
+    const double piv = sqrt(A[k * LDM + k]);
+    __syncthreads();
+    if (tid == 0) A[k * LDM + k] = piv;
+    for (int i = k + 1 + tid; i < Mp; i += nt) A[i * LDM + k] /= piv;
+    __syncthreads();
+    const int rem = Mp - k - 1;
+    for (int idx = tid; idx < rem * rem; idx += nt) {
+      const int i = k + 1 + idx / rem, j = k + 1 + idx % rem;
+      if (j <= i) A[i * LDM + j] -= A[i * LDM + k] * A[j * LDM + k];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < Mp * Mp; idx += nt) {
+    const int i = idx / Mp, j = idx % Mp;
+    if (j > i) A[i * LDM + j] = 0.0;
+  }
+  __syncthreads();
+}
+
+// Warp-level triangular solves; lane i owns component i (i < Mp <= 32).  L lower-triangular in shared memory.
+__device__ __forceinline__ double warp_fwd_subst(const double* L, int Mp, double d) {  // returns (L^-1 d)_lane
+  const int lane = threadIdx.x & 31;
+  double out = 0.0;
+  for (int k = 0; k < Mp; ++k) {
+    const double bk = __shfl_sync(kFull, d, k) / L[k * LDM + k];
+    if (lane == k) out = bk;
+    if (lane > k && lane < Mp) d -= L[lane * LDM + k] * bk;
+  }
+  return out;
+}
+__device__ __forceinline__ double warp_bwd_subst(const double* L, int Mp, double d) {  // returns (L^-T d)_lane
+  const int lane = threadIdx.x & 31;
+  double out = 0.0;
+  for (int k = Mp - 1; k >= 0; --k) {
+    const double bk = __shfl_sync(kFull, d, k) / L[k * LDM + k];
+    if (lane == k) out = bk;
+    if (lane < k) d -= L[k * LDM + lane] * bk;
+  }
+  return out;
+}
+
+__global__ void kuu_kernel(int D, int M, double jitter, const double* __restrict__ Z, const double* __restrict__ ls,
+                           const double* __restrict__ var, double* __restrict__ K) {
+  const int pl = blockIdx.x, l = pl % D, Mp = M + 2;
+  const double ell = ls[pl], s2 = var[pl];
+  for (int idx = threadIdx.x; idx < Mp * Mp; idx += blockDim.x) {
+    const int i = idx / Mp, j = idx % Mp;
+    const double r = fabs(zy_at(Z, D, l, i) - zy_at(Z, D, l, j)) / ell;
+    K[(size_t)pl * Mp * Mp + idx] = s2 * vg_matern52(r) + (i == j ? jitter : 0.0);
+  }
+}
+
+__global__ void kuf_kernel(int D, int M, int N, const double* __restrict__ Z, const double* __restrict__ X,
+                           const double* __restrict__ ls, const double* __restrict__ var, double* __restrict__ Kuf) {
+  const int pl = blockIdx.x, l = pl % D, Mp = M + 2;
+  const double ell = ls[pl], s2 = var[pl];
+  for (int idx = threadIdx.x; idx < Mp * N; idx += blockDim.x) {
+    const int m = idx / N, n = idx % N;
+    const double r = fabs(zy_at(Z, D, l, m) - X[(size_t)n * D + l]) / ell;
+    Kuf[(size_t)pl * Mp * N + idx] = s2 * vg_matern52(r);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kuu + chol + q_sqrt un-whitening + KL, one CTA (128 threads) per (problem, latent)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, double jitter, vgpmp_params P,
+                                                        double* __restrict__ Lc_out, double* __restrict__ S_out,
+                                                        double* __restrict__ kl_l, double* __restrict__ kvec) {
+  __shared__ double zy[32], Ksm[32 * LDM], Lsm[32 * LDM], mu[32], red[8], cvec[2];
+  const int pl = blockIdx.x, p = pl / D, l = pl % D, Mp = M + 2, tid = threadIdx.x;
+  const double ell = P.lengthscales[pl], s2 = P.variances[pl];
+  if (tid < Mp) {
+    zy[tid] = zy_at(P.Z, D, l, tid);
+    mu[tid] = tid < 2 ? P.query_latent[((size_t)p * 2 + tid) * D + l] : P.q_mu[((size_t)p * M + tid - 2) * D + l];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < Mp * Mp; idx += blockDim.x) {
+    const int i = idx / Mp, j = idx % Mp;
+    const double k = s2 * vg_matern52(fabs(zy[i] - zy[j]) / ell) + (i == j ? jitter : 0.0);
+    Ksm[i * LDM + j] = k;
+    Lsm[i * LDM + j] = k;
+  }
+  chol_inplace(Lsm, Mp);
+  if (Lc_out != nullptr)
+    for (int idx = tid; idx < Mp * Mp; idx += blockDim.x)
+      Lc_out[(size_t)pl * Mp * Mp + idx] = Lsm[(idx / Mp) * LDM + idx % Mp];
+
+  // q_sqrt property: Lc @ pad(_q_sqrt) + jitter * diag(1,1,0,...)   models/vgpmp.py:208-218
+  const double* q = P.q_sqrt + (size_t)pl * M * M;
+  if (S_out != nullptr) {
+    for (int idx = tid; idx < Mp * Mp; idx += blockDim.x) {
+      const int i = idx / Mp, j = idx % Mp;
+      double acc = 0.0;
+      if (i >= 2 && j >= 2 && j <= i)
+        for (int k = j; k <= i; ++k) acc += Lsm[i * LDM + k] * q[(k - 2) * M + (j - 2)];
+      if (i == j && i < 2) acc += jitter;
+      S_out[(size_t)pl * Mp * Mp + idx] = acc;
+    }
+  }
+
+  // prior_kl: p_mu = K[:, :2] chol_solve(L[:2,:2], q~);  a = (L^-1 (mu - p_mu))[2:]   prior_kl.py:24-34
+  if (tid == 0) {
+    const double l00 = Lsm[0], l10 = Lsm[LDM], l11 = Lsm[LDM + 1];
+    const double y0 = mu[0] / l00, y1 = (mu[1] - l10 * y0) / l11;
+    const double c1 = y1 / l11, c0 = (y0 - l10 * c1) / l00;
+    cvec[0] = c0; cvec[1] = c1;
+  }
+  __syncthreads();
+  double part = 0.0;
+  if (tid < 32) {
+    double d = 0.0;
+    if (tid < Mp) d = mu[tid] - (Ksm[tid * LDM] * cvec[0] + Ksm[tid * LDM + 1] * cvec[1]);
+    const double b = warp_fwd_subst(Lsm, Mp, d);
+    if (kvec != nullptr) {
+      if (tid < Mp) kvec[(size_t)pl * (Mp + 4) + tid] = b;
+      if (tid < 2) kvec[(size_t)pl * (Mp + 4) + Mp + tid] = cvec[tid];
+    }
+    if (tid >= 2 && tid < Mp) part = b * b;  // mahalanobis of the whitened difference
+  }
+  // gauss_kl(white): 0.5 * (maha - M - sum log diag(q)^2 + sum q^2)
+  for (int idx = tid; idx < M * M; idx += blockDim.x) {
+    const int a = idx / M, c = idx % M;
+    if (c <= a) {
+      const double v = q[idx];
+      part += v * v;
+      if (a == c) part -= log(v * v);
+    }
+  }
+  const double tot = block_sum(part, red);
+  if (tid == 0 && kl_l != nullptr) kl_l[pl] = 0.5 * (tot - (double)M);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Random-Fourier prior draw + pathwise (Matheron) update, one CTA per (problem, latent).
+//   phase 1: f0[s,x] = sum_b phi_b(x) w[s,b],  h0 = d f0 / d lengthscale, x over the Nq query points then the Mp
+//            inducing points.  A warp owns 32 points and one slice of the bases; the cos/sin feature lives in a
+//            register and is consumed immediately by the kST sample accumulators (w is a warp-uniform load).
+//   phase 2: u = mu + S eps_u;  v = Khat^-1 (u - f0(Zy) - sqrt(jitter) eps_j);  f = f0(X) + Kfu v.
+// ---------------------------------------------------------------------------------------------
+struct PathwiseArgs {
+  int D, M, Nq, S, B, XG, KS;
+  double jitter;
+  const double *Z, *Xq, *ls, *var, *q_mu, *query_latent;
+  const double *omega, *tau, *w, *eps_u, *eps_j;
+  const double *Lc, *Sfull;
+  double *f, *v, *f0, *h0;
+};
+
+__global__ void __launch_bounds__(768) pathwise_kernel(PathwiseArgs a) {
+  extern __shared__ double sm[];
+  const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, B = a.B, A = Nq + Mp;
+  const int pl = blockIdx.x, p = pl / D, l = pl % D;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
+  const int XP = a.XG * 32;
+  // shared-memory carve-up
+  double* red = sm;                               // [KS][2][kST][XP]
+  double* Lsm = red + (size_t)a.KS * 2 * kST * XP;  // [Mp][LDM]
+  double* Ssm = Lsm + 32 * LDM;                   // [Mp][LDM]
+  double* Kfu = Ssm + 32 * LDM;                   // [Nq][Mp]
+  double* vs = Kfu + (size_t)Nq * Mp;             // [kST][32]
+  double* mu = vs + kST * 32;                     // [32]
+  double* zy = mu + 32;                           // [32]
+
+  const double ell = a.ls[pl], s2 = a.var[pl];
+  const double amp = sqrt(2.0 * s2 / (double)B);
+  const double sqrtj = sqrt(a.jitter);
+  if (tid < Mp) {
+    zy[tid] = zy_at(a.Z, D, l, tid);
+    mu[tid] = tid < 2 ? a.query_latent[((size_t)p * 2 + tid) * D + l] : a.q_mu[((size_t)p * M + tid - 2) * D + l];
+  }
+  for (int idx = tid; idx < Mp * Mp; idx += nt) {
+    const int i = idx / Mp, j = idx % Mp;
+    Lsm[i * LDM + j] = a.Lc[(size_t)pl * Mp * Mp + idx];
+    Ssm[i * LDM + j] = a.Sfull[(size_t)pl * Mp * Mp + idx];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < Nq * Mp; idx += nt) {
+    const int n = idx / Mp, m = idx % Mp;
+    Kfu[idx] = s2 * vg_matern52(fabs(a.Xq[(size_t)n * D + l] - zy[m]) / ell);
+  }
+
+  // this thread's point, scaled by 1/lengthscale (GPflow kernel.scale)
+  const int xg = warp % a.XG, ks = warp / a.XG;
+  const int x = xg * 32 + lane;
+  double pt[VGPMP_MAX_DOF];
+#pragma unroll
+  for (int d = 0; d < VGPMP_MAX_DOF; ++d) {
+    double v = 0.0;
+    if (d < D && x < A) {
+      if (x < Nq) v = a.Xq[(size_t)x * D + d];
+      else v = zy_at(a.Z, D, d, x - Nq);
+    }
+    pt[d] = v / ell;
+  }
+  const int Bs = (B + a.KS - 1) / a.KS;
+  const int b0 = ks * Bs, b1 = min(B, b0 + Bs);
+  const double* om = a.omega + (size_t)pl * B * D;
+  const double* ta = a.tau + (size_t)pl * B;
+  const double* wp = a.w + (size_t)pl * S * B;
+
+  for (int s0 = 0; s0 < S; s0 += kST) {
+    double acc0[kST], acc1[kST];
+#pragma unroll
+    for (int i = 0; i < kST; ++i) { acc0[i] = 0.0; acc1[i] = 0.0; }
+    const int ns = min(kST, S - s0);
+    if (ks < a.KS) {
+      for (int b = b0; b < b1; ++b) {
+        double pr = 0.0;
+#pragma unroll
+        for (int d = 0; d < VGPMP_MAX_DOF; ++d)
+          if (d < D) pr += pt[d] * __ldg(om + (size_t)b * D + d);
+        double sn, cs;
+        sincos(pr + __ldg(ta + b), &sn, &cs);
+        const double c = amp * cs, g = amp * sn * pr / ell;
+#pragma unroll
+        for (int i = 0; i < kST; ++i) {
+          if (i < ns) {
+            const double wv = __ldg(wp + (size_t)(s0 + i) * B + b);
+            acc0[i] += c * wv;
+            acc1[i] += g * wv;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kST; ++i) {
+        red[((size_t)(ks * 2 + 0) * kST + i) * XP + x] = acc0[i];
+        red[((size_t)(ks * 2 + 1) * kST + i) * XP + x] = acc1[i];
+      }
+    }
+    __syncthreads();
+    // reduce the base slices (fixed order) into slice 0 and publish f0 / h0
+    for (int idx = tid; idx < 2 * kST * XP; idx += nt) {
+      double t = red[idx];
+      for (int k = 1; k < a.KS; ++k) t += red[(size_t)k * 2 * kST * XP + idx];
+      red[idx] = t;
+      const int which = idx / (kST * XP), i = (idx / XP) % kST, xx = idx % XP;
+      if (i < ns && xx < A) {
+        double* dst = which == 0 ? a.f0 : a.h0;
+        if (dst != nullptr) dst[((size_t)pl * S + s0 + i) * A + xx] = t;
+      }
+    }
+    __syncthreads();
+    // pathwise update, one warp per sample of the tile
+    if (warp < ns) {
+      const int s = s0 + warp;
+      const double* eu = a.eps_u + ((size_t)pl * S + s) * Mp;
+      double r = 0.0;
+      if (lane < Mp) {
+        double u = mu[lane];
+        for (int k = 0; k <= lane; ++k) u += Ssm[lane * LDM + k] * eu[k];
+        r = u - red[(size_t)warp * XP + Nq + lane] - sqrtj * a.eps_j[((size_t)pl * S + s) * Mp + lane];
+      }
+      const double y = warp_fwd_subst(Lsm, Mp, r);
+      const double vv = warp_bwd_subst(Lsm, Mp, y);
+      vs[warp * 32 + lane] = lane < Mp ? vv : 0.0;
+      if (lane < Mp && a.v != nullptr) a.v[((size_t)pl * S + s) * Mp + lane] = vv;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < ns * Nq; idx += nt) {
+      const int i = idx / Nq, n = idx % Nq;
+      double fv = red[(size_t)i * XP + n];
+      for (int m = 0; m < Mp; ++m) fv += Kfu[n * Mp + m] * vs[i * 32 + m];
+      a.f[(((size_t)p * S + s0 + i) * Nq + n) * D + l] = fv;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reverse pass of the GP side, one CTA (256 threads) per (problem, latent).
+// ---------------------------------------------------------------------------------------------
+struct BackwardArgs {
+  int D, M, N, S, B;
+  double jitter;
+  const double *Z, *X, *ls, *var, *q_sqrt;
+  const double *eps_u;
+  const double *Lc, *kvec, *v, *f0, *h0, *df;
+  double *d_q_mu, *d_q_sqrt, *d_ls, *d_var;
+};
+
+constexpr int kBT = 8;  // samples per tile (= warps) in the reverse pass
+
+__global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
+  extern __shared__ double sm[];
+  const int D = a.D, M = a.M, Mp = M + 2, N = a.N, S = a.S, A = N + Mp;
+  const int pl = blockIdx.x, p = pl / D, l = pl % D;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
+  double* Lsm = sm;                    // [32][LDM] chol factor
+  double* G = Lsm + 32 * LDM;          // [32][LDM] d ELBO / d Khat (general, not symmetrised)
+  double* GS = G + 32 * LDM;           // [32][LDM] d ELBO / d q_sqrt_full
+  double* GL = GS + 32 * LDM;          // [32][LDM] d ELBO / d Lc
+  double* Kfu = GL + 32 * LDM;         // [N][Mp]
+  double* gv = Kfu + (size_t)N * Mp;   // [kBT][32]
+  double* gr = gv + kBT * 32;          // [kBT][32]
+  double* vsm = gr + kBT * 32;         // [kBT][32]
+  double* gmu = vsm + kBT * 32;        // [32]
+  double* zy = gmu + 32;               // [32]
+  double* bvec = zy + 32;              // [32]
+  double* gd = bvec + 32;              // [32]
+  double* red = gd + 32;               // [8]
+  double* misc = red + 8;              // [8]
+
+  const double ell = a.ls[pl], s2 = a.var[pl];
+  if (tid < 32) {
+    zy[tid] = tid < Mp ? zy_at(a.Z, D, l, tid) : 0.0;
+    bvec[tid] = tid < Mp ? a.kvec[(size_t)pl * (Mp + 4) + tid] : 0.0;
+    gmu[tid] = 0.0;
+  }
+  for (int idx = tid; idx < 32 * LDM; idx += nt) { G[idx] = 0.0; GS[idx] = 0.0; GL[idx] = 0.0; Lsm[idx] = 0.0; }
+  __syncthreads();
+  for (int idx = tid; idx < Mp * Mp; idx += nt) Lsm[(idx / Mp) * LDM + idx % Mp] = a.Lc[(size_t)pl * Mp * Mp + idx];
+  for (int idx = tid; idx < N * Mp; idx += nt) {
+    const int n = idx / Mp, m = idx % Mp;
+    Kfu[idx] = s2 * vg_matern52(fabs(a.X[(size_t)n * D + l] - zy[m]) / ell);
+  }
+  __syncthreads();
+
+  double acc_ls = 0.0, acc_var = 0.0;  // per-thread partial hyper-parameter gradients
+  const double* dfp = a.df + (size_t)p * S * N * D + l;  // df[s,n] at dfp[(s*N+n)*D]
+
+  for (int s0 = 0; s0 < S; s0 += kBT) {
+    const int ns = min(kBT, S - s0);
+    // (1) gv[s,m] = sum_n Kfu[n,m] df[s,n]   and stage v
+    for (int idx = tid; idx < kBT * 32; idx += nt) {
+      const int i = idx >> 5, m = idx & 31;
+      double t = 0.0, vv = 0.0;
+      if (i < ns && m < Mp) {
+        const double* dfs = dfp + (size_t)(s0 + i) * N * D;
+        for (int n = 0; n < N; ++n) t += Kfu[n * Mp + m] * dfs[(size_t)n * D];
+        vv = a.v[((size_t)pl * S + s0 + i) * Mp + m];
+      }
+      gv[idx] = t;
+      vsm[idx] = vv;
+    }
+    __syncthreads();
+    // (3) gr = Khat^-1 gv (warp per sample)
+    if (warp < kBT) {
+      const double y = warp_fwd_subst(Lsm, Mp, gv[warp * 32 + lane]);
+      const double z = warp_bwd_subst(Lsm, Mp, y);
+      gr[warp * 32 + lane] = (warp < ns && lane < Mp) ? z : 0.0;
+    }
+    __syncthreads();
+    // (2) Kfu path to the hyper-parameters: sum_{s} df[s,n] v[s,m] dKfu[n,m]/dtheta
+    for (int idx = tid; idx < N * Mp; idx += nt) {
+      const int n = idx / Mp, m = idx % Mp;
+      double t = 0.0;
+      for (int i = 0; i < ns; ++i) t += dfp[((size_t)(s0 + i) * N + n) * D] * vsm[i * 32 + m];
+      const double r = fabs(a.X[(size_t)n * D + l] - zy[m]) / ell;
+      acc_var += t * vg_matern52(r);
+      acc_ls += t * s2 * vg_matern52_dr(r) * (-r / ell);
+    }
+    // (4) G -= gr v^T ; (6) GS += gr eps_u^T ; gmu += gr
+    for (int idx = tid; idx < Mp * Mp; idx += nt) {
+      const int i = idx / Mp, j = idx % Mp;
+      double t = 0.0, u = 0.0;
+      for (int k = 0; k < ns; ++k) {
+        const double g = gr[k * 32 + i];
+        t += g * vsm[k * 32 + j];
+        u += g * a.eps_u[((size_t)pl * S + s0 + k) * Mp + j];
+      }
+      G[i * LDM + j] -= t;
+      GS[i * LDM + j] += u;
+    }
+    if (tid < Mp) {
+      double t = 0.0;
+      for (int k = 0; k < ns; ++k) t += gr[k * 32 + tid];
+      gmu[tid] += t;
+    }
+    // (5) prior path: d f0(X) = df, d f0(Zy) = -gr
+    for (int idx = tid; idx < ns * A; idx += nt) {
+      const int i = idx / A, xx = idx % A;
+      const double g = xx < N ? dfp[((size_t)(s0 + i) * N + xx) * D] : -gr[i * 32 + xx - N];
+      const size_t o = ((size_t)pl * S + s0 + i) * A + xx;
+      acc_var += g * a.f0[o] / (2.0 * s2);
+      acc_ls += g * a.h0[o];
+    }
+    __syncthreads();
+  }
+
+  // (7) q_sqrt_full = Lc pad(q) + jitter diag  ->  d q = tril((Lc^T GS)[2:,2:]),  GL += GS pad(q)^T
+  const double* q = a.q_sqrt + (size_t)pl * M * M;
+  double* dq = a.d_q_sqrt + (size_t)pl * M * M;
+  for (int idx = tid; idx < M * M; idx += nt) {
+    const int r_ = idx / M, c_ = idx % M;
+    double t = 0.0;
+    if (c_ <= r_) {
+      for (int i = r_ + 2; i < Mp; ++i) t += Lsm[i * LDM + r_ + 2] * GS[i * LDM + c_ + 2];
+      const double qv = q[idx];
+      t -= qv - (r_ == c_ ? 1.0 / qv : 0.0);  // - d KL / d q_sqrt
+    }
+    dq[idx] = t;
+  }
+  for (int idx = tid; idx < Mp * Mp; idx += nt) {
+    const int i = idx / Mp, k = idx % Mp;
+    if (k >= 2 && k <= i) {
+      double t = 0.0;
+      for (int j = 2; j <= k; ++j) t += GS[i * LDM + j] * q[(k - 2) * M + (j - 2)];
+      GL[i * LDM + k] += t;
+    }
+  }
+  __syncthreads();
+  // (8) KL reverse: b = L^-1 d, KL = 0.5 sum_{i>=2} b_i^2 + ...;  ELBO carries -KL
+  if (warp == 0) {
+    const double gb = (lane >= 2 && lane < Mp) ? -bvec[lane] : 0.0;
+    const double g = warp_bwd_subst(Lsm, Mp, gb);  // d ELBO / d d
+    gd[lane] = lane < Mp ? g : 0.0;
+  }
+  __syncthreads();
+  const double c0 = a.kvec[(size_t)pl * (Mp + 4) + Mp], c1 = a.kvec[(size_t)pl * (Mp + 4) + Mp + 1];
+  for (int idx = tid; idx < Mp * Mp; idx += nt) {
+    const int i = idx / Mp, j = idx % Mp;
+    if (j <= i) GL[i * LDM + j] -= gd[i] * bvec[j];
+  }
+  if (tid < Mp) {
+    gmu[tid] += gd[tid];
+    // p_mu = Khat[:, :2] c  ->  d Khat[i, 0:2] += (-gd_i) c
+    G[tid * LDM + 0] -= gd[tid] * c0;
+    G[tid * LDM + 1] -= gd[tid] * c1;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // gc = Khat[:, :2]^T (-gd);  c = K22^-1 q~  ->  d K22 -= (K22^-1 gc) c^T
+    double gc0 = 0.0, gc1 = 0.0;
+    for (int i = 0; i < Mp; ++i) {
+      const double k0 = s2 * vg_matern52(fabs(zy[i] - zy[0]) / ell) + (i == 0 ? a.jitter : 0.0);
+      const double k1 = s2 * vg_matern52(fabs(zy[i] - zy[1]) / ell) + (i == 1 ? a.jitter : 0.0);
+      gc0 -= k0 * gd[i];
+      gc1 -= k1 * gd[i];
+    }
+    const double l00 = Lsm[0], l10 = Lsm[LDM], l11 = Lsm[LDM + 1];
+    const double y0 = gc0 / l00, y1 = (gc1 - l10 * y0) / l11;
+    const double e1 = y1 / l11, e0 = (y0 - l10 * e1) / l00;
+    G[0] -= e0 * c0;       G[1] -= e0 * c1;
+    G[LDM] -= e1 * c0;     G[LDM + 1] -= e1 * c1;
+  }
+  __syncthreads();
+  // (9) Cholesky reverse (Murray 2016): Khat_bar = L^-T Phi(L^T L_bar) L^-1, Phi = tril with halved diagonal
+  double* Pm = GS;  // reuse
+  __syncthreads();
+  for (int idx = tid; idx < Mp * Mp; idx += nt) {
+    const int i = idx / Mp, j = idx % Mp;
+    double t = 0.0;
+    if (j <= i) {
+      for (int k = i; k < Mp; ++k) t += Lsm[k * LDM + i] * GL[k * LDM + j];
+      if (i == j) t *= 0.5;
+    }
+    Pm[i * LDM + j] = t;
+  }
+  __syncthreads();
+  // Y = L^-T P (column by column), stored back in Pm
+  for (int col = warp; col < Mp; col += (nt >> 5)) {
+    const double y = warp_bwd_subst(Lsm, Mp, lane < Mp ? Pm[lane * LDM + col] : 0.0);
+    __syncwarp();
+    if (lane < Mp) Pm[lane * LDM + col] = y;
+  }
+  __syncthreads();
+  // Khat_bar = Y L^-1  <=>  rows: solve L^T w = Y[row,:]^T
+  for (int row = warp; row < Mp; row += (nt >> 5)) {
+    const double wv = warp_bwd_subst(Lsm, Mp, lane < Mp ? Pm[row * LDM + lane] : 0.0);
+    if (lane < Mp) G[row * LDM + lane] += wv;
+  }
+  __syncthreads();
+  // (10) contract with d Khat / d theta
+  for (int idx = tid; idx < Mp * Mp; idx += nt) {
+    const int i = idx / Mp, j = idx % Mp;
+    const double r = fabs(zy[i] - zy[j]) / ell;
+    const double g = G[i * LDM + j];
+    acc_var += g * vg_matern52(r);
+    acc_ls += g * s2 * vg_matern52_dr(r) * (-r / ell);
+  }
+  const double tv = block_sum(acc_var, red);
+  const double tl = block_sum(acc_ls, red);
+  if (tid == 0) {
+    a.d_var[pl] = tv;
+    a.d_ls[pl] = tl;
+  }
+  if (tid >= 2 && tid < Mp) a.d_q_mu[((size_t)p * M + tid - 2) * D + l] = gmu[tid];
+  (void)misc;
+}
+
+// ELBO[p] = alpha/S * sum_{s,n} logp - sum_l KL_l      models/vgpmp.py:287-289
+__global__ void __launch_bounds__(256) elbo_reduce_kernel(int D, int SN, double scale, const double* __restrict__ logp,
+                                                         const double* __restrict__ kl_l, double* __restrict__ elbo,
+                                                         double* __restrict__ kl_out) {
+  __shared__ double red[8];
+  const int p = blockIdx.x;
+  double t = 0.0;
+  for (int i = threadIdx.x; i < SN; i += blockDim.x) t += logp[(size_t)p * SN + i];
+  const double lik = block_sum(t, red);
+  if (threadIdx.x == 0) {
+    double kl = 0.0;
+    for (int l = 0; l < D; ++l) kl += kl_l[(size_t)p * D + l];
+    elbo[p] = scale * lik - kl;
+    if (kl_out != nullptr) kl_out[p] = kl;
+  }
+}
+
+// Keras Adam on the unconstrained variables, loss = -ELBO.
+__device__ __forceinline__ double softplus_d(double x) { return x > 30.0 ? x : log1p(exp(x)); }
+
+__global__ void adam_kernel(int D, int M, int Bp, vgpmp_adam st, vgpmp_grads g, double lr_t) {
+  const int per = M * D + D * M * M + 2 * D;
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (size_t)Bp * per) return;
+  const int p = (int)(gid / per), e = (int)(gid % per);
+  double grad, *var_ptr;
+  int kind;  // 0 q_mu, 1 q_sqrt, 2 ls, 3 var
+  int local;
+  if (e < M * D) { kind = 0; local = e; }
+  else if (e < M * D + D * M * M) { kind = 1; local = e - M * D; }
+  else if (e < M * D + D * M * M + D) { kind = 2; local = e - M * D - D * M * M; }
+  else { kind = 3; local = e - M * D - D * M * M - D; }
+  bool train;
+  if (kind == 0) { train = st.train_q_mu; var_ptr = st.q_mu + (size_t)p * M * D + local; grad = g.d_q_mu[(size_t)p * M * D + local]; }
+  else if (kind == 1) {
+    const int rc = local % (M * M);
+    train = st.train_q_sqrt && (rc % M) <= (rc / M);
+    var_ptr = st.q_sqrt + (size_t)p * D * M * M + local; grad = g.d_q_sqrt[(size_t)p * D * M * M + local];
+  } else if (kind == 2) {
+    train = st.train_lengthscales; var_ptr = st.raw_lengthscales + (size_t)p * D + local;
+    grad = g.d_lengthscales[(size_t)p * D + local];
+  } else {
+    train = st.train_variances; var_ptr = st.raw_variances + (size_t)p * D + local;
+    grad = g.d_variances[(size_t)p * D + local];
+  }
+  if (!train) return;
+  double x = *var_ptr;
+  if (kind >= 2) grad *= 1.0 / (1.0 + exp(-x));  // d softplus / d raw
+  grad = -grad;                                   // minimise -ELBO
+  double m = st.m[gid], v = st.v[gid];
+  m += (grad - m) * (1.0 - st.beta1);
+  v += (grad * grad - v) * (1.0 - st.beta2);
+  st.m[gid] = m;
+  st.v[gid] = v;
+  x -= lr_t * m / (sqrt(v) + st.eps);
+  *var_ptr = x;
+  if (kind == 2) st.lengthscales[(size_t)p * D + local] = softplus_d(x);
+  if (kind == 3) st.variances[(size_t)p * D + local] = st.variance_lower + softplus_d(x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 draw generator: element-wise counters, so any launch shape / any GPU produces the same draw for the
+// same (seed, iteration, stream, problem, latent, row, column).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    c[1] = (uint32_t)p1; c[3] = (uint32_t)p0; c[0] = n0; c[2] = n2;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {  // (0,1), 53 bits
+  const uint64_t x = ((uint64_t)hi << 32 | lo) >> 11;
+  return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
+}
+// two independent N(0,1) from one Philox block
+__device__ __forceinline__ void normal2(uint64_t seed, uint64_t iter, uint32_t stream, uint64_t idx, double& z0, double& z1) {
+  uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)iter, stream ^ ((uint32_t)(iter >> 32) << 8)};
+  philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const double r = sqrt(-2.0 * log(u01(c[0], c[1])));
+  double sn, cs;
+  sincospi(2.0 * u01(c[2], c[3]), &sn, &cs);
+  z0 = r * cs; z1 = r * sn;
+}
+
+struct RngArgs {
+  int D, B, S, Mp, Bp;
+  int64_t problem_offset, sample_offset;
+  uint64_t seed, iteration;
+  double *omega, *tau, *w, *eps_u, *eps_j;
+};
+
+__global__ void rng_fill_kernel(RngArgs a) {
+  const size_t n_om = (size_t)a.Bp * a.D * a.B;            // one thread per basis row (gamma shared by the row)
+  const size_t n_w = (size_t)a.Bp * a.D * a.S * a.B;
+  const size_t n_e = (size_t)a.Bp * a.D * a.S * a.Mp;
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid < n_om) {
+    if (a.omega == nullptr) return;
+    const size_t b = gid % a.B, l = (gid / a.B) % a.D, p = gid / ((size_t)a.B * a.D) + a.problem_offset;
+    const uint64_t key = (p * a.D + l) * a.B + b;
+    // Gamma(5/2, rate 5/2) = chi^2_5 / 5  -> omega = z / sqrt(gamma): Matern-5/2 spectral density (Student-t_5)
+    double g[6];
+    normal2(a.seed, a.iteration, 1u, key * 3 + 0, g[0], g[1]);
+    normal2(a.seed, a.iteration, 1u, key * 3 + 1, g[2], g[3]);
+    normal2(a.seed, a.iteration, 1u, key * 3 + 2, g[4], g[5]);
+    const double gam = (g[0] * g[0] + g[1] * g[1] + g[2] * g[2] + g[3] * g[3] + g[4] * g[4]) / 5.0;
+    const double rs = rsqrt(gam);
+    for (int d = 0; d < a.D; d += 2) {
+      double z0, z1;
+      normal2(a.seed, a.iteration, 2u, key * 4 + d / 2, z0, z1);
+      a.omega[gid * a.D + d] = z0 * rs;
+      if (d + 1 < a.D) a.omega[gid * a.D + d + 1] = z1 * rs;
+    }
+    uint32_t c[4] = {(uint32_t)key, (uint32_t)(key >> 32), (uint32_t)a.iteration, 3u};
+    philox4x32(c, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    a.tau[gid] = 6.283185307179586476925 * u01(c[0], c[1]);
+    return;
+  }
+  size_t e = gid - n_om;
+  if (e < n_w) {
+    if (a.w == nullptr) return;
+    const size_t b = e % a.B, s = (e / a.B) % a.S + a.sample_offset, l = (e / ((size_t)a.B * a.S)) % a.D;
+    const size_t p = e / ((size_t)a.B * a.S * a.D) + a.problem_offset;
+    const uint64_t key = ((p * a.D + l) * (uint64_t)(1u << 24) + s) * a.B + b;  // sample index < 2^24
+    double z0, z1;
+    normal2(a.seed, a.iteration, 4u, key, z0, z1);
+    a.w[e] = z0;
+    return;
+  }
+  e -= n_w;
+  if (e < n_e) {
+    if (a.eps_u == nullptr) return;
+    const size_t m = e % a.Mp, s = (e / a.Mp) % a.S + a.sample_offset, l = (e / ((size_t)a.Mp * a.S)) % a.D;
+    const size_t p = e / ((size_t)a.Mp * a.S * a.D) + a.problem_offset;
+    const uint64_t key = ((p * a.D + l) * (uint64_t)(1u << 24) + s) * 32 + m;
+    double z0, z1;
+    normal2(a.seed, a.iteration, 5u, key, z0, z1);
+    a.eps_u[e] = z0;
+    a.eps_j[e] = z1;
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_kuu(vgpmp_handle* h, const double* Z, const double* ls, const double* var, double jitter, double* K,
+                       int Bp, int M, cudaStream_t s) {
+  kuu_kernel<<<Bp * h->robot.dof, 128, 0, s>>>(h->robot.dof, M, jitter, Z, ls, var, K);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_kuf(vgpmp_handle* h, const double* Z, const double* X, const double* ls, const double* var,
+                       double* Kuf, int Bp, int M, int N, cudaStream_t s) {
+  kuf_kernel<<<Bp * h->robot.dof, 128, 0, s>>>(h->robot.dof, M, N, Z, X, ls, var, Kuf);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gp_prepare(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, double* Lc, double* Sfull,
+                              double* kl_l, double* kvec, cudaStream_t s) {
+  gp_prepare_kernel<<<d.num_problems * h->robot.dof, 128, 0, s>>>(h->robot.dof, d.num_inducing, h->lik.jitter, p, Lc,
+                                                                  Sfull, kl_l, kvec);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
+                            const double* Xq, int Nq, const double* Lc, const double* Sfull, double* f, double* v,
+                            double* f0, double* h0, cudaStream_t s) {
+  PathwiseArgs a;
+  a.D = h->robot.dof; a.M = d.num_inducing; a.Nq = Nq; a.S = d.num_samples; a.B = d.num_bases;
+  const int Mp = a.M + 2, A = Nq + Mp;
+  a.XG = (A + 31) / 32;
+  if (a.XG > 24) return cudaErrorInvalidValue;
+  a.KS = 24 / a.XG;
+  if (a.KS > a.B) a.KS = a.B;
+  a.jitter = h->lik.jitter;
+  a.Z = p.Z; a.Xq = Xq; a.ls = p.lengthscales; a.var = p.variances; a.q_mu = p.q_mu; a.query_latent = p.query_latent;
+  a.omega = r.omega; a.tau = r.tau; a.w = r.w; a.eps_u = r.eps_u; a.eps_j = r.eps_j;
+  a.Lc = Lc; a.Sfull = Sfull; a.f = f; a.v = v; a.f0 = f0; a.h0 = h0;
+  const int threads = 32 * a.XG * a.KS;
+  const size_t smem = sizeof(double) * ((size_t)a.KS * 2 * kST * a.XG * 32 + 2 * 32 * LDM + (size_t)Nq * Mp + kST * 32 + 64);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(pathwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  pathwise_kernel<<<d.num_problems * a.D, threads, smem, s>>>(a);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
+                               const GpScratch& ws, const vgpmp_grads& g, cudaStream_t s) {
+  BackwardArgs a;
+  a.D = h->robot.dof; a.M = d.num_inducing; a.N = d.num_timesteps; a.S = d.num_samples; a.B = d.num_bases;
+  a.jitter = h->lik.jitter;
+  a.Z = p.Z; a.X = p.X; a.ls = p.lengthscales; a.var = p.variances; a.q_sqrt = p.q_sqrt;
+  a.eps_u = r.eps_u;
+  a.Lc = ws.Lc; a.kvec = ws.kvec; a.v = ws.v; a.f0 = ws.f0; a.h0 = ws.h0; a.df = ws.df;
+  a.d_q_mu = g.d_q_mu; a.d_q_sqrt = g.d_q_sqrt; a.d_ls = g.d_lengthscales; a.d_var = g.d_variances;
+  const int Mp = a.M + 2;
+  const size_t smem = sizeof(double) * (4 * 32 * LDM + (size_t)a.N * Mp + 3 * kBT * 32 + 4 * 32 + 16);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(gp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  gp_backward_kernel<<<d.num_problems * a.D, 256, smem, s>>>(a);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_elbo_reduce(vgpmp_handle* h, const vgpmp_dims& d, const double* logp, const double* kl_l,
+                               double* elbo, double* kl_out, cudaStream_t s) {
+  elbo_reduce_kernel<<<d.num_problems, 256, 0, s>>>(h->robot.dof, d.num_samples * d.num_timesteps,
+                                                     h->lik.alpha / (double)d.num_samples, logp, kl_l, elbo, kl_out);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adam(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_adam& st, const vgpmp_grads& g, cudaStream_t s) {
+  const int D = h->robot.dof, M = d.num_inducing;
+  const size_t total = (size_t)d.num_problems * (M * D + D * M * M + 2 * D);
+  const int t = st.step + 1;
+  const double lr_t = st.learning_rate * sqrt(1.0 - pow(st.beta2, t)) / (1.0 - pow(st.beta1, t));
+  adam_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(D, M, d.num_problems, st, g, lr_t);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rng_fill(vgpmp_handle* h, const vgpmp_dims& d, uint64_t seed, uint64_t iteration,
+                            int64_t problem_offset, int64_t sample_offset, double* omega, double* tau, double* w,
+                            double* eps_u, double* eps_j, cudaStream_t s) {
+  RngArgs a;
+  a.D = h->robot.dof; a.B = d.num_bases; a.S = d.num_samples; a.Mp = d.num_inducing + 2; a.Bp = d.num_problems;
+  a.problem_offset = problem_offset; a.sample_offset = sample_offset; a.seed = seed; a.iteration = iteration;
+  a.omega = omega; a.tau = tau; a.w = w; a.eps_u = eps_u; a.eps_j = eps_j;
+  const size_t n_om = (size_t)a.Bp * a.D * a.B, n_w = (size_t)a.Bp * a.D * a.S * a.B, n_e = (size_t)a.Bp * a.D * a.S * a.Mp;
+  const size_t total = n_om + n_w + n_e;
+  rng_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a);
+  h->launches++;
+  return cudaGetLastError();
+}
