@@ -1,0 +1,311 @@
+"""GPU parity tests: every stage kernel and the fused iteration, through the C-ABI, against the float64 oracle on
+identical seeded inputs, plus the reference-derived golden fixtures.  Tolerances are BASELINE.json's north_star:
+FK poses / SDF values 1e-5 rel, ELBO 1e-4 rel, gradients 1e-3 rel (the float64 kernels land far inside them)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vgpmp_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+ROBOTS = ["franka", "kuka", "wam", "ur10"]
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------ FK
+@pytest.mark.parametrize("name", ROBOTS)
+def test_fk_frames_golden_and_oracle(name, golden_dir):
+    from vgpmp_b200.utils.robot import Robot
+    from vgpmp_b200.utils.sampler import Sampler
+    g = np.load(golden_dir / f"fk_{name}.npz")
+    s = Sampler(None, Robot.from_tables(name, "bookshelves"))
+    frames = _np(s.forward_kinematics(g["thetas"]))
+    assert frames.shape == g["frames"].shape
+    assert np.allclose(frames, g["frames"], rtol=0, atol=1e-13)          # reference RobotMixin.forward_kinematics
+    single = _np(s.forward_kinematics(g["thetas"][1].reshape(-1, 1)))   # the [D,1] call shape of the reference
+    assert single.shape == (s.dof + 1, 4, 4) and np.allclose(single, g["frames"][1], atol=1e-13)
+
+
+@pytest.mark.parametrize("name", ROBOTS)
+def test_fk_spheres_vs_oracle(name):
+    from vgpmp_b200.utils.robot import Robot
+    from vgpmp_b200.utils.sampler import Sampler
+    rob = H.oracle_robot(name)
+    rng = np.random.default_rng(11)
+    th = rob.limits_lo + (rob.limits_hi - rob.limits_lo) * rng.uniform(size=(257, rob.dof))   # ragged vs the 128-thread CTA
+    s = Sampler(None, Robot.from_tables(name, "bookshelves"))
+    got = _np(s.forward_kinematics_cost(th))
+    want = np.stack([O.sphere_positions_np(rob, t) for t in th])
+    assert H.rel_err(got, want) < 1e-12
+    one = _np(s.forward_kinematics_cost(th[0].reshape(-1, 1)))
+    assert one.shape == (rob.num_spheres, 3)
+
+
+def test_fk_empty_batch():
+    from vgpmp_b200.utils.robot import Robot
+    from vgpmp_b200.utils.sampler import Sampler
+    s = Sampler(None, Robot.from_tables("franka"))
+    assert s._eng().fk_spheres(np.zeros((0, 7))).shape == (0, 37, 3)
+
+
+# ------------------------------------------------------------------------------------------------ SDF
+def test_sdf_lookup_golden(golden_dir):
+    from vgpmp_b200.utils.sdf_utils import SignedDistanceField
+    g = np.load(golden_dir / "sdf_small.npz")
+    sdf = SignedDistanceField.from_sdf(golden_dir / "sdf_small.sdf")
+    dist = _np(sdf.get_distance_tf(g["points"]))
+    grad = _np(sdf.get_distance_grad_tf(g["points"]))
+    assert np.array_equal(dist, g["dist"])                                  # bit-exact gather (reference NumPy path)
+    want = np.where(g["grad"] == 0, 0.1, g["grad"])                       # + the TF-only zero rule
+    assert np.array_equal(grad, want)
+    assert (g["grad"] == 0).sum() > 0
+
+
+def test_sdf_lookup_large_random_vs_oracle():
+    sdf = H.small_sdf(seed=3)
+    osdf = O.OracleSDF(sdf.data, sdf.origin, sdf.delta)
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(-1.3, 1.3, size=(100_003, 3))       # a good share outside the grid: clipping on every face
+    pts[:3] = [[1e9, -1e9, 0.0], [np.nextafter(sdf.origin[0], 1), 0, 0], sdf.origin]
+    assert np.array_equal(_np(sdf.get_distance_tf(pts)), osdf.distance(pts))
+    assert np.array_equal(_np(sdf.get_distance_grad_tf(pts)), osdf.distance_grad(pts))
+
+
+# ------------------------------------------------------------------------------------------------ likelihood
+@pytest.mark.parametrize("name,env", [("franka", "bookshelves"), ("kuka", "industrial"), ("wam", "industrial"),
+                                      ("ur10", "bookshelves")])
+def test_loglik_forward_and_reverse_vs_oracle(name, env):
+    case = H.make_case(name, env, num_problems=1, S=5, N=33, M=6, B=8, seed=2)
+    model = H.make_model(case)
+    p = case["oracle"][0]
+    rng = np.random.default_rng(9)
+    f = 0.8 * rng.standard_normal((5, 33, case["D"]))
+    ft = torch.tensor(f, dtype=torch.float64, requires_grad=True)
+    lp = p.log_prob(p.joint_sigmoid(ft))
+    (0.37 * lp.sum()).backward()
+    logp, df = model.likelihood.log_prob_and_grad(f, squash=True, upstream=0.37)
+    assert np.abs(lp.detach().numpy()).max() > 0, "test input never touches the hinge"
+    assert H.rel_err(_np(logp), lp.detach().numpy()) < 1e-10
+    assert H.rel_err(_np(df), ft.grad.numpy()) < 1e-9
+    # joint-space entry point = likelihood.log_prob(F) of the reference
+    g = p.joint_sigmoid(torch.tensor(f)).numpy()
+    assert H.rel_err(_np(model.likelihood.log_prob(g)), lp.detach().numpy()) < 1e-10
+
+
+def test_likelihood_helper_api():
+    case = H.make_case(num_problems=1, S=2, N=9, M=5, B=8)
+    model = H.make_model(case)
+    lik, p = model.likelihood, case["oracle"][0]
+    g = p.joint_sigmoid(torch.tensor(0.5 * np.random.default_rng(0).standard_normal((2, 9, 7))))
+    pts = lik._sample_config_cost(g.numpy())
+    want = O.sphere_positions_torch(p.robot, g).numpy()
+    assert H.rel_err(_np(pts), want) < 1e-12
+    assert H.rel_err(_np(lik._scalar_log_prob(pts)), p.log_prob(g).numpy()) < 1e-10
+
+
+# ------------------------------------------------------------------------------------------------ GP pieces
+def test_kuu_kuf_kconditioned_vs_oracle():
+    from vgpmp_b200.covariances import Kfu, Kuf, Kuu
+    from vgpmp_b200.kernel_conditioning import K_conditioned
+    case = H.make_case(num_problems=1, S=2, N=21, M=24, B=8)
+    model = H.make_model(case)
+    p = case["oracle"][0]
+    ls, var = O._t(case["ls"][0]), O._t(case["var"][0])
+    want_uu = O.kuu(O._t(p.Zy), ls, var, 1e-6).numpy()
+    assert H.rel_err(_np(Kuu(model.inducing_variable, model.kernel, jitter=1e-6)), want_uu) < 1e-14
+    want_uf = O.k_conditioned(O._t(p.Zy), O._t(p.X), ls, var).numpy()
+    assert H.rel_err(_np(Kuf(model.inducing_variable, model.kernel, p.X)), want_uf) < 1e-14
+    assert _np(Kfu(model.inducing_variable, model.kernel, p.X)).shape == (7, 21, 26)
+    assert H.rel_err(_np(K_conditioned(p.Zy, p.X, model.kernel)), want_uf) < 1e-14
+
+
+@pytest.mark.parametrize("M", [1, 7, 24, 30])
+def test_gp_prepare_chol_qsqrt_kl_vs_oracle(M):
+    from vgpmp_b200.kullback_leiblers import prior_kl
+    case = H.make_case(num_problems=3, S=2, N=5, M=M, B=8, seed=M)
+    model = H.make_model(case)
+    eng = model._eng
+    Lc, Sfull, kl = eng.gp_prepare(model._dims(1), model._params(None))
+    for b, p in enumerate(case["oracle"]):
+        ls, var = O._t(case["ls"][b]), O._t(case["var"][b])
+        Lo = torch.linalg.cholesky(O.kuu(O._t(p.Zy), ls, var, O.JITTER)).numpy()
+        assert H.rel_err(_np(Lc[b]), Lo) < 1e-8            # cond(Khat) ~ 1e7: rounding differs from LAPACK at this level
+        So = p.q_sqrt_full(O._t(case["q_sqrt"][b]), ls, var).numpy()
+        assert H.rel_err(_np(Sfull[b]), So) < 1e-8
+        klo = float(p.prior_kl(O._t(case["q_mu"][b]), O._t(case["q_sqrt"][b]), ls, var))
+        assert abs(float(kl[b]) - klo) <= 1e-7 * abs(klo)
+    assert H.rel_err(_np(model.q_sqrt), _np(Sfull)) == 0.0
+    # dispatcher-style entry point on problem 0
+    klo = float(case["oracle"][0].prior_kl(O._t(case["q_mu"][0]), O._t(case["q_sqrt"][0]), O._t(case["ls"][0]),
+                                           O._t(case["var"][0])))
+    from vgpmp_b200.kernels import Matern52, VanillaConditioningSeparateIndependent
+    kern = VanillaConditioningSeparateIndependent([Matern52(variance=v, lengthscales=l)
+                                                   for l, v in zip(case["ls"][0], case["var"][0])])
+    got = float(prior_kl(model.inducing_variable, kern, case["q_mu"][0], case["q_sqrt"][0],
+                         _np(model._query_states[0])))
+    assert abs(got - klo) <= 1e-7 * abs(klo)
+
+
+@pytest.mark.parametrize("S,N,M,B", [(7, 70, 24, 64), (3, 5, 1, 3), (20, 50, 7, 40), (9, 150, 12, 33)])
+def test_pathwise_sample_vs_oracle(S, N, M, B):
+    case = H.make_case(num_problems=2, S=S, N=N, M=M, B=B, seed=S + N)
+    model = H.make_model(case)
+    f = _np(model.predict_f_samples(case["X"], draws=case["draws_stacked"]))
+    for b, p in enumerate(case["oracle"]):
+        want = p.sample_paths(p.X, O._t(case["q_mu"][b]), O._t(case["q_sqrt"][b]), O._t(case["ls"][b]),
+                              O._t(case["var"][b]), case["draws"][b]).numpy()
+        assert f[b].shape == want.shape == (S, N, 7)
+        assert H.rel_err(f[b], want) < 1e-7     # Khat^-1 amplifies rounding by ~cond; still 100x inside the 1e-5 budget
+
+
+# ------------------------------------------------------------------------------------------------ fused iteration
+@pytest.mark.parametrize("name,env,kw", [
+    ("franka", "bookshelves", dict(B=1024)),                      # BASELINE config 2 shapes: S=7, N=70, M=24, B=1024
+    ("wam", "industrial", dict(B=128)),                           # config 1 shapes
+    ("kuka", "industrial", dict(B=96)),                           # config 3 shapes: S=20, N=50, M=7
+    ("ur10", "bookshelves", dict(B=64, S=33)),                    # config 4 robot (D=6), more samples than one tile
+])
+def test_elbo_and_gradients_vs_oracle(name, env, kw):
+    case = H.make_case(name, env, num_problems=2, seed=4, **kw)
+    model = H.make_model(case)
+    out = model.elbo_and_grads(case["X"], draws=case["draws_stacked"], want_aux=True)
+    for b, p in enumerate(case["oracle"]):
+        ref = O.elbo_and_grads(p, case["q_mu"][b], case["q_sqrt"][b], case["ls"][b], case["var"][b], case["draws"][b])
+        assert H.rel_err(_np(out["f"][b]), ref["f"]) < 1e-7
+        flips = int((np.abs(_np(out["logp"][b]) - ref["logp"]) > 1e-6 * np.abs(ref["logp"]).max()).sum())
+        assert flips == 0, f"{flips} (sample,timestep) cells landed in a different voxel than the oracle"
+        assert abs(float(out["kl"][b]) - ref["kl"]) <= 1e-7 * abs(ref["kl"])
+        assert abs(float(out["elbo"][b]) - ref["elbo"]) <= 1e-4 * abs(ref["elbo"])      # north_star tolerance
+        assert abs(float(out["elbo"][b]) - ref["elbo"]) <= 1e-8 * abs(ref["elbo"])      # what float64 actually gives
+        for key in ("q_mu", "q_sqrt", "lengthscales", "variances"):
+            got, want = _np(out["d_" + key][b]), ref["d_" + key]
+            assert got.shape == want.shape
+            assert H.rel_err(got, want) < 1e-3, key                                      # north_star tolerance
+            assert H.rel_err(got, want) < 1e-5, key
+    # forward-only entry point returns the same ELBO
+    e2 = model.elbo(case["X"], draws=case["draws_stacked"])
+    assert torch.equal(e2, out["elbo"])
+
+
+def test_single_problem_api_shapes():
+    case = H.make_case(num_problems=1, S=4, N=12, M=6, B=16)
+    model = H.make_model(case)
+    assert model.q_mu.shape == (8, 7) and model.q_sqrt.shape == (7, 8, 8) and model.query_states.shape == (2, 7)
+    e = model.elbo(case["X"], draws=case["draws_stacked"])
+    assert e.ndim == 0
+    ref = O.elbo_and_grads(case["oracle"][0], case["q_mu"][0], case["q_sqrt"][0], case["ls"][0], case["var"][0],
+                           case["draws"][0])
+    assert abs(float(e) - ref["elbo"]) <= 1e-8 * abs(ref["elbo"])
+    assert float(model.training_loss_closure(case["X"])()) != 0.0
+
+
+def test_adam_training_steps_vs_oracle():
+    """Three optimisation steps with explicit draws: parameters after each step track the oracle's Keras-Adam."""
+    case = H.make_case(num_problems=2, S=5, N=20, M=8, B=32, seed=8)
+    model = H.make_model(case)
+    lr = case["pp"]["learning_rate"]
+    rng = np.random.default_rng(77)
+    states = [O.AdamState() for _ in case["oracle"]]
+    params = [dict(q_mu=case["q_mu"][b].copy(), q_sqrt=case["q_sqrt"][b].copy(),
+                   raw_ls=O.softplus_inv(case["ls"][b]), raw_var=O.softplus_inv(case["var"][b])) for b in range(2)]
+    tril = np.tril(np.ones((8, 8)))
+    for step in range(3):
+        draws = [O.make_draws(rng, 7, 5, 32, 10) for _ in range(2)]
+        stacked = {k: np.stack([d[k] for d in draws]) for k in draws[0]}
+        loss = _np(model.train_step(case["X"], draws=stacked))
+        for b, p in enumerate(case["oracle"]):
+            pr = params[b]
+            ls, var = O.softplus(pr["raw_ls"]), O.softplus(pr["raw_var"])
+            ref = O.elbo_and_grads(p, pr["q_mu"], pr["q_sqrt"], ls, var, draws[b])
+            assert abs(loss[b] + ref["elbo"]) <= 1e-7 * abs(ref["elbo"])
+            sig = lambda x: 1.0 / (1.0 + np.exp(-x))
+            grads = dict(q_mu=-ref["d_q_mu"], q_sqrt=-ref["d_q_sqrt"] * tril,
+                         raw_ls=-ref["d_lengthscales"] * sig(pr["raw_ls"]), raw_var=-ref["d_variances"] * sig(pr["raw_var"]))
+            O.adam_step(pr, grads, states[b], lr)
+            pr["q_sqrt"] = np.tril(pr["q_sqrt"])
+            assert H.rel_err(_np(model._q_mu[b]), pr["q_mu"]) < 1e-6
+            assert H.rel_err(_np(model._q_sqrt[b]), pr["q_sqrt"]) < 1e-6
+            assert H.rel_err(_np(model._lengthscales[b]), O.softplus(pr["raw_ls"])) < 1e-6
+            assert H.rel_err(_np(model._variances[b]), O.softplus(pr["raw_var"])) < 1e-6
+
+
+def test_trainable_flags_freeze_parameters():
+    from vgpmp_b200.utils.miscellaneous import disable_param_opt
+    case = H.make_case(num_problems=1, S=3, N=10, M=5, B=16)
+    model = H.make_model(case)
+    disable_param_opt(model, dict(q_mu=True, q_sqrt=False, lengthscales=False, kernel_variance=True, sigma_obs=False,
+                                  inducing_variable=False, alpha=False))
+    before = [t.clone() for t in (model._q_mu, model._q_sqrt, model._lengthscales, model._variances)]
+    model.train_step(case["X"], draws=case["draws_stacked"])
+    after = (model._q_mu, model._q_sqrt, model._lengthscales, model._variances)
+    changed = [not torch.equal(a, b) for a, b in zip(after, before)]
+    assert changed == [True, False, False, True]
+
+
+# ------------------------------------------------------------------------------------------------ device RNG
+def test_device_draws_distribution_and_reproducibility():
+    case = H.make_case(num_problems=2, S=16, N=10, M=6, B=512)
+    model = H.make_model(case, seed=123)
+    eng = model._eng
+    dims = model._dims(10)
+    d1 = {k: _np(v) for k, v in eng.rng_fill(dims, 123, 0).items()}
+    d2 = {k: _np(v) for k, v in eng.rng_fill(dims, 123, 0).items()}
+    d3 = {k: _np(v) for k, v in eng.rng_fill(dims, 123, 1).items()}
+    for k in d1:
+        assert np.array_equal(d1[k], d2[k]) and not np.array_equal(d1[k], d3[k])
+        assert np.all(np.isfinite(d1[k]))
+    assert abs(d1["w"].mean()) < 0.02 and abs(d1["w"].std() - 1) < 0.02
+    assert abs(d1["eps_u"].std() - 1) < 0.1 and abs(np.corrcoef(d1["eps_u"].ravel(), d1["eps_j"].ravel())[0, 1]) < 0.1
+    assert d1["tau"].min() >= 0 and d1["tau"].max() < 2 * np.pi and abs(d1["tau"].mean() - np.pi) < 0.1
+    # Matern-5/2 spectral draws are Student-t with 5 dof: variance 5/3, heavier tails than a normal
+    om = d1["omega"].ravel()
+    assert abs(np.var(om) - 5 / 3) < 0.25 and (np.abs(om) > 4).mean() > 2e-3
+    # sample-sharded generation (config 4): ranks draw disjoint sample slices of the same streams
+    half = eng.dims(2, 6, 10, 8, 512)
+    a = {k: _np(v) for k, v in eng.rng_fill(half, 123, 0, sample_offset=0).items()}
+    b = {k: _np(v) for k, v in eng.rng_fill(half, 123, 0, sample_offset=8).items()}
+    assert np.array_equal(np.concatenate([a["w"], b["w"]], axis=2), d1["w"])
+    assert np.array_equal(np.concatenate([a["eps_u"], b["eps_u"]], axis=2), d1["eps_u"])
+    assert np.array_equal(a["omega"], d1["omega"]) and np.array_equal(b["tau"], d1["tau"])
+    # problem-sharded generation (configs 3/5)
+    one = eng.dims(1, 6, 10, 16, 512)
+    c = {k: _np(v) for k, v in eng.rng_fill(one, 123, 0, problem_offset=1).items()}
+    assert np.array_equal(c["w"][0], d1["w"][1]) and np.array_equal(c["omega"][0], d1["omega"][1])
+
+
+def test_device_rng_elbo_matches_oracle_on_the_materialised_draws():
+    case = H.make_case(num_problems=2, S=7, N=30, M=10, B=128, seed=21)
+    model = H.make_model(case, seed=99)
+    out = model.elbo_and_grads(case["X"])                                  # draws from Philox(seed=99, step=0)
+    draws = {k: _np(v) for k, v in model._draw_buf[1].items()}
+    for b, p in enumerate(case["oracle"]):
+        ref = O.elbo_and_grads(p, case["q_mu"][b], case["q_sqrt"][b], case["ls"][b], case["var"][b],
+                               {k: v[b] for k, v in draws.items()})
+        assert abs(float(out["elbo"][b]) - ref["elbo"]) <= 1e-8 * abs(ref["elbo"])
+        assert H.rel_err(_np(out["d_q_mu"][b]), ref["d_q_mu"]) < 1e-5
+
+
+def test_training_loop_improves_elbo_on_reference_problem():
+    """Franka / bookshelves-like scene, reference planner_params, 40 Adam steps: the (noisy) ELBO rises."""
+    from vgpmp_b200.utils.miscellaneous import training_loop
+    case = H.make_case("franka", "bookshelves", num_problems=4, B=256, perturb=False)
+    model = H.make_model(case, seed=5)
+    losses = torch.stack(training_loop(model, case["X"], 40)).cpu().numpy()
+    assert losses.shape == (40, 4) and np.all(np.isfinite(losses))
+    assert np.median(losses[-5:], axis=0).mean() < np.median(losses[:5], axis=0).mean()
+    best = model.get_best_sample(model.likelihood.joint_sigmoid(model.predict_f_samples(case["X"], num_samples=150)))
+    assert best.shape == (4,)
+
+
+def test_errors_are_reported_not_swallowed():
+    from vgpmp_b200 import _cabi
+    case = H.make_case(num_problems=1, S=2, N=5, M=5, B=8)
+    model = H.make_model(case)
+    eng = model._eng
+    with pytest.raises(_cabi.VgpmpError, match="num_inducing"):
+        eng.gp_prepare(eng.dims(1, 31, 5, 2, 8), model._params(None))

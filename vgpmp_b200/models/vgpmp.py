@@ -1,0 +1,276 @@
+"""`VGPMP` planner model (reference: gpflow_vgpmp/models/vgpmp.py:59-339).
+
+Same constructor / `initialize` / property / method names as the reference.  All state lives in HBM as float64
+buffers; `elbo`, its gradients and the Adam update are calls into libvgpmp_b200.so.  A model holds a *batch* of
+Bp independent planning problems (query_states [Bp,2,D]); Bp = 1 reproduces the reference object.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from .. import _cabi
+from ..inducing_variables import ConditionedVariableInducingPoints, SharedIndependentInducingVariables
+from ..kernels import Matern52, SeparateIndependent, SharedIndependent, VanillaConditioningSeparateIndependent
+from ..likelihoods import VariationalMonteCarloLikelihood
+
+__all__ = ["VGPMP", "initialize_Z", "AdamConfig"]
+
+DEFAULT_JITTER = 1e-6
+
+
+def initialize_Z(num_latent_gps, num_inducing):
+    """linspace(.1,.9,M) replicated over the latent GPs (models/vgpmp.py:37-42; sigmoid-bounded to (.09,.91) there)."""
+    return np.array([np.full(num_latent_gps, t) for t in np.linspace(0.1, 0.9, num_inducing)], dtype=np.float64)
+
+
+def _softplus_inv(y):
+    y = np.asarray(y, dtype=np.float64)
+    return y + np.log(-np.expm1(-y))
+
+
+class AdamConfig:
+    """tf.optimizers.Adam(learning_rate, beta_1=0.8, beta_2=0.95) (models/vgpmp.py:77); epsilon = Keras default 1e-7."""
+
+    def __init__(self, learning_rate, beta_1=0.8, beta_2=0.95, epsilon=1e-7):
+        self.learning_rate, self.beta_1, self.beta_2, self.epsilon = float(learning_rate), beta_1, beta_2, epsilon
+
+
+class VGPMP:
+    def __init__(self, kernel, likelihood: VariationalMonteCarloLikelihood, inducing_variable, *, num_latent_gps: int,
+                 alpha: float, query_states, num_samples: int, num_bases: int, num_inducing: int, learning_rate: float,
+                 q_mu=None, num_data=None, whiten: bool = False, prior=None, variance_lower: float = 0.0, seed: int = 0,
+                 **kwargs):
+        if whiten:
+            raise NotImplementedError("the reference builds the model with whiten=False (models/vgpmp.py:198)")
+        if not isinstance(kernel, SeparateIndependent):
+            raise AssertionError("Kernels must be a list of kernels or a SharedIndependent kernel.")
+        self.kernel, self.likelihood, self.inducing_variable = kernel, likelihood, inducing_variable
+        self.num_latent_gps = D = int(num_latent_gps)
+        self.num_samples, self.num_bases, self.num_inducing = int(num_samples), int(num_bases), int(num_inducing)
+        self.num_data, self.prior, self.seed = num_data, prior, int(seed)
+        self.optimizer = AdamConfig(learning_rate)
+        self.alpha = float(alpha)
+        self.trainable = dict(q_mu=True, q_sqrt=True, lengthscales=True, kernel_variance=True)
+        likelihood._alpha = self.alpha
+        self._eng = eng = likelihood._engine()
+        if eng.D != D:
+            raise AssertionError("num_latent_gps must equal the robot's degrees of freedom")
+
+        qs = np.asarray(query_states, dtype=np.float64)
+        qs = qs.reshape(1, 2, D) if qs.ndim == 2 else qs.reshape(-1, 2, D)
+        self.num_problems = Bp = qs.shape[0]
+        self._query_joint = qs
+        self._query_states = eng.dev(likelihood.joint_sigmoid.inverse(qs))            # [Bp,2,D] latent (vgpmp.py:75-76)
+        iv = inducing_variable.inducing_variable if isinstance(inducing_variable, SharedIndependentInducingVariables) \
+            else inducing_variable
+        if len(iv) != self.num_inducing:
+            raise AssertionError("inducing variable size and num_inducing disagree")
+        self._Z = eng.dev(iv._Z)                                                      # [M,D]
+        self._init_variational_parameters(self.num_inducing, q_mu, None, False)
+        ls, var = kernel.hyper_arrays()
+        if np.any(var <= variance_lower):
+            raise ValueError("kernel variance must exceed the lower bound of its positive() transform "
+                             "(SURVEY.md appendix C #14: UR10/industrial variance=0.1 is un-representable)")
+        self._variance_lower = float(variance_lower)
+        self._lengthscales = eng.dev(np.broadcast_to(ls, (Bp, D)).copy())
+        self._variances = eng.dev(np.broadcast_to(var, (Bp, D)).copy())
+        self._raw_lengthscales = eng.dev(_softplus_inv(np.broadcast_to(ls, (Bp, D))))
+        self._raw_variances = eng.dev(_softplus_inv(np.broadcast_to(var, (Bp, D)) - variance_lower))
+        for i, k in enumerate(kernel.kernels):
+            k._bind(self, i)
+        per = self.num_inducing * D + D * self.num_inducing ** 2 + 2 * D
+        self._adam_m = torch.zeros(Bp * per, dtype=torch.float64, device=eng.device)
+        self._adam_v = torch.zeros_like(self._adam_m)
+        self._step = 0
+        self._grads = None
+        self._draw_buf = None
+        self.last_aux = None
+
+    # ---- construction ------------------------------------------------------------------------------
+    @classmethod
+    def initialize(cls, sdf, robot, sampler, lengthscales: List[float], query_states, sigma_obs: float = 0.05,
+                   alpha: float = 1.0, variance: float = 0.1, learning_rate: float = 0.1, num_inducing: int = 14,
+                   num_samples: int = 51, num_bases: int = 1024, scene_offset: List[float] = None, num_data=None,
+                   num_output_dims=None, kernel=None, num_latent_gps: int = None, epsilon: float = 0.05, q_mu=None,
+                   interpolation_method: Optional[str] = 'linear', **kwargs):
+        """models/vgpmp.py:84-198.  Extra planner_params keys (num_steps, time_spacing_*) are swallowed like there."""
+        qs = np.asarray(query_states, dtype=np.float64)
+        if num_output_dims is None:
+            num_output_dims = qs.shape[-1]
+        if num_latent_gps is None:
+            num_latent_gps = num_output_dims
+        if num_data is None:
+            num_data = 2
+        assert lengthscales is not None, "Lengthscales have not been set."
+        assert qs.size > 0, "Must pass a motion plan to initialize the model."
+        if scene_offset is None:
+            scene_offset = [0, 0, 0]
+            warnings.warn("Offset has not been set. Defaulting to [0, 0, 0].")
+        assert len(lengthscales) == num_latent_gps
+        assert num_output_dims == num_latent_gps
+        if kernel is not None:
+            assert isinstance(kernel, (SeparateIndependent, SharedIndependent)), \
+                "Kernels must be a list of kernels or a SharedIndependent kernel."
+        else:
+            kernel = VanillaConditioningSeparateIndependent(
+                [Matern52(lengthscales=lengthscales[i], variance=variance) for i in range(num_latent_gps)])
+        conditioned_timesteps = np.stack([np.zeros(num_output_dims), np.ones(num_output_dims)])
+        Z = initialize_Z(num_latent_gps, num_inducing)
+        _Z = ConditionedVariableInducingPoints(Z=Z, conditioned_timesteps=conditioned_timesteps)
+        likelihood = VariationalMonteCarloLikelihood(sigma_obs=sigma_obs, robot=robot, sdf=sdf, sampler=sampler,
+                                                     offset=scene_offset, epsilon=epsilon)
+        batched = qs.ndim == 3
+        q3 = qs.reshape(-1, 2, num_output_dims)
+        if q_mu is None:
+            if interpolation_method is None:
+                q_mu = likelihood.joint_sigmoid(np.zeros((q3.shape[0], num_inducing, num_latent_gps)))
+            elif interpolation_method == 'linear':
+                steps = (np.arange(num_inducing, dtype=np.float64) / num_inducing)[None, :, None]   # i / M, never reaches the goal
+                q_mu = q3[:, :1, :] + (q3[:, 1:2, :] - q3[:, :1, :]) * steps
+            elif interpolation_method == 'waypoint':
+                raise NotImplementedError("'waypoint' builds a [3,D] q_mu in the reference, which its own shape check "
+                                          "rejects unless num_inducing == 3 (models/vgpmp.py:172-175)")
+            else:
+                raise NotImplementedError
+        else:
+            assert isinstance(q_mu, np.ndarray)
+            q_mu = np.broadcast_to(q_mu.reshape(-1, num_inducing, num_latent_gps), (q3.shape[0], num_inducing, num_latent_gps))
+        return cls(kernel=kernel, likelihood=likelihood, inducing_variable=SharedIndependentInducingVariables(_Z),
+                   num_latent_gps=num_latent_gps, num_samples=num_samples, num_bases=num_bases, num_data=num_data,
+                   query_states=qs if batched else q3[0], num_inducing=num_inducing, learning_rate=learning_rate,
+                   alpha=alpha, q_mu=q_mu if batched else q_mu[0], whiten=False,
+                   **{k: v for k, v in kwargs.items() if k in ("variance_lower", "seed")})
+
+    def _init_variational_parameters(self, num_inducing, q_mu, q_sqrt, q_diag):
+        """models/vgpmp.py:255-263: _q_mu = joint_sigmoid.inverse(q_mu); _q_sqrt = I per latent."""
+        eng, D, Bp = self._eng, self.num_latent_gps, self.num_problems
+        q = np.asarray(q_mu, dtype=np.float64).reshape(-1, num_inducing, D)
+        q = np.broadcast_to(q, (Bp, num_inducing, D))
+        self._q_mu = eng.dev(self.likelihood.joint_sigmoid.inverse(q))                              # [Bp,M,D]
+        self._q_sqrt = eng.dev(np.broadcast_to(np.eye(num_inducing), (Bp, D, num_inducing, num_inducing)).copy())
+
+    # ---- properties -------------------------------------------------------------------------------
+    def _squeeze(self, t):
+        return t[0] if self.num_problems == 1 else t
+
+    @property
+    def query_states(self):
+        return self._squeeze(self._query_states)
+
+    @property
+    def q_mu(self):
+        """concat([query_states, _q_mu]) -> [Mp,D] (models/vgpmp.py:200-202)."""
+        return self._squeeze(torch.cat([self._query_states, self._q_mu], dim=1))
+
+    @property
+    def q_sqrt(self):
+        """Lc @ pad(_q_sqrt) + jitter * diag(1,1,0,..) -> [D,Mp,Mp] (models/vgpmp.py:208-218)."""
+        _, Sfull, _ = self._eng.gp_prepare(self._dims(1), self._params(None))
+        return self._squeeze(Sfull)
+
+    @property
+    def trainable_variables(self):
+        out = []
+        if self.trainable["q_mu"]:
+            out.append(self._q_mu)
+        if self.trainable["q_sqrt"]:
+            out.append(self._q_sqrt)
+        if self.trainable["lengthscales"]:
+            out.append(self._raw_lengthscales)
+        if self.trainable["kernel_variance"]:
+            out.append(self._raw_variances)
+        return out
+
+    # ---- plumbing ----------------------------------------------------------------------------------
+    def _dims(self, N, S=None):
+        return self._eng.dims(self.num_problems, self.num_inducing, N, self.num_samples if S is None else S, self.num_bases)
+
+    def _params(self, X):
+        return self._eng.params_struct(self._q_mu, self._q_sqrt, self._lengthscales, self._variances, self._query_states,
+                                       self._Z, X)
+
+    def _make_draws(self, dims, draws):
+        """Explicit draws (parity mode: dict of arrays shaped like vgpmp_draws) or device Philox draws (seed, step)."""
+        eng = self._eng
+        if draws is not None:
+            Bp, D, B, S, Mp = dims.num_problems, eng.D, dims.num_bases, dims.num_samples, dims.num_inducing + 2
+            shapes = dict(omega=(Bp, D, B, D), tau=(Bp, D, B), w=(Bp, D, S, B), eps_u=(Bp, D, S, Mp), eps_j=(Bp, D, S, Mp))
+            return {k: eng.dev(draws[k]).reshape(shapes[k]) for k in shapes}
+        key = (dims.num_problems, dims.num_samples, dims.num_bases)
+        if self._draw_buf is None or self._draw_buf[0] != key:
+            self._draw_buf = (key, eng.alloc_draws(dims))
+        return eng.rng_fill(dims, self.seed, self._step, self._draw_buf[1])
+
+    # ---- reference API ---------------------------------------------------------------------------
+    def elbo(self, data, draws=None):
+        """alpha * sum_n mean_s log p - KL (models/vgpmp.py:265-289).  Scalar tensor (or [Bp])."""
+        X = self._eng.dev(data).reshape(-1, self.num_latent_gps)
+        dims = self._dims(X.shape[0])
+        out = self._eng.elbo_fwd_bwd(dims, self._params(X), self._make_draws(dims, draws), need_grad=False)
+        return self._squeeze(out["elbo"])
+
+    def elbo_and_grads(self, data, draws=None, want_aux=False):
+        X = self._eng.dev(data).reshape(-1, self.num_latent_gps)
+        dims = self._dims(X.shape[0])
+        return self._eng.elbo_fwd_bwd(dims, self._params(X), self._make_draws(dims, draws), need_grad=True,
+                                      want_aux=want_aux)
+
+    def maximum_log_likelihood_objective(self, data):
+        return self.elbo(data)
+
+    def training_loss(self, data):
+        return -self.elbo(data)
+
+    def training_loss_closure(self, data, **_):
+        X = self._eng.dev(data).reshape(-1, self.num_latent_gps)
+
+        def closure():
+            return -self.elbo(X)
+        closure.model, closure.data = self, X
+        return closure
+
+    def _adam_struct(self) -> _cabi.Adam:
+        o, t = self.optimizer, self.trainable
+        return _cabi.Adam(self._q_mu.data_ptr(), self._q_sqrt.data_ptr(), self._raw_lengthscales.data_ptr(),
+                          self._raw_variances.data_ptr(), self._lengthscales.data_ptr(), self._variances.data_ptr(),
+                          self._adam_m.data_ptr(), self._adam_v.data_ptr(), self._variance_lower, o.learning_rate,
+                          o.beta_1, o.beta_2, o.epsilon, self._step, int(t["q_mu"]), int(t["q_sqrt"]),
+                          int(t["lengthscales"]), int(t["kernel_variance"]))
+
+    def train_step(self, X, draws=None):
+        """One optimization_step (utils/miscellaneous.py:68-84): ELBO forward + reverse + Adam; returns loss = -ELBO."""
+        eng = self._eng
+        X = eng.dev(X).reshape(-1, self.num_latent_gps)
+        dims = self._dims(X.shape[0])
+        out = eng.elbo_fwd_bwd(dims, self._params(X), self._make_draws(dims, draws), need_grad=True)
+        gs = _cabi.Grads(out["d_q_mu"].data_ptr(), out["d_q_sqrt"].data_ptr(), out["d_lengthscales"].data_ptr(),
+                         out["d_variances"].data_ptr())
+        st = self._adam_struct()
+        eng._chk(eng.lib.vgpmp_adam_step(eng.h, C.byref(dims), C.byref(st), C.byref(gs), eng._stream()), "adam_step")
+        self._step = st.step
+        self._grads = out
+        return self._squeeze(-out["elbo"])
+
+    def predict_f_samples(self, X, num_samples=None, draws=None):
+        """temporary_paths + predict_f_samples (models/vgpmp.py:281-282): [S,N,D] latent samples."""
+        S = self.num_samples if num_samples is None else int(num_samples)
+        dims = self._dims(1, S)
+        f = self._eng.pathwise_sample(dims, self._params(None), self._make_draws(dims, draws), X)
+        return self._squeeze(f)
+
+    def debug_likelihood(self, data):
+        lp = self.likelihood.log_prob(data)
+        return torch.sum(torch.mean(lp, dim=0))
+
+    def get_best_sample(self, samples):
+        """argmax_s sum_n log_prob (models/vgpmp.py:336-339)."""
+        cost = torch.sum(self.likelihood.log_prob(samples), dim=-1)
+        return torch.argmax(cost, dim=-1)
+
+    def initialize_optimizer(self, learning_rate):
+        return AdamConfig(learning_rate)
