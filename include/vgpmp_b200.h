@@ -201,6 +201,16 @@ int vgpmp_train_step_host(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* s
                           size_t ws_bytes, void* stream);
 size_t vgpmp_draws_bytes(const vgpmp_dims* dims, int dof);
 
+/* ---- measurement hooks (bench.py / profiles; no reference counterpart beyond the `timing` decorator of
+ * utils/miscellaneous.py:46-56) ---------------------------------------------------------------------------
+ * With profiling enabled every stage launch of vgpmp_elbo_fwd_bwd / vgpmp_adam_step / vgpmp_rng_fill is bracketed by
+ * CUDA events on the launching stream; vgpmp_profile_collect synchronises, returns the summed milliseconds and launch
+ * counts per stage (arrays of VGPMP_NUM_STAGES) and clears the record. */
+#define VGPMP_NUM_STAGES 7
+int vgpmp_profile_enable(vgpmp_handle* h, int on);
+int vgpmp_profile_collect(vgpmp_handle* h, double* stage_ms, int64_t* stage_launches);
+const char* vgpmp_stage_name(int stage);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

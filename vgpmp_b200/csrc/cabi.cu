@@ -23,6 +23,34 @@ int check_cuda(vgpmp_handle* h, cudaError_t e, const char* what) {
   return fail(h, VGPMP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+cudaEvent_t take_event(vgpmp_handle* h) {
+  if (!h->event_pool.empty()) {
+    cudaEvent_t e = h->event_pool.back();
+    h->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+// RAII bracket of one stage launch; a no-op unless profiling is on
+struct StageSpan {
+  vgpmp_handle* h;
+  cudaStream_t s;
+  cudaEvent_t b = nullptr;
+  StageSpan(vgpmp_handle* h_, int stage, cudaStream_t s_) : h(h_), s(s_) {
+    if (!h->profiling) return;
+    cudaEvent_t a = take_event(h);
+    b = take_event(h);
+    cudaEventRecord(a, s);
+    h->spans.push_back({stage, a, b});
+  }
+  ~StageSpan() {
+    if (b) cudaEventRecord(b, s);
+  }
+};
+
 struct Carver {
   char* base;
   size_t off = 0;
@@ -144,9 +172,40 @@ int vgpmp_create(vgpmp_handle** out, int device, const vgpmp_robot_desc* robot, 
   return VGPMP_OK;
 }
 
+int vgpmp_profile_enable(vgpmp_handle* h, int on) {
+  if (!h) return VGPMP_ERR_INVALID;
+  h->profiling = on != 0;
+  return VGPMP_OK;
+}
+
+int vgpmp_profile_collect(vgpmp_handle* h, double* stage_ms, int64_t* stage_launches) {
+  if (!h || !stage_ms || !stage_launches) return fail(h, VGPMP_ERR_INVALID, "profile_collect: bad argument");
+  for (int i = 0; i < VGPMP_NUM_STAGES; ++i) { stage_ms[i] = 0.0; stage_launches[i] = 0; }
+  int rc = check_cuda(h, cudaDeviceSynchronize(), "profile_collect sync");
+  for (auto& sp : h->spans) {
+    float ms = 0.f;
+    if (!rc && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+      stage_ms[sp.stage] += ms;
+      stage_launches[sp.stage] += 1;
+    }
+    h->event_pool.push_back(sp.a);
+    h->event_pool.push_back(sp.b);
+  }
+  h->spans.clear();
+  return rc;
+}
+
+const char* vgpmp_stage_name(int stage) {
+  static const char* names[VGPMP_NUM_STAGES] = {"rng_fill", "gp_prepare", "pathwise_sample", "loglik_fwd_bwd",
+                                                "elbo_reduce", "gp_backward", "adam"};
+  return (stage >= 0 && stage < VGPMP_NUM_STAGES) ? names[stage] : "?";
+}
+
 int vgpmp_destroy(vgpmp_handle* h) {
   if (!h) return VGPMP_OK;
   cudaSetDevice(h->device);
+  for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  for (auto e : h->event_pool) cudaEventDestroy(e);
   if (h->grid_dev) cudaFree(h->grid_dev);
   delete h;
   return VGPMP_OK;
@@ -167,23 +226,23 @@ size_t vgpmp_draws_bytes(const vgpmp_dims* d, int dof) {
 }
 
 int vgpmp_fk_frames(vgpmp_handle* h, const double* joints, double* frames, int64_t n, void* stream) {
-  if (!h || !joints || !frames || n < 0) return fail(h, VGPMP_ERR_INVALID, "fk_frames: bad argument");
+  if (!h || n < 0 || (n > 0 && (!joints || !frames))) return fail(h, VGPMP_ERR_INVALID, "fk_frames: bad argument");
   return check_cuda(h, launch_fk_frames(h, joints, frames, n, (cudaStream_t)stream), "fk_frames");
 }
 
 int vgpmp_fk_spheres(vgpmp_handle* h, const double* joints, double* centres, int64_t n, void* stream) {
-  if (!h || !joints || !centres || n < 0) return fail(h, VGPMP_ERR_INVALID, "fk_spheres: bad argument");
+  if (!h || n < 0 || (n > 0 && (!joints || !centres))) return fail(h, VGPMP_ERR_INVALID, "fk_spheres: bad argument");
   return check_cuda(h, launch_fk_spheres(h, joints, centres, n, (cudaStream_t)stream), "fk_spheres");
 }
 
 int vgpmp_sdf_lookup(vgpmp_handle* h, const double* pts, double* dist, double* grad, int64_t n, void* stream) {
-  if (!h || !pts || !dist || n < 0) return fail(h, VGPMP_ERR_INVALID, "sdf_lookup: bad argument");
+  if (!h || n < 0 || (n > 0 && (!pts || !dist))) return fail(h, VGPMP_ERR_INVALID, "sdf_lookup: bad argument");
   return check_cuda(h, launch_sdf_lookup(h, pts, dist, grad, n, (cudaStream_t)stream), "sdf_lookup");
 }
 
 int vgpmp_loglik_fwd_bwd(vgpmp_handle* h, const double* in, int squash, double upstream, double* logp, double* d_in,
                          int64_t n, void* stream) {
-  if (!h || !in || !logp || n < 0) return fail(h, VGPMP_ERR_INVALID, "loglik_fwd_bwd: bad argument");
+  if (!h || n < 0 || (n > 0 && (!in || !logp))) return fail(h, VGPMP_ERR_INVALID, "loglik_fwd_bwd: bad argument");
   return check_cuda(h, launch_loglik(h, in, squash, upstream, logp, d_in, n, (cudaStream_t)stream), "loglik_fwd_bwd");
 }
 
@@ -255,19 +314,32 @@ int vgpmp_elbo_fwd_bwd(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_para
   double* f = (aux && aux->f) ? aux->f : g.f;
   double* logp = (aux && aux->logp) ? aux->logp : g.logp;
   const bool bwd = gr != nullptr;
-  if ((rc = check_cuda(h, launch_gp_prepare(h, *dims, *p, g.Lc, g.Sfull, g.kl_l, g.kvec, s), "gp_prepare"))) return rc;
-  if ((rc = check_cuda(h, launch_pathwise(h, *dims, *p, *r, p->X, dims->num_timesteps, g.Lc, g.Sfull, f,
-                                          bwd ? g.v : nullptr, bwd ? g.f0 : nullptr, bwd ? g.h0 : nullptr, s),
-                       "pathwise")))
-    return rc;
-  if ((rc = check_cuda(h, launch_loglik(h, f, 1, h->lik.alpha / (double)dims->num_samples, logp, bwd ? g.df : nullptr,
-                                        ncfg, s), "loglik")))
-    return rc;
-  if ((rc = check_cuda(h, launch_elbo_reduce(h, *dims, logp, g.kl_l, elbo, aux ? aux->kl : nullptr, s), "elbo_reduce")))
-    return rc;
+  {
+    StageSpan sp(h, ST_PREPARE, s);
+    if ((rc = check_cuda(h, launch_gp_prepare(h, *dims, *p, g.Lc, g.Sfull, g.kl_l, g.kvec, s), "gp_prepare"))) return rc;
+  }
+  {
+    StageSpan sp(h, ST_PATHWISE, s);
+    if ((rc = check_cuda(h, launch_pathwise(h, *dims, *p, *r, p->X, dims->num_timesteps, g.Lc, g.Sfull, f,
+                                            bwd ? g.v : nullptr, bwd ? g.f0 : nullptr, bwd ? g.h0 : nullptr, s),
+                         "pathwise")))
+      return rc;
+  }
+  {
+    StageSpan sp(h, ST_LOGLIK, s);
+    if ((rc = check_cuda(h, launch_loglik(h, f, 1, h->lik.alpha / (double)dims->num_samples, logp,
+                                          bwd ? g.df : nullptr, ncfg, s), "loglik")))
+      return rc;
+  }
+  {
+    StageSpan sp(h, ST_REDUCE, s);
+    if ((rc = check_cuda(h, launch_elbo_reduce(h, *dims, logp, g.kl_l, elbo, aux ? aux->kl : nullptr, s), "elbo_reduce")))
+      return rc;
+  }
   if (bwd) {
     GpScratch gs = g;
     gs.f = f;
+    StageSpan sp(h, ST_BACKWARD, s);
     if ((rc = check_cuda(h, launch_gp_backward(h, *dims, *p, *r, gs, *gr, s), "gp_backward"))) return rc;
   }
   (void)D;
@@ -278,7 +350,10 @@ int vgpmp_adam_step(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* st, con
   int rc = check_dims(h, dims);
   if (rc) return rc;
   if (!st || !g) return fail(h, VGPMP_ERR_INVALID, "adam_step: bad argument");
-  rc = check_cuda(h, launch_adam(h, *dims, *st, *g, (cudaStream_t)stream), "adam_step");
+  {
+    StageSpan sp(h, ST_ADAM, (cudaStream_t)stream);
+    rc = check_cuda(h, launch_adam(h, *dims, *st, *g, (cudaStream_t)stream), "adam_step");
+  }
   if (!rc) st->step += 1;
   return rc;
 }
@@ -290,6 +365,7 @@ int vgpmp_rng_fill(vgpmp_handle* h, const vgpmp_dims* dims, uint64_t seed, uint6
   if (rc) return rc;
   if ((omega == nullptr) != (tau == nullptr) || (eps_u == nullptr) != (eps_j == nullptr))
     return fail(h, VGPMP_ERR_INVALID, "rng_fill: omega/tau and eps_u/eps_j come in pairs");
+  StageSpan sp(h, ST_RNG, (cudaStream_t)stream);
   return check_cuda(h, launch_rng_fill(h, *dims, seed, iteration, problem_offset, sample_offset, omega, tau, w, eps_u,
                                        eps_j, (cudaStream_t)stream), "rng_fill");
 }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 #include "../../include/vgpmp_b200.h"
 
@@ -44,7 +45,14 @@ struct vgpmp_handle {
   double* grid_dev = nullptr;
   uint64_t launches = 0;
   std::string err;
+  // stage profiling (bench.py): event pairs recorded on the launching stream
+  bool profiling = false;
+  struct Span { int stage; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> event_pool;
 };
+
+enum VgStage { ST_RNG = 0, ST_PREPARE, ST_PATHWISE, ST_LOGLIK, ST_REDUCE, ST_BACKWARD, ST_ADAM };
 
 // ---- launchers implemented in kinematics.cu -------------------------------------------------
 cudaError_t launch_fk_frames(vgpmp_handle* h, const double* joints, double* frames, int64_t n, cudaStream_t s);
