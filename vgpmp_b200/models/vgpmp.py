@@ -256,6 +256,39 @@ class VGPMP:
         self._grads = out
         return self._squeeze(-out["elbo"])
 
+    def train_step_host(self, X_host: torch.Tensor):
+        """The same optimisation step driven from HOST buffers through `vgpmp_train_step_host`: X [N,D] is read from
+        (pinned) host memory, copied to the device, the step's randomness is drawn on the device, and loss = -ELBO [Bp]
+        is copied back to pinned host memory before the call returns (like `loss = tf_optimization_step(...)` feeding
+        the tqdm readout, utils/miscellaneous.py:101-103).  Returns a CPU tensor view of the pinned loss buffer."""
+        eng, D = self._eng, self.num_latent_gps
+        if X_host.device.type != "cpu" or X_host.dtype != torch.float64 or not X_host.is_contiguous():
+            raise TypeError("train_step_host expects a contiguous float64 CPU tensor (pinned for async copies)")
+        N = X_host.numel() // D
+        dims = self._dims(N)
+        hs = getattr(self, "_host_state", None)
+        if hs is None or hs["N"] != N:
+            nbytes = int(eng.lib.vgpmp_draws_bytes(C.byref(dims), D))
+            hs = dict(N=N, X_dev=eng.empty(N, D), draws=torch.empty(nbytes, dtype=torch.uint8, device=eng.device),
+                      elbo=eng.empty(self.num_problems),
+                      loss=torch.empty(self.num_problems, dtype=torch.float64).pin_memory(),
+                      g=dict(d_q_mu=eng.empty(self.num_problems, self.num_inducing, D),
+                             d_q_sqrt=eng.empty(self.num_problems, D, self.num_inducing, self.num_inducing),
+                             d_lengthscales=eng.empty(self.num_problems, D), d_variances=eng.empty(self.num_problems, D)))
+            self._host_state = hs
+        g = hs["g"]
+        gs = _cabi.Grads(g["d_q_mu"].data_ptr(), g["d_q_sqrt"].data_ptr(), g["d_lengthscales"].data_ptr(),
+                         g["d_variances"].data_ptr())
+        st = self._adam_struct()
+        ws = eng.workspace(dims)
+        eng._chk(eng.lib.vgpmp_train_step_host(eng.h, C.byref(dims), C.byref(st), self._query_states.data_ptr(),
+                                               self._Z.data_ptr(), X_host.data_ptr(), hs["X_dev"].data_ptr(),
+                                               self.seed, hs["draws"].data_ptr(), hs["draws"].numel(), C.byref(gs),
+                                               hs["elbo"].data_ptr(), hs["loss"].data_ptr(), ws.data_ptr(), ws.numel(),
+                                               eng._stream()), "train_step_host")
+        self._step = st.step
+        return hs["loss"]
+
     def predict_f_samples(self, X, num_samples=None, draws=None):
         """temporary_paths + predict_f_samples (models/vgpmp.py:281-282): [S,N,D] latent samples."""
         S = self.num_samples if num_samples is None else int(num_samples)
