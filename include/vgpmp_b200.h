@@ -206,6 +206,10 @@ size_t vgpmp_draws_bytes(const vgpmp_dims* dims, int dof);
  * With profiling enabled every stage launch of vgpmp_elbo_fwd_bwd / vgpmp_adam_step / vgpmp_rng_fill is bracketed by
  * CUDA events on the launching stream; vgpmp_profile_collect synchronises, returns the summed milliseconds and launch
  * counts per stage (arrays of VGPMP_NUM_STAGES) and clears the record. */
+/* Tuning switches (all default on).  "grid_fast_path": when X and Z are rank-1 equispaced grids (always true for the
+ * reference's init_trainset / initialize_Z) the Fourier features are generated by rotation recurrences; 0 forces the
+ * general per-point sincos kernel. */
+int vgpmp_set_option(vgpmp_handle* h, const char* name, int value);
 #define VGPMP_NUM_STAGES 7
 int vgpmp_profile_enable(vgpmp_handle* h, int on);
 int vgpmp_profile_collect(vgpmp_handle* h, double* stage_ms, int64_t* stage_launches);

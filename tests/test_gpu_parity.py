@@ -151,16 +151,44 @@ def test_gp_prepare_chol_qsqrt_kl_vs_oracle(M):
     assert abs(got - klo) <= 1e-7 * abs(klo)
 
 
-@pytest.mark.parametrize("S,N,M,B", [(7, 70, 24, 64), (3, 5, 1, 3), (20, 50, 7, 40), (9, 150, 12, 33)])
-def test_pathwise_sample_vs_oracle(S, N, M, B):
+@pytest.mark.parametrize("grid", [1, 0])
+@pytest.mark.parametrize("S,N,M,B", [(7, 70, 24, 64), (3, 5, 1, 3), (20, 50, 7, 40), (9, 150, 12, 33), (8, 2, 2, 32),
+                                     (17, 300, 30, 70)])
+def test_pathwise_sample_vs_oracle(S, N, M, B, grid):
+    """grid=1: equispaced rank-1 fast path (rotation recurrences); grid=0: general per-point sincos kernel."""
     case = H.make_case(num_problems=2, S=S, N=N, M=M, B=B, seed=S + N)
     model = H.make_model(case)
+    model._eng.set_option("grid_fast_path", grid)
     f = _np(model.predict_f_samples(case["X"], draws=case["draws_stacked"]))
     for b, p in enumerate(case["oracle"]):
         want = p.sample_paths(p.X, O._t(case["q_mu"][b]), O._t(case["q_sqrt"][b]), O._t(case["ls"][b]),
                               O._t(case["var"][b]), case["draws"][b]).numpy()
         assert f[b].shape == want.shape == (S, N, 7)
         assert H.rel_err(f[b], want) < 1e-7     # Khat^-1 amplifies rounding by ~cond; still 100x inside the 1e-5 budget
+
+
+def test_pathwise_sample_irregular_inputs_fall_back_to_general_kernel():
+    """X not equispaced / columns of Z not identical: the device-side probe must route to the general kernel."""
+    case = H.make_case(num_problems=2, S=5, N=40, M=9, B=48, seed=31)
+    rng = np.random.default_rng(1)
+    Xirr = np.sort(rng.uniform(0, 1, size=(40, 1)), axis=0) * np.ones((1, 7))
+    Xirr[:, 3] = Xirr[:, 3] ** 2                                     # columns differ
+    Zirr = case["Z"] + 0.01 * rng.standard_normal(case["Z"].shape)
+    model = H.make_model(case)
+    model._Z.copy_(model._eng.dev(Zirr))
+    f = _np(model.predict_f_samples(Xirr, draws=case["draws_stacked"]))
+    for b, p in enumerate(case["oracle"]):
+        p2 = O.OracleProblem(**{**p.__dict__, "X": Xirr, "Z": Zirr})
+        want = p2.sample_paths(Xirr, O._t(case["q_mu"][b]), O._t(case["q_sqrt"][b]), O._t(case["ls"][b]),
+                               O._t(case["var"][b]), case["draws"][b]).numpy()
+        assert H.rel_err(f[b], want) < 1e-7
+    # nearly-but-not-exactly equispaced X (1e-9 wobble) must also be treated as irregular, not silently snapped to a grid
+    Xw = case["X"][:40] + 1e-9 * rng.standard_normal((40, 1))
+    f2 = _np(model.predict_f_samples(Xw, draws=case["draws_stacked"]))
+    p2 = O.OracleProblem(**{**case["oracle"][0].__dict__, "X": Xw, "Z": Zirr})
+    want = p2.sample_paths(Xw, O._t(case["q_mu"][0]), O._t(case["q_sqrt"][0]), O._t(case["ls"][0]), O._t(case["var"][0]),
+                           case["draws"][0]).numpy()
+    assert H.rel_err(f2[0], want) < 1e-7
 
 
 # ------------------------------------------------------------------------------------------------ fused iteration
@@ -170,9 +198,11 @@ def test_pathwise_sample_vs_oracle(S, N, M, B):
     ("kuka", "industrial", dict(B=96)),                           # config 3 shapes: S=20, N=50, M=7
     ("ur10", "bookshelves", dict(B=64, S=33)),                    # config 4 robot (D=6), more samples than one tile
 ])
-def test_elbo_and_gradients_vs_oracle(name, env, kw):
+@pytest.mark.parametrize("grid", [1, 0])
+def test_elbo_and_gradients_vs_oracle(name, env, kw, grid):
     case = H.make_case(name, env, num_problems=2, seed=4, **kw)
     model = H.make_model(case)
+    model._eng.set_option("grid_fast_path", grid)
     out = model.elbo_and_grads(case["X"], draws=case["draws_stacked"], want_aux=True)
     for b, p in enumerate(case["oracle"]):
         ref = O.elbo_and_grads(p, case["q_mu"][b], case["q_sqrt"][b], case["ls"][b], case["var"][b], case["draws"][b])

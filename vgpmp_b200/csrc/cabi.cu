@@ -77,6 +77,7 @@ GpScratch carve(void* ws, int D, const vgpmp_dims& d, size_t* total) {
   g.f = c.take(Bp * S * N * D);
   g.df = c.take(Bp * S * N * D);
   g.logp = c.take(Bp * S * N);
+  g.meta = c.take(8);
   *total = c.off;
   return g;
 }
@@ -170,6 +171,12 @@ int vgpmp_create(vgpmp_handle** out, int device, const vgpmp_robot_desc* robot, 
   h->sdf.delta = sdf->delta;
   *out = h;
   return VGPMP_OK;
+}
+
+int vgpmp_set_option(vgpmp_handle* h, const char* name, int value) {
+  if (!h || !name) return fail(h, VGPMP_ERR_INVALID, "set_option: bad argument");
+  if (std::strcmp(name, "grid_fast_path") == 0) { h->allow_grid_path = value != 0; return VGPMP_OK; }
+  return fail(h, VGPMP_ERR_INVALID, std::string("set_option: unknown option ") + name);
 }
 
 int vgpmp_profile_enable(vgpmp_handle* h, int on) {
@@ -295,7 +302,7 @@ int vgpmp_pathwise_sample(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_p
   if (ws_bytes < need) return fail(h, VGPMP_ERR_WORKSPACE, "pathwise_sample: workspace too small (size it with num_timesteps = num_query)");
   cudaStream_t s = (cudaStream_t)stream;
   if ((rc = check_cuda(h, launch_gp_prepare(h, dq, *p, g.Lc, g.Sfull, g.kl_l, g.kvec, s), "gp_prepare"))) return rc;
-  return check_cuda(h, launch_pathwise(h, dq, *p, *r, Xq, num_query, g.Lc, g.Sfull, f, nullptr, nullptr, nullptr, s),
+  return check_cuda(h, launch_pathwise(h, dq, *p, *r, Xq, num_query, g.Lc, g.Sfull, f, nullptr, nullptr, nullptr, g.meta, s),
                     "pathwise_sample");
 }
 
@@ -321,7 +328,7 @@ int vgpmp_elbo_fwd_bwd(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_para
   {
     StageSpan sp(h, ST_PATHWISE, s);
     if ((rc = check_cuda(h, launch_pathwise(h, *dims, *p, *r, p->X, dims->num_timesteps, g.Lc, g.Sfull, f,
-                                            bwd ? g.v : nullptr, bwd ? g.f0 : nullptr, bwd ? g.h0 : nullptr, s),
+                                            bwd ? g.v : nullptr, bwd ? g.f0 : nullptr, bwd ? g.h0 : nullptr, g.meta, s),
                          "pathwise")))
       return rc;
   }

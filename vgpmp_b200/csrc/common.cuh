@@ -46,6 +46,7 @@ struct vgpmp_handle {
   uint64_t launches = 0;
   std::string err;
   // stage profiling (bench.py): event pairs recorded on the launching stream
+  bool allow_grid_path = true;  // equispaced rank-1 fast path of the pathwise sampler (vgpmp_set_option)
   bool profiling = false;
   struct Span { int stage; cudaEvent_t a, b; };
   std::vector<Span> spans;
@@ -73,6 +74,7 @@ struct GpScratch {  // carved from the caller's workspace by cabi.cu
   double* f;       // [Bp,S,N,D]
   double* df;      // [Bp,S,N,D]
   double* logp;    // [Bp,S,N]
+  double* meta;    // [8] input-structure probe {grid flag, t0, dt, z0, dz}
 };
 
 cudaError_t launch_kuu(vgpmp_handle* h, const double* Z, const double* ls, const double* var, double jitter, double* K,
@@ -83,7 +85,7 @@ cudaError_t launch_gp_prepare(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_
                               double* kl_l, double* kvec, cudaStream_t s);
 cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
                             const double* Xq, int Nq, const double* Lc, const double* Sfull, double* f, double* v,
-                            double* f0, double* h0, cudaStream_t s);
+                            double* f0, double* h0, double* meta, cudaStream_t s);
 cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
                                const GpScratch& ws, const vgpmp_grads& g, cudaStream_t s);
 cudaError_t launch_elbo_reduce(vgpmp_handle* h, const vgpmp_dims& d, const double* logp, const double* kl_l,

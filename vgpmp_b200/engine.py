@@ -122,6 +122,9 @@ class Engine:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
+    def set_option(self, name: str, value: int):
+        self._chk(self.lib.vgpmp_set_option(self.h, name.encode(), int(value)), "set_option")
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.vgpmp_launch_count(self.h))
