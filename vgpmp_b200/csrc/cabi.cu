@@ -153,22 +153,34 @@ int vgpmp_create(vgpmp_handle** out, int device, const vgpmp_robot_desc* robot, 
     for (int k = 0; k < 3; ++k) r.sphere_off[p][k] = robot->sphere_offsets[3 * p + k];
     r.sphere_rad[p] = robot->sphere_radii[p];
   }
+  for (int k = 0; k <= r.dof; ++k) {
+    int end = 0;
+    while (end < r.num_spheres && r.sphere_frame[end] <= k) ++end;
+    r.frame_end[k] = end;
+  }
   h->lik.sigma_obs = lik->sigma_obs; h->lik.epsilon = lik->epsilon; h->lik.alpha = lik->alpha;
   h->lik.jitter = lik->jitter;
   for (int k = 0; k < 3; ++k) h->lik.offset[k] = lik->scene_offset[k];
 
   const size_t cells = (size_t)sdf->nx * sdf->ny * sdf->nz;
-  if ((e = cudaMalloc(&h->grid_dev, cells * sizeof(double))) != cudaSuccess ||
-      (e = cudaMemcpy(h->grid_dev, sdf->data, cells * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) {
-    std::string msg = std::string("SDF upload: ") + cudaGetErrorString(e);
-    if (h->grid_dev) cudaFree(h->grid_dev);
-    delete h;
-    return fail(nullptr, VGPMP_ERR_CUDA, msg);
-  }
-  h->sdf.grid = h->grid_dev;
   h->sdf.nx = sdf->nx; h->sdf.ny = sdf->ny; h->sdf.nz = sdf->nz;
   for (int k = 0; k < 3; ++k) h->sdf.origin[k] = sdf->origin[k];
   h->sdf.delta = sdf->delta;
+  h->sdf.inv_delta = 1.0 / sdf->delta;
+  // upload the raw grid, expand it into {value, gradient} records (see SdfDev), release the raw copy
+  double* raw = nullptr;
+  if ((e = cudaMalloc(&raw, cells * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(&h->rec_dev, cells * sizeof(double4))) != cudaSuccess ||
+      (e = cudaMemcpy(raw, sdf->data, cells * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = launch_sdf_build(h, raw, nullptr)) != cudaSuccess || (e = cudaDeviceSynchronize()) != cudaSuccess) {
+    std::string msg = std::string("SDF upload: ") + cudaGetErrorString(e);
+    if (raw) cudaFree(raw);
+    if (h->rec_dev) cudaFree(h->rec_dev);
+    delete h;
+    return fail(nullptr, VGPMP_ERR_CUDA, msg);
+  }
+  cudaFree(raw);
+  h->sdf.rec = h->rec_dev;
   *out = h;
   return VGPMP_OK;
 }
@@ -213,7 +225,7 @@ int vgpmp_destroy(vgpmp_handle* h) {
   cudaSetDevice(h->device);
   for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
-  if (h->grid_dev) cudaFree(h->grid_dev);
+  if (h->rec_dev) cudaFree(h->rec_dev);
   delete h;
   return VGPMP_OK;
 }

@@ -19,16 +19,21 @@ struct RobotDev {
   double lo[VGPMP_MAX_DOF], hi[VGPMP_MAX_DOF];
   double base[12];                  // rows 0..2 of the 4x4 base pose
   int sphere_frame[VGPMP_MAX_SPHERES];
+  int frame_end[VGPMP_MAX_DOF + 2];  // spheres of frame k are [frame_end[k-1], frame_end[k])
   double sphere_off[VGPMP_MAX_SPHERES][3];
   double sphere_rad[VGPMP_MAX_SPHERES];
 };
 
+// The SDF lives in HBM as one 32-byte record per voxel: {value, d/dx, d/dy, d/dz} with the reference's clipped central
+// differences and its "exact zero -> 0.1" rule already applied (they depend only on the grid and the voxel index, so
+// hoisting them to vgpmp_create is bit-identical to evaluating the 7-point stencil at lookup time).  One sphere-SDF
+// evaluation = one aligned 256-bit load = one DRAM sector, instead of seven scattered 8-byte gathers.
 struct SdfDev {
-  const double* grid;  // [nx,ny,nz], z fastest
+  const double4* rec;  // [nx,ny,nz] records, z fastest
   int nx, ny, nz, pad_;
   double origin[3];
   double delta;
-  double inv_2delta_unused;
+  double inv_delta;   // 1/delta (index fast path, see voxel_index)
 };
 
 struct LikDev {
@@ -42,7 +47,7 @@ struct vgpmp_handle {
   RobotDev robot{};
   SdfDev sdf{};
   LikDev lik{};
-  double* grid_dev = nullptr;
+  double4* rec_dev = nullptr;
   uint64_t launches = 0;
   std::string err;
   // stage profiling (bench.py): event pairs recorded on the launching stream
@@ -58,6 +63,7 @@ enum VgStage { ST_RNG = 0, ST_PREPARE, ST_PATHWISE, ST_LOGLIK, ST_REDUCE, ST_BAC
 // ---- launchers implemented in kinematics.cu -------------------------------------------------
 cudaError_t launch_fk_frames(vgpmp_handle* h, const double* joints, double* frames, int64_t n, cudaStream_t s);
 cudaError_t launch_fk_spheres(vgpmp_handle* h, const double* joints, double* centres, int64_t n, cudaStream_t s);
+cudaError_t launch_sdf_build(vgpmp_handle* h, const double* raw_dev, cudaStream_t s);
 cudaError_t launch_sdf_lookup(vgpmp_handle* h, const double* pts, double* dist, double* grad, int64_t n, cudaStream_t s);
 cudaError_t launch_loglik(vgpmp_handle* h, const double* in, int squash, double upstream, double* logp, double* d_in,
                           int64_t n, cudaStream_t s);

@@ -15,6 +15,8 @@
 // shared memory; triangular solves are warp-per-right-hand-side with the running vector in registers and the pivot
 // broadcast by shuffle.  Matrices in shared memory use a row stride of 33 doubles so that both row and column walks
 // are bank-conflict free.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -360,12 +362,13 @@ __global__ void __launch_bounds__(256) analyze_grid_kernel(int D, int M, int Nq,
 // The second half (update + Kfu v) is shared with the general kernel.
 // ---------------------------------------------------------------------------------------------
 constexpr int kGB = 32;   // bases per tile
-constexpr int kXT = 4;    // points per phase-2 thread
 
 __device__ __forceinline__ void pathwise_update_tail(const PathwiseArgs& a, int pl, int p, int l, int s0, int ns,
                                                      const double* f0s, int XP, const double* Lsm, const double* Ssm,
-                                                     const double* Kfu, double* vs, const double* mu, double sqrtj) {
+                                                     int lds, const double* Kfu, double* vs, const double* mu,
+                                                     double sqrtj) {
   // f0s[i*XP + x]: prior draw of sample s0+i at point x (x < Nq: query points, then the Mp inducing points)
+  // Ssm: q_sqrt_full with leading dimension lds (shared or global memory)
   const int Mp = a.M + 2, Nq = a.Nq, S = a.S, D = a.D;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
   for (int i = warp; i < ns; i += nw) {
@@ -374,7 +377,7 @@ __device__ __forceinline__ void pathwise_update_tail(const PathwiseArgs& a, int 
     double r = 0.0;
     if (lane < Mp) {
       double u = mu[lane];
-      for (int k = 0; k <= lane; ++k) u += Ssm[lane * LDM + k] * eu[k];
+      for (int k = 0; k <= lane; ++k) u += Ssm[lane * lds + k] * eu[k];
       r = u - f0s[(size_t)i * XP + Nq + lane] - sqrtj * a.eps_j[((size_t)pl * S + s) * Mp + lane];
     }
     const double y = warp_fwd_subst(Lsm, Mp, r);
@@ -392,23 +395,44 @@ __device__ __forceinline__ void pathwise_update_tail(const PathwiseArgs& a, int 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, const double* __restrict__ meta, int AP) {
+// one chunk of an equispaced run: points first..first+count-1 of the grid g0 + k*dg, written at column col0 + k
+__device__ __forceinline__ void rotate_run(double* fc, double* fd, int col0, int first, int count, double g0, double dg,
+                                           double c, double tau, double amp, double inv_ell) {
+  if (count <= 0) return;
+  double sn, cs, sd, cd;
+  const double tn = g0 + dg * first;
+  sincos(tn * c + tau, &sn, &cs);
+  sincos(dg * c, &sd, &cd);
+  cs *= amp; sn *= amp;
+  double q = tn * c * inv_ell;
+  const double dq = dg * c * inv_ell;
+  for (int k = 0; k < count; ++k) {
+    fc[col0 + first + k] = cs;
+    fd[col0 + first + k] = sn * q;      // d/d lengthscale of amp cos(t c + tau), c = sum(omega)/lengthscale
+    const double c2 = cs * cd - sn * sd;
+    sn = sn * cd + cs * sd;
+    cs = c2;
+    q += dq;
+  }
+}
+
+template <int XT>
+__global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, const double* __restrict__ meta) {
   if (meta[0] == 0.0) return;  // inputs are not an equispaced rank-1 grid: the general kernel does the work
   extern __shared__ __align__(16) double sm[];
   const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, B = a.B, A = Nq + Mp;
   const int pl = blockIdx.x, p = pl / D, l = pl % D;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
-  const int XG = (A + kXT - 1) / kXT, XP = XG * kXT;
+  const int XG = (A + XT - 1) / XT, XP = XG * XT, AP = XP | 1;   // odd row stride: conflict-free column walks
   // main-loop view of shared memory
   double* feat = sm;                                  // [2][kGB][AP]
-  double* Wt = feat + (size_t)2 * kGB * AP;           // [2 buffers][kGB][kST]
+  double* Wt = feat + (((size_t)2 * kGB * AP + 1) & ~(size_t)1);   // [2 buffers][kGB][kST], 16-byte aligned
   double* cb = Wt + 2 * kGB * kST;                    // [2][kGB] c_b = sum_d omega_bd / lengthscale
   double* tb = cb + 2 * kGB;                          // [2][kGB] tau_b
-  // tail view (after the base loop the feature tile is dead): red | Lsm | Ssm | Kfu | vs | mu | zy
-  double* red = sm;                                   // [2 slices][2][kST][XP]
+  // tail view (after the base loop the feature tile is dead): red | Lsm | Kfu | vs | mu | zy
+  double* red = sm;                                   // [KS][2][kST][XP]
   double* Lsm = red + (size_t)2 * 2 * kST * XP;
-  double* Ssm = Lsm + 32 * LDM;
-  double* Kfu = Ssm + 32 * LDM;                       // [Nq][Mp]
+  double* Kfu = Lsm + 32 * LDM;                       // [Nq][Mp]
   double* vs = Kfu + (size_t)Nq * Mp;                 // [kST][32]
   double* mu = vs + kST * 32;
   double* zy = mu + 32;
@@ -420,102 +444,88 @@ __global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, c
   const double* ta = a.tau + (size_t)pl * B;
   const double* wp = a.w + (size_t)pl * S * B;
 
-  // phase-1 role: lane = basis within the tile, warp = chunk of points (last chunk = the Mp inducing points)
-  const int nxc = nw - 1;                             // chunks over the query points
+  // phase-1 roles: lane = basis within the tile; warps 0..nxc-1 walk chunks of the query grid, the last two warps
+  // walk the inducing points (conditioned endpoints + first half of Z | second half of Z)
+  const int nxc = nw - 2;
   const int per = (Nq + nxc - 1) / nxc;
-  // phase-2 role
-  const int KS = (2 * 2 * XG <= nt) ? 2 : 1;          // split the tile's bases over two thread groups when they fit
+  const int mhalf = (M + 1) / 2;
+  // phase-2 roles: thread = (base slice ks, cos|dl feature, point group xg); its XT points are xg + i*XG
+  const int KS = max(1, min(4, nt / (2 * XG)));
   const bool worker = tid < 2 * KS * XG;
   const int xg = tid % XG, which = (tid / XG) & 1, ks = tid / (2 * XG);
-  const int bper = kGB / KS;
+  const int bper = (kGB + KS - 1) / KS;
 
   for (int s0 = 0; s0 < S; s0 += kST) {
     const int ns = min(kST, S - s0);
-    double acc[kXT][kST];
+    double acc[XT][kST];
 #pragma unroll
-    for (int i = 0; i < kXT; ++i)
+    for (int i = 0; i < XT; ++i)
 #pragma unroll
       for (int j = 0; j < kST; ++j) acc[i][j] = 0.0;
 
+    // staging registers: this thread's share of the next tile's operands (prefetched one tile ahead)
+    double st_c = 0.0, st_t = 0.0, st_w[2] = {0.0, 0.0};
+    auto prefetch = [&](int b0) {
+      const int nb = min(kGB, B - b0);
+      st_c = 0.0; st_t = 0.0;
+      if (tid < kGB && tid < nb) {
+        for (int d = 0; d < D; ++d) st_c += om[(size_t)(b0 + tid) * D + d];
+        st_c *= inv_ell;
+        st_t = ta[b0 + tid];
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int idx = tid + k * nt;       // kGB*kST = 256 elements, nt >= 128
+        const int i = idx / kGB, b = idx % kGB;
+        st_w[k] = (idx < kGB * kST && i < ns && b < nb) ? wp[(size_t)(s0 + i) * B + b0 + b] : 0.0;
+      }
+    };
+    prefetch(0);
     int buf = 0;
     for (int b0 = 0; b0 < B; b0 += kGB, buf ^= 1) {
-      const int nb = min(kGB, B - b0);
-      // stage this tile's weights / frequencies (other buffer than the tile still being contracted)
-      if (tid < kGB) {
-        double c = 0.0, t = 0.0;
-        if (tid < nb) {
-          for (int d = 0; d < D; ++d) c += om[(size_t)(b0 + tid) * D + d];
-          c *= inv_ell;
-          t = ta[b0 + tid];
-        }
-        cb[buf * kGB + tid] = c; tb[buf * kGB + tid] = t;
+      if (tid < kGB) { cb[buf * kGB + tid] = st_c; tb[buf * kGB + tid] = st_t; }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int idx = tid + k * nt;
+        if (idx < kGB * kST) Wt[(buf * kGB + idx % kGB) * kST + idx / kGB] = st_w[k];
       }
-      for (int idx = tid; idx < kGB * kST; idx += nt) {  // W[b][s], coalesced over b
-        const int i = idx / kGB, b = idx % kGB;
-        Wt[(buf * kGB + b) * kST + i] = (i < ns && b < nb) ? wp[(size_t)(s0 + i) * B + b0 + b] : 0.0;
-      }
+      if (b0 + kGB < B) prefetch(b0 + kGB);   // lands while this tile is being processed
       __syncthreads();  // staging visible; previous tile's contraction finished -> feature tile is free
-      {  // phase 1: rotate (amp cos, amp sin) along the grid; q = (t c) / lengthscale advances by dq
+      {  // phase 1: features by rotation along the grid
         const double c = cb[buf * kGB + lane], tau = tb[buf * kGB + lane];
         double* fc = feat + (size_t)lane * AP;
         double* fd = feat + (size_t)(kGB + lane) * AP;
-        double sn, cs, sd, cd;
         if (warp < nxc) {
-          const int n0 = warp * per, n1 = min(Nq, n0 + per);
-          if (n0 < n1) {
-            const double tn = t0 + dt * n0;
-            sincos(tn * c + tau, &sn, &cs);
-            sincos(dt * c, &sd, &cd);
-            cs *= amp; sn *= amp;
-            double q = tn * c * inv_ell;
-            const double dq = dt * c * inv_ell;
-            for (int n = n0; n < n1; ++n) {
-              fc[n] = cs;
-              fd[n] = sn * q;
-              const double c2 = cs * cd - sn * sd;
-              sn = sn * cd + cs * sd;
-              cs = c2;
-              q += dq;
-            }
-          }
-        } else {
+          const int n0 = warp * per;
+          rotate_run(fc, fd, 0, n0, min(Nq, n0 + per) - n0, t0, dt, c, tau, amp, inv_ell);
+        } else if (warp == nxc) {
+          double sn, cs;
           sincos(tau, &sn, &cs);                       // Zy[0] = 0
           fc[Nq] = amp * cs; fd[Nq] = 0.0;
           sincos(c + tau, &sn, &cs);                   // Zy[1] = 1
           fc[Nq + 1] = amp * cs; fd[Nq + 1] = amp * sn * c * inv_ell;
-          sincos(z0 * c + tau, &sn, &cs);
-          sincos(dz * c, &sd, &cd);
-          cs *= amp; sn *= amp;
-          double q = z0 * c * inv_ell;
-          const double dq = dz * c * inv_ell;
-          for (int m = 0; m < M; ++m) {
-            fc[Nq + 2 + m] = cs;
-            fd[Nq + 2 + m] = sn * q;
-            const double c2 = cs * cd - sn * sd;
-            sn = sn * cd + cs * sd;
-            cs = c2;
-            q += dq;
-          }
+          rotate_run(fc, fd, Nq + 2, 0, mhalf, z0, dz, c, tau, amp, inv_ell);
+        } else {
+          rotate_run(fc, fd, Nq + 2, mhalf, M - mhalf, z0, dz, c, tau, amp, inv_ell);
         }
       }
       __syncthreads();
-      if (worker) {  // phase 2
-        const double* fsrc = feat + (size_t)which * kGB * AP + (size_t)xg * kXT;
+      if (worker) {  // phase 2: XT x kST register tile, features as conflict-free 64-bit loads, weights broadcast
+        const double* fsrc = feat + (size_t)which * kGB * AP + xg;
         const double* wsrc = Wt + (size_t)buf * kGB * kST;
-        const int bb0 = ks * bper, bb1 = bb0 + bper;
-#pragma unroll 4
+        const int bb0 = ks * bper, bb1 = min(kGB, bb0 + bper);
+#pragma unroll 2
         for (int b = bb0; b < bb1; ++b) {
-          const double2 f01 = *reinterpret_cast<const double2*>(fsrc + (size_t)b * AP);
-          const double2 f23 = *reinterpret_cast<const double2*>(fsrc + (size_t)b * AP + 2);
-          const double fv[kXT] = {f01.x, f01.y, f23.x, f23.y};
-          double wv[kST];
+          double fv[XT], wv[kST];
+#pragma unroll
+          for (int i = 0; i < XT; ++i) fv[i] = fsrc[(size_t)b * AP + i * XG];
 #pragma unroll
           for (int j = 0; j < kST; j += 2) {
             const double2 w2 = *reinterpret_cast<const double2*>(wsrc + b * kST + j);
             wv[j] = w2.x; wv[j + 1] = w2.y;
           }
 #pragma unroll
-          for (int i = 0; i < kXT; ++i)
+          for (int i = 0; i < XT; ++i)
 #pragma unroll
             for (int j = 0; j < kST; ++j) acc[i][j] += fv[i] * wv[j];
         }
@@ -525,28 +535,19 @@ __global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, c
     // publish red[ks][which][s][x] over the dead feature tile, load the tail operands behind it, fold the slices
     if (worker) {
 #pragma unroll
-      for (int i = 0; i < kXT; ++i)
+      for (int i = 0; i < XT; ++i)
 #pragma unroll
-        for (int j = 0; j < kST; ++j) red[((size_t)(ks * 2 + which) * kST + j) * XP + xg * kXT + i] = acc[i][j];
+        for (int j = 0; j < kST; ++j) red[((size_t)(ks * 2 + which) * kST + j) * XP + xg + i * XG] = acc[i][j];
     }
     if (tid < 32) {
       zy[tid] = tid < Mp ? zy_at(a.Z, D, l, tid) : 0.0;
       mu[tid] = tid >= Mp ? 0.0 : (tid < 2 ? a.query_latent[((size_t)p * 2 + tid) * D + l]
                                           : a.q_mu[((size_t)p * M + tid - 2) * D + l]);
     }
-    for (int idx = tid; idx < Mp * Mp; idx += nt) {
-      const int i = idx / Mp, j = idx % Mp;
-      Lsm[i * LDM + j] = a.Lc[(size_t)pl * Mp * Mp + idx];
-      Ssm[i * LDM + j] = a.Sfull[(size_t)pl * Mp * Mp + idx];
-    }
     __syncthreads();
-    for (int idx = tid; idx < Nq * Mp; idx += nt) {
-      const int n = idx / Mp, m = idx % Mp;
-      Kfu[idx] = s2 * vg_matern52(fabs(a.Xq[(size_t)n * D + l] - zy[m]) / ell);
-    }
     for (int idx = tid; idx < 2 * kST * XP; idx += nt) {
       double t = red[idx];
-      if (KS == 2) t += red[(size_t)2 * kST * XP + idx];
+      for (int k = 1; k < KS; ++k) t += red[(size_t)k * 2 * kST * XP + idx];
       red[idx] = t;
       const int wh = idx / (kST * XP), i = (idx / XP) % kST, xx = idx % XP;
       if (i < ns && xx < A) {
@@ -554,8 +555,15 @@ __global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, c
         if (dst != nullptr) dst[((size_t)pl * S + s0 + i) * A + xx] = t;
       }
     }
+    __syncthreads();  // slices 1.. of red are dead from here on: Lsm / Kfu live behind slice 1
+    for (int idx = tid; idx < Mp * Mp; idx += nt)
+      Lsm[(idx / Mp) * LDM + idx % Mp] = a.Lc[(size_t)pl * Mp * Mp + idx];
+    for (int idx = tid; idx < Nq * Mp; idx += nt) {
+      const int n = idx / Mp, m = idx % Mp;
+      Kfu[idx] = s2 * vg_matern52(fabs(a.Xq[(size_t)n * D + l] - zy[m]) / ell);
+    }
     __syncthreads();
-    pathwise_update_tail(a, pl, p, l, s0, ns, red, XP, Lsm, Ssm, Kfu, vs, mu, sqrtj);
+    pathwise_update_tail(a, pl, p, l, s0, ns, red, XP, Lsm, a.Sfull + (size_t)pl * Mp * Mp, Mp, Kfu, vs, mu, sqrtj);
   }
 }
 
@@ -848,14 +856,22 @@ __device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {  // (0,1), 53 
   const uint64_t x = ((uint64_t)hi << 32 | lo) >> 11;
   return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
 }
-// two independent N(0,1) from one Philox block
-__device__ __forceinline__ void normal2(uint64_t seed, uint64_t iter, uint32_t stream, uint64_t idx, double& z0, double& z1) {
+// Four independent N(0,1) from one Philox block.  The draws are random inputs, not arithmetic of the reference: the
+// Box-Muller transform runs in float32 on the SFU (32-bit uniforms, |z| < 6.7) and is widened to float64.  Parity
+// tests feed the *materialised* draws to the oracle, so this choice cannot leak into a parity result.
+__device__ __forceinline__ void normal4(uint64_t seed, uint64_t iter, uint32_t stream, uint64_t idx, double z[4]) {
   uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)iter, stream ^ ((uint32_t)(iter >> 32) << 8)};
   philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-  const double r = sqrt(-2.0 * log(u01(c[0], c[1])));
-  double sn, cs;
-  sincospi(2.0 * u01(c[2], c[3]), &sn, &cs);
-  z0 = r * cs; z1 = r * sn;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float u1 = ((float)c[2 * k] + 0.5f) * 2.3283064365386963e-10f;       // (0,1]
+    const float u2 = ((float)c[2 * k + 1] + 0.5f) * 2.3283064365386963e-10f;
+    const float r = sqrtf(-2.0f * __logf(fminf(u1, 0.99999994f)));
+    float sn, cs;
+    __sincosf(6.283185307179586f * u2, &sn, &cs);
+    z[2 * k] = (double)(r * cs);
+    z[2 * k + 1] = (double)(r * sn);
+  }
 }
 
 struct RngArgs {
@@ -865,28 +881,27 @@ struct RngArgs {
   double *omega, *tau, *w, *eps_u, *eps_j;
 };
 
-__global__ void rng_fill_kernel(RngArgs a) {
+__global__ void __launch_bounds__(256) rng_fill_kernel(RngArgs a) {
+  const size_t B4 = (a.B + 3) / 4, M2 = (a.Mp + 1) / 2;
   const size_t n_om = (size_t)a.Bp * a.D * a.B;            // one thread per basis row (gamma shared by the row)
-  const size_t n_w = (size_t)a.Bp * a.D * a.S * a.B;
-  const size_t n_e = (size_t)a.Bp * a.D * a.S * a.Mp;
+  const size_t n_w = (size_t)a.Bp * a.D * a.S * B4;        // one thread per 4 consecutive bases
+  const size_t n_e = (size_t)a.Bp * a.D * a.S * M2;        // one thread per 2 consecutive inducing rows (eps_u, eps_j)
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid < n_om) {
     if (a.omega == nullptr) return;
     const size_t b = gid % a.B, l = (gid / a.B) % a.D, p = gid / ((size_t)a.B * a.D) + a.problem_offset;
     const uint64_t key = (p * a.D + l) * a.B + b;
     // Gamma(5/2, rate 5/2) = chi^2_5 / 5  -> omega = z / sqrt(gamma): Matern-5/2 spectral density (Student-t_5)
-    double g[6];
-    normal2(a.seed, a.iteration, 1u, key * 3 + 0, g[0], g[1]);
-    normal2(a.seed, a.iteration, 1u, key * 3 + 1, g[2], g[3]);
-    normal2(a.seed, a.iteration, 1u, key * 3 + 2, g[4], g[5]);
-    const double gam = (g[0] * g[0] + g[1] * g[1] + g[2] * g[2] + g[3] * g[3] + g[4] * g[4]) / 5.0;
+    double z[16];
+    const int ncall = (5 + a.D + 3) / 4;                    // <= 4 for D <= 8
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k < ncall) normal4(a.seed, a.iteration, 1u, key * 4 + k, z + 4 * k);
+    const double gam = (z[0] * z[0] + z[1] * z[1] + z[2] * z[2] + z[3] * z[3] + z[4] * z[4]) / 5.0;
     const double rs = rsqrt(gam);
-    for (int d = 0; d < a.D; d += 2) {
-      double z0, z1;
-      normal2(a.seed, a.iteration, 2u, key * 4 + d / 2, z0, z1);
-      a.omega[gid * a.D + d] = z0 * rs;
-      if (d + 1 < a.D) a.omega[gid * a.D + d + 1] = z1 * rs;
-    }
+#pragma unroll
+    for (int d = 0; d < VGPMP_MAX_DOF; ++d)
+      if (d < a.D) a.omega[gid * a.D + d] = z[5 + d] * rs;
     uint32_t c[4] = {(uint32_t)key, (uint32_t)(key >> 32), (uint32_t)a.iteration, 3u};
     philox4x32(c, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
     a.tau[gid] = 6.283185307179586476925 * u01(c[0], c[1]);
@@ -895,24 +910,33 @@ __global__ void rng_fill_kernel(RngArgs a) {
   size_t e = gid - n_om;
   if (e < n_w) {
     if (a.w == nullptr) return;
-    const size_t b = e % a.B, s = (e / a.B) % a.S + a.sample_offset, l = (e / ((size_t)a.B * a.S)) % a.D;
-    const size_t p = e / ((size_t)a.B * a.S * a.D) + a.problem_offset;
-    const uint64_t key = ((p * a.D + l) * (uint64_t)(1u << 24) + s) * a.B + b;  // sample index < 2^24
-    double z0, z1;
-    normal2(a.seed, a.iteration, 4u, key, z0, z1);
-    a.w[e] = z0;
+    const size_t b4 = e % B4, sl = (e / B4) % a.S, l = (e / (B4 * a.S)) % a.D, pl_ = e / (B4 * a.S * a.D);
+    const size_t s = sl + a.sample_offset, p = pl_ + a.problem_offset;
+    const uint64_t key = ((p * a.D + l) * (uint64_t)(1u << 24) + s) * B4 + b4;  // sample index < 2^24
+    double z[4];
+    normal4(a.seed, a.iteration, 4u, key, z);
+    double* dst = a.w + ((pl_ * a.D + l) * a.S + sl) * a.B + b4 * 4;
+    if (b4 * 4 + 4 <= (size_t)a.B && (a.B & 1) == 0) {
+      reinterpret_cast<double2*>(dst)[0] = make_double2(z[0], z[1]);
+      reinterpret_cast<double2*>(dst)[1] = make_double2(z[2], z[3]);
+    } else {
+      for (int k = 0; k < 4; ++k)
+        if (b4 * 4 + k < (size_t)a.B) dst[k] = z[k];
+    }
     return;
   }
   e -= n_w;
   if (e < n_e) {
     if (a.eps_u == nullptr) return;
-    const size_t m = e % a.Mp, s = (e / a.Mp) % a.S + a.sample_offset, l = (e / ((size_t)a.Mp * a.S)) % a.D;
-    const size_t p = e / ((size_t)a.Mp * a.S * a.D) + a.problem_offset;
-    const uint64_t key = ((p * a.D + l) * (uint64_t)(1u << 24) + s) * 32 + m;
-    double z0, z1;
-    normal2(a.seed, a.iteration, 5u, key, z0, z1);
-    a.eps_u[e] = z0;
-    a.eps_j[e] = z1;
+    const size_t m2 = e % M2, sl = (e / M2) % a.S, l = (e / (M2 * a.S)) % a.D, pl_ = e / (M2 * a.S * a.D);
+    const size_t s = sl + a.sample_offset, p = pl_ + a.problem_offset;
+    const uint64_t key = ((p * a.D + l) * (uint64_t)(1u << 24) + s) * 16 + m2;
+    double z[4];
+    normal4(a.seed, a.iteration, 5u, key, z);
+    const size_t o = ((pl_ * a.D + l) * a.S + sl) * a.Mp + m2 * 2;
+    a.eps_u[o] = z[0];
+    a.eps_j[o] = z[2];
+    if (m2 * 2 + 1 < (size_t)a.Mp) { a.eps_u[o + 1] = z[1]; a.eps_j[o + 1] = z[3]; }
   }
 }
 
@@ -959,28 +983,46 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
   a.Lc = Lc; a.Sfull = Sfull; a.f = f; a.v = v; a.f0 = f0; a.h0 = h0;
   cudaError_t e;
   // fast path: equispaced rank-1 inputs (decided on the device, see analyze_grid_kernel)
-  const int XGq = (A + kXT - 1) / kXT;
-  const bool grid_ok = h->allow_grid_path && 2 * XGq <= 256 && Nq >= 2 && a.M >= 2 &&
-                       sizeof(double) * ((size_t)2 * 2 * kST * XGq * kXT + 2 * 32 * LDM + (size_t)Nq * Mp + kST * 32 + 64) <= 200 * 1024;
+  int XT = 3, threads = 128;
+  {
+    // pick the points-per-thread / CTA size that keeps every warp busy in the contraction phase
+    double best = -1.0;
+    for (int nt : {128, 256})
+      for (int xt : {3, 4}) {
+        const int xg = (A + xt - 1) / xt;
+        if (2 * xg > nt) continue;
+        const int ks = std::max(1, std::min(4, nt / (2 * xg)));
+        const double fill = (double)(2 * ks * xg) / nt - (nt == 256 ? 0.05 : 0.0) - (xt == 3 ? 0.0 : 0.01);
+        if (fill > best) { best = fill; XT = xt; threads = nt; }
+      }
+    if (best < 0) XT = 0;
+  }
+  bool grid_ok = h->allow_grid_path && XT != 0 && Nq >= 2 && a.M >= 2;
+  size_t smem_g = 0;
+  if (grid_ok) {
+    const int XGq = (A + XT - 1) / XT, XP = XGq * XT, AP = XP | 1;
+    const size_t main_view = (((size_t)2 * kGB * AP + 1) & ~(size_t)1) + 2 * kGB * kST + 4 * kGB;
+    const size_t tail_view = (size_t)2 * 2 * kST * XP + 32 * LDM + (size_t)Nq * Mp + kST * 32 + 64;
+    const int ks = std::max(1, std::min(4, threads / (2 * XGq)));
+    const size_t red_view = (size_t)ks * 2 * kST * XP;
+    smem_g = sizeof(double) * std::max(std::max(main_view, tail_view), red_view);
+    grid_ok = smem_g <= 200 * 1024;
+  }
   if (grid_ok) {
     analyze_grid_kernel<<<1, 256, 0, s>>>(a.D, a.M, Nq, Xq, p.Z, meta);
-    const int threads = (2 * 2 * XGq <= 128) ? 128 : 256;
-    const int A4 = XGq * kXT, AP = A4 + 2;
-    const size_t main_view = (size_t)2 * kGB * AP + 2 * kGB * kST + 4 * kGB;
-    const size_t tail_view = (size_t)2 * 2 * kST * A4 + 2 * 32 * LDM + (size_t)Nq * Mp + kST * 32 + 64;
-    const size_t smem_g = sizeof(double) * (main_view > tail_view ? main_view : tail_view);
-    if ((e = cudaFuncSetAttribute(pathwise_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g)) != cudaSuccess)
+    auto kern = XT == 3 ? pathwise_grid_kernel<3> : pathwise_grid_kernel<4>;
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g)) != cudaSuccess)
       return e;
-    pathwise_grid_kernel<<<d.num_problems * a.D, threads, smem_g, s>>>(a, meta, AP);
+    kern<<<d.num_problems * a.D, threads, smem_g, s>>>(a, meta);
     h->launches += 2;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
-  const int threads = 32 * a.XG * a.KS;
+  const int threads_gen = 32 * a.XG * a.KS;
   const size_t smem = sizeof(double) * ((size_t)a.KS * 2 * kST * a.XG * 32 + 2 * 32 * LDM + (size_t)Nq * Mp + kST * 32 + 64);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   e = cudaFuncSetAttribute(pathwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  pathwise_kernel<<<d.num_problems * a.D, threads, smem, s>>>(a, grid_ok ? meta : nullptr);
+  pathwise_kernel<<<d.num_problems * a.D, threads_gen, smem, s>>>(a, grid_ok ? meta : nullptr);
   h->launches++;
   return cudaGetLastError();
 }
@@ -1029,7 +1071,8 @@ cudaError_t launch_rng_fill(vgpmp_handle* h, const vgpmp_dims& d, uint64_t seed,
   a.D = h->robot.dof; a.B = d.num_bases; a.S = d.num_samples; a.Mp = d.num_inducing + 2; a.Bp = d.num_problems;
   a.problem_offset = problem_offset; a.sample_offset = sample_offset; a.seed = seed; a.iteration = iteration;
   a.omega = omega; a.tau = tau; a.w = w; a.eps_u = eps_u; a.eps_j = eps_j;
-  const size_t n_om = (size_t)a.Bp * a.D * a.B, n_w = (size_t)a.Bp * a.D * a.S * a.B, n_e = (size_t)a.Bp * a.D * a.S * a.Mp;
+  const size_t n_om = (size_t)a.Bp * a.D * a.B, n_w = (size_t)a.Bp * a.D * a.S * ((a.B + 3) / 4),
+               n_e = (size_t)a.Bp * a.D * a.S * ((a.Mp + 1) / 2);
   const size_t total = n_om + n_w + n_e;
   rng_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a);
   h->launches++;

@@ -69,39 +69,61 @@ __device__ __forceinline__ int clamp_index(double q, int n) {
   return min(max(i, 0), n - 1);
 }
 
+// trunc((a)/delta) exactly as the reference computes it (a correctly rounded float64 division, then truncation), but
+// without paying for a division per axis per sphere: a * (1/delta) is within 2 ulp of a/delta, so the two can only
+// truncate differently when the product sits within a few ulp of an integer -- only then is the true division done.
+__device__ __forceinline__ int voxel_index(double a, double delta, double inv_delta, int n) {
+  double q = a * inv_delta;
+  const double k = rint(q);
+  if (fabs(q - k) <= 8.0 * 2.220446049250313e-16 * fabs(k)) q = a / delta;  // (also taken at k == 0 only if q == 0)
+  return clamp_index(q, n);
+}
+
 struct Voxel {
   int ix, iy, iz;
 };
 
 __device__ __forceinline__ Voxel sdf_voxel(const SdfDev& s, double x, double y, double z) {
   Voxel v;
-  v.ix = clamp_index((x - s.origin[0]) / s.delta, s.nx);
-  v.iy = clamp_index((y - s.origin[1]) / s.delta, s.ny);
-  v.iz = clamp_index((z - s.origin[2]) / s.delta, s.nz);
+  v.ix = voxel_index(x - s.origin[0], s.delta, s.inv_delta, s.nx);
+  v.iy = voxel_index(y - s.origin[1], s.delta, s.inv_delta, s.ny);
+  v.iz = voxel_index(z - s.origin[2], s.delta, s.inv_delta, s.nz);
   return v;
 }
 
-__device__ __forceinline__ double sdf_at(const SdfDev& s, int ix, int iy, int iz) {
-  return __ldg(s.grid + ((size_t)ix * s.ny + iy) * s.nz + iz);
+__device__ __forceinline__ size_t sdf_cell(const SdfDev& s, int ix, int iy, int iz) {
+  return ((size_t)ix * s.ny + iy) * s.nz + iz;
 }
 
-// value + gradient: the 7-point stencil of one sphere-SDF evaluation (7 grid elements = 56 B algorithmic)
-__device__ __forceinline__ double sdf_value_grad(const SdfDev& s, double x, double y, double z, double g[3]) {
-  const Voxel v = sdf_voxel(s, x, y, z);
-  const int xp = min(v.ix + 1, s.nx - 1), xm = max(v.ix - 1, 0);
-  const int yp = min(v.iy + 1, s.ny - 1), ym = max(v.iy - 1, 0);
-  const int zp = min(v.iz + 1, s.nz - 1), zm = max(v.iz - 1, 0);
-  // issue all seven loads before any use
-  const double c = sdf_at(s, v.ix, v.iy, v.iz);
-  const double ax = sdf_at(s, xp, v.iy, v.iz), bx = sdf_at(s, xm, v.iy, v.iz);
-  const double ay = sdf_at(s, v.ix, yp, v.iz), by = sdf_at(s, v.ix, ym, v.iz);
-  const double az = sdf_at(s, v.ix, v.iy, zp), bz = sdf_at(s, v.ix, v.iy, zm);
-  const double den = 2.0 * s.delta;
-  double gx = (ax - bx) / den, gy = (ay - by) / den, gz = (az - bz) / den;
-  g[0] = (gx == 0.0) ? 0.1 : gx;  // sdf_utils.py:124,129,135
-  g[1] = (gy == 0.0) ? 0.1 : gy;
-  g[2] = (gz == 0.0) ? 0.1 : gz;
-  return c;
+__device__ __forceinline__ double sdf_value(const SdfDev& s, const Voxel& v) {
+  return __ldg(reinterpret_cast<const double*>(s.rec + sdf_cell(s, v.ix, v.iy, v.iz)));
+}
+
+// one sphere-SDF evaluation: value + stencil gradient in a single 256-bit read-only load (LDG.E.256, sm_100+)
+__device__ __forceinline__ double4 sdf_record(const SdfDev& s, const Voxel& v) {
+  double4 r;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+      : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
+      : "l"(s.rec + sdf_cell(s, v.ix, v.iy, v.iz)));
+  return r;
+}
+
+// Builds the records from the raw grid: sdf_utils.py:100-136 verbatim per voxel (clipped neighbours, /(2 delta), 0 -> 0.1)
+__global__ void __launch_bounds__(256) sdf_build_kernel(const double* __restrict__ raw, double4* __restrict__ rec,
+                                                       int nx, int ny, int nz, double delta) {
+  const size_t cells = (size_t)nx * ny * nz;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cells) return;
+  const int iz = (int)(i % nz), iy = (int)((i / nz) % ny), ix = (int)(i / ((size_t)nz * ny));
+  auto at = [&](int x, int y, int z) { return raw[((size_t)x * ny + y) * nz + z]; };
+  const double den = 2.0 * delta;
+  double gx = (at(min(ix + 1, nx - 1), iy, iz) - at(max(ix - 1, 0), iy, iz)) / den;
+  double gy = (at(ix, min(iy + 1, ny - 1), iz) - at(ix, max(iy - 1, 0), iz)) / den;
+  double gz = (at(ix, iy, min(iz + 1, nz - 1)) - at(ix, iy, max(iz - 1, 0))) / den;
+  gx = (gx == 0.0) ? 0.1 : gx;  // sdf_utils.py:124,129,135
+  gy = (gy == 0.0) ? 0.1 : gy;
+  gz = (gz == 0.0) ? 0.1 : gz;
+  rec[i] = make_double4(raw[i], gx, gy, gz);
 }
 
 __global__ void __launch_bounds__(kThreads) fk_frames_kernel(RobotDev rb, const double* __restrict__ joints,
@@ -149,14 +171,13 @@ __global__ void __launch_bounds__(kThreads) sdf_lookup_kernel(SdfDev sdf, const 
                                                              int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (i >= n) return;
-  const double x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+  const Voxel v = sdf_voxel(sdf, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
   if (grad != nullptr) {
-    double g[3];
-    dist[i] = sdf_value_grad(sdf, x, y, z, g);
-    grad[3 * i] = g[0]; grad[3 * i + 1] = g[1]; grad[3 * i + 2] = g[2];
+    const double4 r = sdf_record(sdf, v);
+    dist[i] = r.x;
+    grad[3 * i] = r.y; grad[3 * i + 1] = r.z; grad[3 * i + 2] = r.w;
   } else {
-    const Voxel v = sdf_voxel(sdf, x, y, z);
-    dist[i] = sdf_at(sdf, v.ix, v.iy, v.iz);
+    dist[i] = sdf_value(sdf, v);
   }
 }
 
@@ -167,105 +188,124 @@ __device__ __forceinline__ double stable_sigmoid(double x) {
 }
 
 // Fused likelihood: squash -> FK -> spheres -> SDF stencil -> hinge -> logp, plus the reverse pass to the input.
-template <int D, bool BWD>
-__global__ void __launch_bounds__(kThreads) loglik_kernel(RobotDev rb, SdfDev sdf, LikDev lk,
+// Spheres of a frame are handled NB at a time: all NB record loads (one 256-bit load per sphere) are issued before the first
+// one is consumed.  The joint axes needed by the reverse pass (7 doubles per
+// joint) are parked in shared memory, [value][thread] so that a warp's accesses are contiguous.
+template <int NB>
+struct SphereBatch {
+  double x[NB], y[NB], z[NB];
+  double4 r[NB];  // {value, gx, gy, gz}
+};
+
+template <int D, bool BWD, int NB>
+__global__ void __launch_bounds__(kThreads, 4) loglik_kernel(RobotDev rb, SdfDev sdf, LikDev lk,
                                                          const double* __restrict__ in, int squash, double upstream,
                                                          double* __restrict__ logp, double* __restrict__ d_in,
                                                          int64_t n) {
-  const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  extern __shared__ double axes[];  // BWD only: [D][7][kThreads]  (axis z, axis x point n, prefix term)
+  const int tid = threadIdx.x;
+  const int64_t c = (int64_t)blockIdx.x * kThreads + tid;
   if (c >= n) return;
-
-  double th[D], dsq[D];
-#pragma unroll
-  for (int j = 0; j < D; ++j) {
-    const double x = in[c * D + j];
-    if (squash) {
-      const double s = stable_sigmoid(x);
-      const double span = rb.hi[j] - rb.lo[j];
-      th[j] = rb.lo[j] + span * s;
-      dsq[j] = span * s * (1.0 - s);
-    } else {
-      th[j] = x;
-      dsq[j] = 1.0;
-    }
-  }
 
   Frame A;
   frame_from_base(rb, A);
   double Fw[3] = {0.0, 0.0, 0.0}, Tw[3] = {0.0, 0.0, 0.0};  // running wrench of the spheres seen so far
-  double az[D][3], an[D][3], cj[D];                         // joint axis, axis x point, prefix term
   double lp = 0.0;
   const double inv_sigma = 1.0 / lk.sigma_obs;
   int p = 0;
 
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k <= D; ++k) {
     if (k > 0) {
       const int j = k - 1;
+      const double xin = in[c * D + j];
+      const double thj = squash ? rb.lo[j] + (rb.hi[j] - rb.lo[j]) * stable_sigmoid(xin) : xin;
+      double zx, zy, zz, ox, oy, oz;
       if (BWD && !rb.craig) {  // Spong: joint j turns about z of frame j-1, through its origin
-        az[j][0] = A.r[2]; az[j][1] = A.r[5]; az[j][2] = A.r[8];
-        an[j][0] = az[j][1] * A.t[2] - az[j][2] * A.t[1];
-        an[j][1] = az[j][2] * A.t[0] - az[j][0] * A.t[2];
-        an[j][2] = az[j][0] * A.t[1] - az[j][1] * A.t[0];
+        zx = A.r[2]; zy = A.r[5]; zz = A.r[8]; ox = A.t[0]; oy = A.t[1]; oz = A.t[2];
       }
-      frame_step(rb, j, th[j], A);
-      if (BWD && rb.craig) {   // Craig: joint j turns about z of frame j (its own frame), through its origin
-        az[j][0] = A.r[2]; az[j][1] = A.r[5]; az[j][2] = A.r[8];
-        an[j][0] = az[j][1] * A.t[2] - az[j][2] * A.t[1];
-        an[j][1] = az[j][2] * A.t[0] - az[j][0] * A.t[2];
-        an[j][2] = az[j][0] * A.t[1] - az[j][1] * A.t[0];
-      }
-      if (BWD)
-        cj[j] = az[j][0] * Tw[0] + az[j][1] * Tw[1] + az[j][2] * Tw[2] -
-                (an[j][0] * Fw[0] + an[j][1] * Fw[1] + an[j][2] * Fw[2]);
-    }
-    while (p < rb.num_spheres && rb.sphere_frame[p] == k) {
-      const double ox = rb.sphere_off[p][0], oy = rb.sphere_off[p][1], oz = rb.sphere_off[p][2];
-      const double x = A.r[0] * ox + A.r[1] * oy + A.r[2] * oz + A.t[0];
-      const double y = A.r[3] * ox + A.r[4] * oy + A.r[5] * oz + A.t[1];
-      const double z = A.r[6] * ox + A.r[7] * oy + A.r[8] * oz + A.t[2];
-      double g[3];
-      double dist;
+      frame_step(rb, j, thj, A);
       if (BWD) {
-        dist = sdf_value_grad(sdf, x - lk.offset[0], y - lk.offset[1], z - lk.offset[2], g);
-      } else {
-        const Voxel v = sdf_voxel(sdf, x - lk.offset[0], y - lk.offset[1], z - lk.offset[2]);
-        dist = sdf_at(sdf, v.ix, v.iy, v.iz);
+        if (rb.craig) {        // Craig: joint j turns about z of frame j (its own frame), through its origin
+          zx = A.r[2]; zy = A.r[5]; zz = A.r[8]; ox = A.t[0]; oy = A.t[1]; oz = A.t[2];
+        }
+        const double nx = zy * oz - zz * oy, ny = zz * ox - zx * oz, nz = zx * oy - zy * ox;
+        double* slot = axes + (size_t)j * 7 * kThreads + tid;
+        slot[0] = zx; slot[kThreads] = zy; slot[2 * kThreads] = zz;
+        slot[3 * kThreads] = nx; slot[4 * kThreads] = ny; slot[5 * kThreads] = nz;
+        slot[6 * kThreads] = zx * Tw[0] + zy * Tw[1] + zz * Tw[2] - (nx * Fw[0] + ny * Fw[1] + nz * Fw[2]);
       }
-      dist -= rb.sphere_rad[p];
-      const double hinge = fmax(lk.epsilon - dist, 0.0);
-      lp -= 0.5 * (hinge * inv_sigma) * hinge;
-      if (BWD && hinge > 0.0) {
-        // d logp / d dist = hinge / sigma; the custom gradient defines d dist / d x := stencil gradient
-        const double w = hinge * inv_sigma;
-        const double gx = w * g[0], gy = w * g[1], gz = w * g[2];
-        Fw[0] += gx; Fw[1] += gy; Fw[2] += gz;
-        Tw[0] += y * gz - z * gy;
-        Tw[1] += z * gx - x * gz;
-        Tw[2] += x * gy - y * gx;
+    }
+    const int pend = rb.frame_end[k];
+    for (p = (k == 0 ? 0 : rb.frame_end[k - 1]); p < pend; p += NB) {
+      SphereBatch<NB> sb;
+      // stage 1: positions, voxel indices, all loads
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        const int q = min(p + i, pend - 1);  // tail lanes of the batch repeat the last sphere (weight 0 below)
+        const double ox = rb.sphere_off[q][0], oy = rb.sphere_off[q][1], oz = rb.sphere_off[q][2];
+        sb.x[i] = A.r[0] * ox + A.r[1] * oy + A.r[2] * oz + A.t[0];
+        sb.y[i] = A.r[3] * ox + A.r[4] * oy + A.r[5] * oz + A.t[1];
+        sb.z[i] = A.r[6] * ox + A.r[7] * oy + A.r[8] * oz + A.t[2];
+        const Voxel v = sdf_voxel(sdf, sb.x[i] - lk.offset[0], sb.y[i] - lk.offset[1], sb.z[i] - lk.offset[2]);
+        if (BWD) sb.r[i] = sdf_record(sdf, v);
+        else sb.r[i].x = sdf_value(sdf, v);
       }
-      ++p;
+      // stage 2: hinge, log-probability, wrench
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        if (p + i < pend) {
+          const double dist = sb.r[i].x - rb.sphere_rad[p + i];
+          const double hinge = fmax(lk.epsilon - dist, 0.0);
+          lp -= 0.5 * (hinge * inv_sigma) * hinge;
+          if (BWD && hinge > 0.0) {
+            // d logp / d dist = hinge / sigma; the custom gradient defines d dist / d x := stencil gradient
+            double gx = sb.r[i].y, gy = sb.r[i].z, gz = sb.r[i].w;
+            const double w = hinge * inv_sigma;
+            gx *= w; gy *= w; gz *= w;
+            Fw[0] += gx; Fw[1] += gy; Fw[2] += gz;
+            Tw[0] += sb.y[i] * gz - sb.z[i] * gy;
+            Tw[1] += sb.z[i] * gx - sb.x[i] * gz;
+            Tw[2] += sb.x[i] * gy - sb.y[i] * gx;
+          }
+        }
+      }
     }
   }
   logp[c] = lp;
   if (BWD) {
 #pragma unroll
     for (int j = 0; j < D; ++j) {
-      const double dth = az[j][0] * Tw[0] + az[j][1] * Tw[1] + az[j][2] * Tw[2] -
-                         (an[j][0] * Fw[0] + an[j][1] * Fw[1] + an[j][2] * Fw[2]) - cj[j];
-      d_in[c * D + j] = upstream * dth * dsq[j];
+      const double* slot = axes + (size_t)j * 7 * kThreads + tid;
+      const double dth = slot[0] * Tw[0] + slot[kThreads] * Tw[1] + slot[2 * kThreads] * Tw[2] -
+                         (slot[3 * kThreads] * Fw[0] + slot[4 * kThreads] * Fw[1] + slot[5 * kThreads] * Fw[2]) -
+                         slot[6 * kThreads];
+      double dsq = 1.0;
+      if (squash) {
+        const double s = stable_sigmoid(in[c * D + j]);
+        dsq = (rb.hi[j] - rb.lo[j]) * s * (1.0 - s);
+      }
+      d_in[c * D + j] = upstream * dth * dsq;
     }
   }
 }
+
+constexpr int kSphereBatch = 2;
 
 template <int D>
 cudaError_t launch_loglik_d(vgpmp_handle* h, const double* in, int squash, double upstream, double* logp, double* d_in,
                             int64_t n, cudaStream_t s) {
   const unsigned blocks = (unsigned)((n + kThreads - 1) / kThreads);
-  if (d_in != nullptr)
-    loglik_kernel<D, true><<<blocks, kThreads, 0, s>>>(h->robot, h->sdf, h->lik, in, squash, upstream, logp, d_in, n);
-  else
-    loglik_kernel<D, false><<<blocks, kThreads, 0, s>>>(h->robot, h->sdf, h->lik, in, squash, upstream, logp, d_in, n);
+  if (d_in != nullptr) {
+    const size_t smem = sizeof(double) * D * 7 * kThreads;
+    auto kern = loglik_kernel<D, true, kSphereBatch>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<blocks, kThreads, smem, s>>>(h->robot, h->sdf, h->lik, in, squash, upstream, logp, d_in, n);
+  } else {
+    loglik_kernel<D, false, kSphereBatch><<<blocks, kThreads, 0, s>>>(h->robot, h->sdf, h->lik, in, squash, upstream,
+                                                                     logp, d_in, n);
+  }
   return cudaGetLastError();
 }
 
@@ -281,6 +321,14 @@ cudaError_t launch_fk_frames(vgpmp_handle* h, const double* joints, double* fram
 cudaError_t launch_fk_spheres(vgpmp_handle* h, const double* joints, double* centres, int64_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   fk_spheres_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, s>>>(h->robot, joints, centres, n);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sdf_build(vgpmp_handle* h, const double* raw_dev, cudaStream_t s) {
+  const size_t cells = (size_t)h->sdf.nx * h->sdf.ny * h->sdf.nz;
+  sdf_build_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(raw_dev, h->rec_dev, h->sdf.nx, h->sdf.ny, h->sdf.nz,
+                                                                  h->sdf.delta);
   h->launches++;
   return cudaGetLastError();
 }
