@@ -87,6 +87,11 @@ typedef struct {
   int32_t num_timesteps;/* N  */
   int32_t num_samples;  /* S  */
   int32_t num_bases;    /* B  */
+  /* Single-problem large-sample mode (samples sharded over GPUs): this call holds num_samples of
+   * total_samples Monte-Carlo samples and 1/kl_shards of the (replicated) KL term, so that SUMMING elbo and gradients
+   * over the shards (one NCCL all-reduce) gives exactly the unsharded result.  0 means "not sharded". */
+  int32_t total_samples;
+  int32_t kl_shards;
 } vgpmp_dims;
 
 /* Model state of a batch of planning problems (models/vgpmp.py:59-82,200-218,255-263). */

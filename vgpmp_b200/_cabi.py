@@ -30,7 +30,8 @@ class LikDesc(C.Structure):
 
 class Dims(C.Structure):
     _fields_ = [("num_problems", C.c_int32), ("num_inducing", C.c_int32), ("num_timesteps", C.c_int32),
-                ("num_samples", C.c_int32), ("num_bases", C.c_int32)]
+                ("num_samples", C.c_int32), ("num_bases", C.c_int32), ("total_samples", C.c_int32),
+                ("kl_shards", C.c_int32)]
 
 
 class Params(C.Structure):

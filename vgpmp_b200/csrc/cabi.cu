@@ -88,7 +88,11 @@ int check_dims(vgpmp_handle* h, const vgpmp_dims* d) {
     return fail(h, VGPMP_ERR_INVALID, "all dims must be >= 1");
   if (d->num_inducing + 2 > VGPMP_MAX_MP) return fail(h, VGPMP_ERR_INVALID, "num_inducing + 2 must be <= 32");
   if (d->num_timesteps + d->num_inducing + 2 > 768) return fail(h, VGPMP_ERR_INVALID, "num_timesteps + Mp must be <= 768");
-  if (d->num_samples >= (1 << 24)) return fail(h, VGPMP_ERR_INVALID, "num_samples must be < 2^24");
+  if (d->num_samples >= (1 << 24) || d->total_samples >= (1 << 24))
+    return fail(h, VGPMP_ERR_INVALID, "num_samples must be < 2^24");
+  if (d->total_samples != 0 && d->total_samples < d->num_samples)
+    return fail(h, VGPMP_ERR_INVALID, "total_samples must be 0 or >= num_samples");
+  if (d->kl_shards < 0) return fail(h, VGPMP_ERR_INVALID, "kl_shards must be >= 0");
   return VGPMP_OK;
 }
 
@@ -346,7 +350,7 @@ int vgpmp_elbo_fwd_bwd(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_para
   }
   {
     StageSpan sp(h, ST_LOGLIK, s);
-    if ((rc = check_cuda(h, launch_loglik(h, f, 1, h->lik.alpha / (double)dims->num_samples, logp,
+    if ((rc = check_cuda(h, launch_loglik(h, f, 1, h->lik.alpha / (double)(dims->total_samples > 0 ? dims->total_samples : dims->num_samples), logp,
                                           bwd ? g.df : nullptr, ncfg, s), "loglik")))
       return rc;
   }

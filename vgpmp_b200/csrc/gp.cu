@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, c
 // ---------------------------------------------------------------------------------------------
 struct BackwardArgs {
   int D, M, N, S, B;
-  double jitter;
+  double jitter, klw;
   const double *Z, *X, *ls, *var, *q_sqrt;
   const double *eps_u;
   const double *Lc, *kvec, *v, *f0, *h0, *df;
@@ -599,7 +599,8 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
   double* bvec = zy + 32;              // [32]
   double* gd = bvec + 32;              // [32]
   double* red = gd + 32;               // [8]
-  double* misc = red + 8;              // [8]
+  double* dft = red + 8;               // [kBT][N]  this tile's slice of d ELBO / d f
+  double* epsm = dft + (size_t)kBT * N; // [kBT][32] this tile's eps_u
 
   const double ell = a.ls[pl], s2 = a.var[pl];
   if (tid < 32) {
@@ -621,17 +622,27 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
 
   for (int s0 = 0; s0 < S; s0 += kBT) {
     const int ns = min(kBT, S - s0);
-    // (1) gv[s,m] = sum_n Kfu[n,m] df[s,n]   and stage v
+    // stage this tile's df (strided in global: [s,n,D]), v and eps_u in shared memory
+    for (int idx = tid; idx < kBT * N; idx += nt) {
+      const int i = idx / N, n = idx % N;
+      dft[idx] = i < ns ? dfp[((size_t)(s0 + i) * N + n) * D] : 0.0;
+    }
     for (int idx = tid; idx < kBT * 32; idx += nt) {
       const int i = idx >> 5, m = idx & 31;
-      double t = 0.0, vv = 0.0;
+      const bool ok = i < ns && m < Mp;
+      vsm[idx] = ok ? a.v[((size_t)pl * S + s0 + i) * Mp + m] : 0.0;
+      epsm[idx] = ok ? a.eps_u[((size_t)pl * S + s0 + i) * Mp + m] : 0.0;
+    }
+    __syncthreads();
+    // (1) gv[s,m] = sum_n Kfu[n,m] df[s,n]
+    for (int idx = tid; idx < kBT * 32; idx += nt) {
+      const int i = idx >> 5, m = idx & 31;
+      double t = 0.0;
       if (i < ns && m < Mp) {
-        const double* dfs = dfp + (size_t)(s0 + i) * N * D;
-        for (int n = 0; n < N; ++n) t += Kfu[n * Mp + m] * dfs[(size_t)n * D];
-        vv = a.v[((size_t)pl * S + s0 + i) * Mp + m];
+        const double* dfs = dft + (size_t)i * N;
+        for (int n = 0; n < N; ++n) t += Kfu[n * Mp + m] * dfs[n];
       }
       gv[idx] = t;
-      vsm[idx] = vv;
     }
     __syncthreads();
     // (3) gr = Khat^-1 gv (warp per sample)
@@ -645,7 +656,7 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
     for (int idx = tid; idx < N * Mp; idx += nt) {
       const int n = idx / Mp, m = idx % Mp;
       double t = 0.0;
-      for (int i = 0; i < ns; ++i) t += dfp[((size_t)(s0 + i) * N + n) * D] * vsm[i * 32 + m];
+      for (int i = 0; i < ns; ++i) t += dft[(size_t)i * N + n] * vsm[i * 32 + m];
       const double r = fabs(a.X[(size_t)n * D + l] - zy[m]) / ell;
       acc_var += t * vg_matern52(r);
       acc_ls += t * s2 * vg_matern52_dr(r) * (-r / ell);
@@ -657,7 +668,7 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
       for (int k = 0; k < ns; ++k) {
         const double g = gr[k * 32 + i];
         t += g * vsm[k * 32 + j];
-        u += g * a.eps_u[((size_t)pl * S + s0 + k) * Mp + j];
+        u += g * epsm[k * 32 + j];
       }
       G[i * LDM + j] -= t;
       GS[i * LDM + j] += u;
@@ -670,7 +681,7 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
     // (5) prior path: d f0(X) = df, d f0(Zy) = -gr
     for (int idx = tid; idx < ns * A; idx += nt) {
       const int i = idx / A, xx = idx % A;
-      const double g = xx < N ? dfp[((size_t)(s0 + i) * N + xx) * D] : -gr[i * 32 + xx - N];
+      const double g = xx < N ? dft[(size_t)i * N + xx] : -gr[i * 32 + xx - N];
       const size_t o = ((size_t)pl * S + s0 + i) * A + xx;
       acc_var += g * a.f0[o] / (2.0 * s2);
       acc_ls += g * a.h0[o];
@@ -687,7 +698,7 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
     if (c_ <= r_) {
       for (int i = r_ + 2; i < Mp; ++i) t += Lsm[i * LDM + r_ + 2] * GS[i * LDM + c_ + 2];
       const double qv = q[idx];
-      t -= qv - (r_ == c_ ? 1.0 / qv : 0.0);  // - d KL / d q_sqrt
+      t -= a.klw * (qv - (r_ == c_ ? 1.0 / qv : 0.0));  // - d KL / d q_sqrt
     }
     dq[idx] = t;
   }
@@ -702,7 +713,7 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
   __syncthreads();
   // (8) KL reverse: b = L^-1 d, KL = 0.5 sum_{i>=2} b_i^2 + ...;  ELBO carries -KL
   if (warp == 0) {
-    const double gb = (lane >= 2 && lane < Mp) ? -bvec[lane] : 0.0;
+    const double gb = (lane >= 2 && lane < Mp) ? -a.klw * bvec[lane] : 0.0;
     const double g = warp_bwd_subst(Lsm, Mp, gb);  // d ELBO / d d
     gd[lane] = lane < Mp ? g : 0.0;
   }
@@ -719,20 +730,27 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
     G[tid * LDM + 1] -= gd[tid] * c1;
   }
   __syncthreads();
-  if (tid == 0) {
-    // gc = Khat[:, :2]^T (-gd);  c = K22^-1 q~  ->  d K22 -= (K22^-1 gc) c^T
+  if (warp == 0) {
+    // gc = Khat[:, :2]^T (-gd);  c = K22^-1 q~  ->  d K22 -= (K22^-1 gc) c^T     (lane i owns row i of Khat[:, :2])
     double gc0 = 0.0, gc1 = 0.0;
-    for (int i = 0; i < Mp; ++i) {
-      const double k0 = s2 * vg_matern52(fabs(zy[i] - zy[0]) / ell) + (i == 0 ? a.jitter : 0.0);
-      const double k1 = s2 * vg_matern52(fabs(zy[i] - zy[1]) / ell) + (i == 1 ? a.jitter : 0.0);
-      gc0 -= k0 * gd[i];
-      gc1 -= k1 * gd[i];
+    if (lane < Mp) {
+      const double k0 = s2 * vg_matern52(fabs(zy[lane] - zy[0]) / ell) + (lane == 0 ? a.jitter : 0.0);
+      const double k1 = s2 * vg_matern52(fabs(zy[lane] - zy[1]) / ell) + (lane == 1 ? a.jitter : 0.0);
+      gc0 = -k0 * gd[lane];
+      gc1 = -k1 * gd[lane];
     }
-    const double l00 = Lsm[0], l10 = Lsm[LDM], l11 = Lsm[LDM + 1];
-    const double y0 = gc0 / l00, y1 = (gc1 - l10 * y0) / l11;
-    const double e1 = y1 / l11, e0 = (y0 - l10 * e1) / l00;
-    G[0] -= e0 * c0;       G[1] -= e0 * c1;
-    G[LDM] -= e1 * c0;     G[LDM + 1] -= e1 * c1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      gc0 += __shfl_xor_sync(kFull, gc0, o);
+      gc1 += __shfl_xor_sync(kFull, gc1, o);
+    }
+    if (lane == 0) {
+      const double l00 = Lsm[0], l10 = Lsm[LDM], l11 = Lsm[LDM + 1];
+      const double y0 = gc0 / l00, y1 = (gc1 - l10 * y0) / l11;
+      const double e1 = y1 / l11, e0 = (y0 - l10 * e1) / l00;
+      G[0] -= e0 * c0;       G[1] -= e0 * c1;
+      G[LDM] -= e1 * c0;     G[LDM + 1] -= e1 * c1;
+    }
   }
   __syncthreads();
   // (9) Cholesky reverse (Murray 2016): Khat_bar = L^-T Phi(L^T L_bar) L^-1, Phi = tril with halved diagonal
@@ -776,11 +794,11 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
     a.d_ls[pl] = tl;
   }
   if (tid >= 2 && tid < Mp) a.d_q_mu[((size_t)p * M + tid - 2) * D + l] = gmu[tid];
-  (void)misc;
 }
 
 // ELBO[p] = alpha/S * sum_{s,n} logp - sum_l KL_l      models/vgpmp.py:287-289
-__global__ void __launch_bounds__(256) elbo_reduce_kernel(int D, int SN, double scale, const double* __restrict__ logp,
+__global__ void __launch_bounds__(256) elbo_reduce_kernel(int D, int SN, double scale, double klw,
+                                                         const double* __restrict__ logp,
                                                          const double* __restrict__ kl_l, double* __restrict__ elbo,
                                                          double* __restrict__ kl_out) {
   __shared__ double red[8];
@@ -791,7 +809,7 @@ __global__ void __launch_bounds__(256) elbo_reduce_kernel(int D, int SN, double 
   if (threadIdx.x == 0) {
     double kl = 0.0;
     for (int l = 0; l < D; ++l) kl += kl_l[(size_t)p * D + l];
-    elbo[p] = scale * lik - kl;
+    elbo[p] = scale * lik - klw * kl;
     if (kl_out != nullptr) kl_out[p] = kl;
   }
 }
@@ -1032,12 +1050,13 @@ cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp
   BackwardArgs a;
   a.D = h->robot.dof; a.M = d.num_inducing; a.N = d.num_timesteps; a.S = d.num_samples; a.B = d.num_bases;
   a.jitter = h->lik.jitter;
+  a.klw = d.kl_shards > 1 ? 1.0 / (double)d.kl_shards : 1.0;
   a.Z = p.Z; a.X = p.X; a.ls = p.lengthscales; a.var = p.variances; a.q_sqrt = p.q_sqrt;
   a.eps_u = r.eps_u;
   a.Lc = ws.Lc; a.kvec = ws.kvec; a.v = ws.v; a.f0 = ws.f0; a.h0 = ws.h0; a.df = ws.df;
   a.d_q_mu = g.d_q_mu; a.d_q_sqrt = g.d_q_sqrt; a.d_ls = g.d_lengthscales; a.d_var = g.d_variances;
   const int Mp = a.M + 2;
-  const size_t smem = sizeof(double) * (4 * 32 * LDM + (size_t)a.N * Mp + 3 * kBT * 32 + 4 * 32 + 16);
+  const size_t smem = sizeof(double) * (4 * 32 * LDM + (size_t)a.N * Mp + 4 * kBT * 32 + 4 * 32 + 16 + (size_t)kBT * a.N);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(gp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -1048,8 +1067,10 @@ cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp
 
 cudaError_t launch_elbo_reduce(vgpmp_handle* h, const vgpmp_dims& d, const double* logp, const double* kl_l,
                                double* elbo, double* kl_out, cudaStream_t s) {
+  const int stot = d.total_samples > 0 ? d.total_samples : d.num_samples;
+  const double klw = d.kl_shards > 1 ? 1.0 / (double)d.kl_shards : 1.0;
   elbo_reduce_kernel<<<d.num_problems, 256, 0, s>>>(h->robot.dof, d.num_samples * d.num_timesteps,
-                                                     h->lik.alpha / (double)d.num_samples, logp, kl_l, elbo, kl_out);
+                                                     h->lik.alpha / (double)stot, klw, logp, kl_l, elbo, kl_out);
   h->launches++;
   return cudaGetLastError();
 }

@@ -113,8 +113,8 @@ class Engine:
     def _chk(self, rc, what):
         _cabi.check(self.h, rc, what)
 
-    def dims(self, Bp, M, N, S, B) -> _cabi.Dims:
-        return _cabi.Dims(int(Bp), int(M), int(N), int(S), int(B))
+    def dims(self, Bp, M, N, S, B, total_samples=0, kl_shards=0) -> _cabi.Dims:
+        return _cabi.Dims(int(Bp), int(M), int(N), int(S), int(B), int(total_samples), int(kl_shards))
 
     def workspace(self, dims: _cabi.Dims) -> torch.Tensor:
         need = int(self.lib.vgpmp_workspace_bytes(self.h, C.byref(dims)))
@@ -214,7 +214,8 @@ class Engine:
     def pathwise_sample(self, dims, params: _cabi.Params, draws: dict, Xq) -> torch.Tensor:
         Xq = self.dev(Xq).reshape(-1, self.D)
         Nq = Xq.shape[0]
-        dq = self.dims(dims.num_problems, dims.num_inducing, Nq, dims.num_samples, dims.num_bases)
+        dq = self.dims(dims.num_problems, dims.num_inducing, Nq, dims.num_samples, dims.num_bases, dims.total_samples,
+                       dims.kl_shards)
         f = self.empty(dims.num_problems, dims.num_samples, Nq, self.D)
         ws = self.workspace(dq)
         ds = self.draws_struct(draws)
@@ -223,14 +224,19 @@ class Engine:
                   "pathwise_sample")
         return f
 
-    def elbo_fwd_bwd(self, dims, params: _cabi.Params, draws: dict, need_grad=True, want_aux=False):
+    def elbo_fwd_bwd(self, dims, params: _cabi.Params, draws: dict, need_grad=True, want_aux=False, out=None):
+        """`out` may hold preallocated 'elbo' / 'd_*' tensors (e.g. views of one packed all-reduce buffer)."""
         Bp, M, N, S = dims.num_problems, dims.num_inducing, dims.num_timesteps, dims.num_samples
-        elbo = self.empty(Bp)
+        pre = out or {}
+        elbo = pre.get("elbo", None)
+        if elbo is None:
+            elbo = self.empty(Bp)
         out = dict(elbo=elbo)
         gs = None
         if need_grad:
-            out.update(d_q_mu=self.empty(Bp, M, self.D), d_q_sqrt=self.empty(Bp, self.D, M, M),
-                       d_lengthscales=self.empty(Bp, self.D), d_variances=self.empty(Bp, self.D))
+            for key, shp in (("d_q_mu", (Bp, M, self.D)), ("d_q_sqrt", (Bp, self.D, M, M)),
+                             ("d_lengthscales", (Bp, self.D)), ("d_variances", (Bp, self.D))):
+                out[key] = pre[key] if key in pre else self.empty(*shp)
             gs = _cabi.Grads(out["d_q_mu"].data_ptr(), out["d_q_sqrt"].data_ptr(), out["d_lengthscales"].data_ptr(),
                              out["d_variances"].data_ptr())
         aux = None

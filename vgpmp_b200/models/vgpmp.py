@@ -90,6 +90,7 @@ class VGPMP:
         self._grads = None
         self._draw_buf = None
         self.last_aux = None
+        self._shard = None          # set by enable_sample_sharding (single-problem large-sample mode)
 
     # ---- construction ------------------------------------------------------------------------------
     @classmethod
@@ -187,7 +188,25 @@ class VGPMP:
         return out
 
     # ---- plumbing ----------------------------------------------------------------------------------
+    def enable_sample_sharding(self, rank: int, world: int, group=None):
+        """Large-sample mode (BASELINE config 4): this process keeps samples [lo, hi) of the model's num_samples; ELBO and
+        gradients are summed over the ranks with one all-reduce per step (vgpmp_b200/utils/sharding.py)."""
+        from ..utils.sharding import packed_layout, shard_range
+        total = self.num_samples if self._shard is None else self._shard["total"]
+        lo, hi = shard_range(total, rank, world)
+        if hi <= lo:
+            raise ValueError("more ranks than samples")
+        self.num_samples = hi - lo
+        n = packed_layout(self.num_problems, self.num_inducing, self.num_latent_gps)["_total"][0]
+        self._shard = dict(rank=rank, world=world, total=total, offset=lo, group=group,
+                           flat=torch.zeros(n, dtype=torch.float64, device=self._eng.device))
+        self._draw_buf = None
+        return self
+
     def _dims(self, N, S=None):
+        if self._shard is not None and S is None:
+            return self._eng.dims(self.num_problems, self.num_inducing, N, self.num_samples, self.num_bases,
+                                  total_samples=self._shard["total"], kl_shards=self._shard["world"])
         return self._eng.dims(self.num_problems, self.num_inducing, N, self.num_samples if S is None else S, self.num_bases)
 
     def _params(self, X):
@@ -204,7 +223,8 @@ class VGPMP:
         key = (dims.num_problems, dims.num_samples, dims.num_bases)
         if self._draw_buf is None or self._draw_buf[0] != key:
             self._draw_buf = (key, eng.alloc_draws(dims))
-        return eng.rng_fill(dims, self.seed, self._step, self._draw_buf[1])
+        off = self._shard["offset"] if (self._shard is not None and dims.total_samples > 0) else 0
+        return eng.rng_fill(dims, self.seed, self._step, self._draw_buf[1], sample_offset=off)
 
     # ---- reference API ---------------------------------------------------------------------------
     def elbo(self, data, draws=None):
@@ -247,7 +267,13 @@ class VGPMP:
         eng = self._eng
         X = eng.dev(X).reshape(-1, self.num_latent_gps)
         dims = self._dims(X.shape[0])
-        out = eng.elbo_fwd_bwd(dims, self._params(X), self._make_draws(dims, draws), need_grad=True)
+        if self._shard is not None:
+            from ..utils.sharding import allreduce_packed, packed_views
+            views = packed_views(self._shard["flat"], self.num_problems, self.num_inducing, self.num_latent_gps)
+            out = eng.elbo_fwd_bwd(dims, self._params(X), self._make_draws(dims, draws), need_grad=True, out=views)
+            allreduce_packed(self._shard["flat"], self._shard["group"])      # one collective: gradients || ELBO
+        else:
+            out = eng.elbo_fwd_bwd(dims, self._params(X), self._make_draws(dims, draws), need_grad=True)
         gs = _cabi.Grads(out["d_q_mu"].data_ptr(), out["d_q_sqrt"].data_ptr(), out["d_lengthscales"].data_ptr(),
                          out["d_variances"].data_ptr())
         st = self._adam_struct()
