@@ -168,6 +168,14 @@ int vgpmp_sdf_lookup(vgpmp_handle* h, const double* pts, double* dist, double* g
  * logp [n]; d_in [n,D] = upstream * d logp / d in (NULL to skip the reverse pass). */
 int vgpmp_loglik_fwd_bwd(vgpmp_handle* h, const double* in, int squash, double upstream, double* logp, double* d_in,
                          int64_t n, void* stream);
+/* min over the P spheres of (sdf(x_p - scene_offset) - r_p) per joint configuration: joints [n,D] -> clearance [n].
+ * The reference's "solved" verdict is pybullet motor tracking (utils/robot.py:416-480), which is outside the hot path;
+ * SURVEY.md 8f-3 defines the collision-free verdict as min clearance > 0 on the best sample. */
+int vgpmp_clearance(vgpmp_handle* h, const double* joints, double* clearance, int64_t n, void* stream);
+/* SVGP posterior mean, `self.posterior().predict_f(X)[0]` in VGPMP.sample_from_posterior (models/vgpmp.py:315):
+ * mean [Bp,Nq,D] = Kfu (Kuu + jitter I)^-1 q_mu_full at Xq [Nq,D].  Workspace as for vgpmp_gp_prepare. */
+int vgpmp_predict_f_mean(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_params* p, const double* Xq, int num_query,
+                         double* mean, void* ws, size_t ws_bytes, void* stream);
 /* K_conditioned / Kuu (covariances/multioutput/Kuus.py:42-53): K [Bp,D,Mp,Mp] = K(Zy,Zy) + jitter I, Zy=[0;1;Z] */
 int vgpmp_kuu(vgpmp_handle* h, const double* Z, const double* lengthscales, const double* variances, double jitter,
               double* K, int num_problems, int num_inducing, void* stream);

@@ -354,6 +354,36 @@ def test_training_loop_improves_elbo_on_reference_problem():
     assert best.shape == (4,)
 
 
+def test_sample_from_posterior_best_sample_and_verdict_vs_oracle():
+    """models/vgpmp.py:312-339 at S=150, Nnew=150: posterior mean, best-sample index, and the collision-free verdict
+    (min clearance > 0) must be identical to the oracle's on the same draws."""
+    case = H.make_case("franka", "bookshelves", num_problems=2, B=64, seed=17, perturb=False)
+    model = H.make_model(case, seed=3)
+    Xnew = np.repeat(np.linspace(0, 1, 150)[:, None], 7, axis=1)
+    mu, best_sample, first, unc = model.sample_from_posterior(Xnew)
+    draws = {k: _np(v) for k, v in model._draw_buf[1].items()}          # the 150-sample draws just used
+    assert mu.shape == (2, 150, 7) and best_sample.shape == (2, 150, 7) and first.shape == (2, 7, 150, 7)
+    assert float(unc) == 2.0
+    verdict, clr = model.collision_free(best_sample)
+    for b, p in enumerate(case["oracle"]):
+        args = [O._t(case[k][b]) for k in ("q_mu", "q_sqrt", "ls", "var")]
+        want_mu = p.joint_sigmoid(p.predict_f_mean(Xnew, args[0], args[2], args[3])).numpy()
+        assert H.rel_err(_np(mu[b]), want_mu) < 1e-7
+        f = p.sample_paths(Xnew, *args, {k: v[b] for k, v in draws.items()})
+        g = p.joint_sigmoid(f)
+        cost = p.log_prob(g).sum(-1).numpy()
+        assert H.rel_err(_np(model.likelihood.log_prob(_np(g))).sum(-1), cost) < 1e-9
+        best = int(np.argmax(cost))
+        assert H.rel_err(_np(best_sample[b]), g[best].numpy()) < 1e-7, "different best sample than the oracle"
+        want_clr = p.clearance(g[best].numpy()).min()
+        assert abs(float(clr[b]) - want_clr) < 1e-12
+        assert bool(verdict[b]) == bool(want_clr > 0)
+    # clearance kernel on a ragged batch, against the oracle
+    th = case["oracle"][0].robot.limits_lo + 0.5 * (case["oracle"][0].robot.limits_hi - case["oracle"][0].robot.limits_lo) * \
+        np.random.default_rng(0).uniform(size=(131, 7))
+    assert np.array_equal(_np(model._eng.clearance(th)), case["oracle"][0].clearance(th))
+
+
 def test_errors_are_reported_not_swallowed():
     from vgpmp_b200 import _cabi
     case = H.make_case(num_problems=1, S=2, N=5, M=5, B=8)

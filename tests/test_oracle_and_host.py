@@ -150,6 +150,55 @@ def test_init_trainset_and_problemset():
     assert np.all(X[:, 0] == X[:, 6]) and X[0, 0] == 0.0 and X[-1, 0] == 1.0
 
 
+REFERENCE_PARAMETERS_YAML = """
+- robot:
+    robot_name: "wam"
+- scene:
+      position: [ 0.85, -0.15, 0.834]
+      orientation: [ 0.0, 0.0, 0.0, 1.0 ]
+      environment_name: "bookshelves"
+      environment_file_name: "bookshelves_mesh"
+      sdf_file_name: "bookshelves_center_vgpmp"
+      objects: []
+      objects_position: []
+      objects_orientation: []
+      benchmark: True
+      non_benchmark_attributes:
+        states: [[0.0, 0.0, 0.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0, 0.0, 0.0]]
+        robot_pos_and_orn: [[ 0.0, 0.0, 0.0 ], [ 0.0, 0.0, 0.0, 1.0 ]]
+        planner_params: {sigma_obs: 0.005, epsilon: 0.05, lengthscales: [5.0, 5.0, 5.0, 2.0, 5.0, 5.0], variance: 0.25,
+                         alpha: 100, num_samples: 7, num_inducing: 24, learning_rate: 0.09, num_steps: 130,
+                         time_spacing_X: 70, time_spacing_Xnew: 150}
+      benchmark_attributes:
+        problemset_name: "bookshelves"
+- trainable_params: {q_mu: True, q_sqrt: True, lengthscales: True, kernel_variance: True, sigma_obs: False,
+                     inducing_variable: False, alpha: False}
+- graphics: {visuals: True, quality: high, GUI: True}
+"""
+
+
+def test_parameter_loader_reads_the_reference_yaml_layout(tmp_path):
+    """Same list-of-dicts layout as the reference's parameters.yaml (shipped configured for WAM + bookshelves)."""
+    from vgpmp_b200.utils.parameter_loader import ParameterLoader, build_environment
+    f = tmp_path / "parameters.yaml"
+    f.write_text(REFERENCE_PARAMETERS_YAML)
+    loader = ParameterLoader().initialize(file_path=f)
+    p = loader.params
+    assert p["robot_params"]["robot_name"] == "wam" and p["robot_params"]["dof"] == 7
+    assert len(p["scene_params"]["queries"]) == 55                      # combinations of 11 states
+    assert p["scene_params"]["robot_pos_and_orn"][0] == [0.0, 0.0, 0.346]
+    assert p["planner_params"]["num_inducing"] == 15 and p["planner_params"]["num_samples"] == 20
+    assert p["trainable_params"]["q_mu"] is True and p["trainable_params"]["alpha"] is False
+    assert "benchmark_attributes" not in p["scene_params"]
+    from vgpmp_b200.utils.sdf_utils import SignedDistanceField
+    robot, sampler, sdf = build_environment(loader, sdf=SignedDistanceField(np.zeros((2, 2, 2)), np.zeros(3), 0.1))
+    o = H.oracle_robot("wam", "bookshelves")
+    assert np.array_equal(sampler.constants().sphere_offsets, o.sphere_offsets)
+    assert np.array_equal(robot.base_pose, o.base_pose)
+    with pytest.raises(AssertionError, match="SDF file"):
+        build_environment(loader)                                         # the reference asserts the .sdf exists
+
+
 def test_rejects_unsupported_configurations():
     from vgpmp_b200.kernels import Matern52
     with pytest.raises(ValueError):

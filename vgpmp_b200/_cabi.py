@@ -71,6 +71,8 @@ SYMBOLS = {
     "vgpmp_fk_spheres": (_I, [_P, _P, _P, _I64, _P]),
     "vgpmp_sdf_lookup": (_I, [_P, _P, _P, _P, _I64, _P]),
     "vgpmp_loglik_fwd_bwd": (_I, [_P, _P, _I, _D, _P, _P, _I64, _P]),
+    "vgpmp_clearance": (_I, [_P, _P, _P, _I64, _P]),
+    "vgpmp_predict_f_mean": (_I, [_P, C.POINTER(Dims), C.POINTER(Params), _P, _I, _P, _P, _SZ, _P]),
     "vgpmp_kuu": (_I, [_P, _P, _P, _P, _D, _P, _I, _I, _P]),
     "vgpmp_kuf": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "vgpmp_gp_prepare": (_I, [_P, C.POINTER(Dims), C.POINTER(Params), _P, _P, _P, _P, _SZ, _P]),

@@ -269,6 +269,24 @@ int vgpmp_loglik_fwd_bwd(vgpmp_handle* h, const double* in, int squash, double u
   return check_cuda(h, launch_loglik(h, in, squash, upstream, logp, d_in, n, (cudaStream_t)stream), "loglik_fwd_bwd");
 }
 
+int vgpmp_clearance(vgpmp_handle* h, const double* joints, double* clearance, int64_t n, void* stream) {
+  if (!h || n < 0 || (n > 0 && (!joints || !clearance))) return fail(h, VGPMP_ERR_INVALID, "clearance: bad argument");
+  return check_cuda(h, launch_clearance(h, joints, clearance, n, (cudaStream_t)stream), "clearance");
+}
+
+int vgpmp_predict_f_mean(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_params* p, const double* Xq, int num_query,
+                         double* mean, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_dims(h, dims);
+  if (rc) return rc;
+  if (!p || !Xq || !mean || !ws || num_query < 1) return fail(h, VGPMP_ERR_INVALID, "predict_f_mean: bad argument");
+  size_t need = 0;
+  GpScratch g = carve(ws, h->robot.dof, *dims, &need);
+  if (ws_bytes < need) return fail(h, VGPMP_ERR_WORKSPACE, "predict_f_mean: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = check_cuda(h, launch_gp_prepare(h, *dims, *p, g.Lc, g.Sfull, g.kl_l, g.kvec, s), "gp_prepare"))) return rc;
+  return check_cuda(h, launch_predict_mean(h, *dims, *p, Xq, num_query, g.Lc, mean, s), "predict_f_mean");
+}
+
 int vgpmp_kuu(vgpmp_handle* h, const double* Z, const double* lengthscales, const double* variances, double jitter,
               double* K, int num_problems, int num_inducing, void* stream) {
   if (!h || !Z || !lengthscales || !variances || !K || num_problems < 1 || num_inducing < 1 ||

@@ -65,6 +65,7 @@ cudaError_t launch_fk_frames(vgpmp_handle* h, const double* joints, double* fram
 cudaError_t launch_fk_spheres(vgpmp_handle* h, const double* joints, double* centres, int64_t n, cudaStream_t s);
 cudaError_t launch_sdf_build(vgpmp_handle* h, const double* raw_dev, cudaStream_t s);
 cudaError_t launch_sdf_lookup(vgpmp_handle* h, const double* pts, double* dist, double* grad, int64_t n, cudaStream_t s);
+cudaError_t launch_clearance(vgpmp_handle* h, const double* joints, double* clearance, int64_t n, cudaStream_t s);
 cudaError_t launch_loglik(vgpmp_handle* h, const double* in, int squash, double upstream, double* logp, double* d_in,
                           int64_t n, cudaStream_t s);
 
@@ -94,6 +95,8 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
                             double* f0, double* h0, double* meta, cudaStream_t s);
 cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
                                const GpScratch& ws, const vgpmp_grads& g, cudaStream_t s);
+cudaError_t launch_predict_mean(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const double* Xq, int Nq,
+                                const double* Lc, double* mean, cudaStream_t s);
 cudaError_t launch_elbo_reduce(vgpmp_handle* h, const vgpmp_dims& d, const double* logp, const double* kl_l,
                                double* elbo, double* kl_out, cudaStream_t s);
 cudaError_t launch_adam(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_adam& st, const vgpmp_grads& g, cudaStream_t s);

@@ -796,6 +796,33 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
   if (tid >= 2 && tid < Mp) a.d_q_mu[((size_t)p * M + tid - 2) * D + l] = gmu[tid];
 }
 
+// SVGP posterior mean at Xq (GPflow posterior().predict_f with whiten=False, models/vgpmp.py:315):
+//   mean[n,l] = Kfu[n,:] Khat^-1 q_mu_full[:,l]        one CTA per (problem, latent)
+__global__ void __launch_bounds__(128) predict_mean_kernel(int D, int M, int Nq, vgpmp_params P,
+                                                          const double* __restrict__ Xq, const double* __restrict__ Lc,
+                                                          double* __restrict__ mean) {
+  __shared__ double Lsm[32 * LDM], wv[32], zy[32];
+  const int pl = blockIdx.x, p = pl / D, l = pl % D, Mp = M + 2, tid = threadIdx.x;
+  const double ell = P.lengthscales[pl], s2 = P.variances[pl];
+  for (int idx = tid; idx < Mp * Mp; idx += blockDim.x) Lsm[(idx / Mp) * LDM + idx % Mp] = Lc[(size_t)pl * Mp * Mp + idx];
+  if (tid < 32) zy[tid] = tid < Mp ? zy_at(P.Z, D, l, tid) : 0.0;
+  __syncthreads();
+  if (tid < 32) {
+    double mu = 0.0;
+    if (tid < Mp)
+      mu = tid < 2 ? P.query_latent[((size_t)p * 2 + tid) * D + l] : P.q_mu[((size_t)p * M + tid - 2) * D + l];
+    const double y = warp_fwd_subst(Lsm, Mp, mu);
+    wv[tid] = warp_bwd_subst(Lsm, Mp, y);
+  }
+  __syncthreads();
+  for (int n = tid; n < Nq; n += blockDim.x) {
+    const double x = Xq[(size_t)n * D + l];
+    double acc = 0.0;
+    for (int m = 0; m < Mp; ++m) acc += s2 * vg_matern52(fabs(x - zy[m]) / ell) * wv[m];
+    mean[((size_t)p * Nq + n) * D + l] = acc;
+  }
+}
+
 // ELBO[p] = alpha/S * sum_{s,n} logp - sum_l KL_l      models/vgpmp.py:287-289
 __global__ void __launch_bounds__(256) elbo_reduce_kernel(int D, int SN, double scale, double klw,
                                                          const double* __restrict__ logp,
@@ -1061,6 +1088,13 @@ cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp
   cudaError_t e = cudaFuncSetAttribute(gp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   gp_backward_kernel<<<d.num_problems * a.D, 256, smem, s>>>(a);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_predict_mean(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const double* Xq, int Nq,
+                                const double* Lc, double* mean, cudaStream_t s) {
+  predict_mean_kernel<<<d.num_problems * h->robot.dof, 128, 0, s>>>(h->robot.dof, d.num_inducing, Nq, p, Xq, Lc, mean);
   h->launches++;
   return cudaGetLastError();
 }

@@ -181,6 +181,30 @@ __global__ void __launch_bounds__(kThreads) sdf_lookup_kernel(SdfDev sdf, const 
   }
 }
 
+// min over spheres of (sdf(x_p - offset) - r_p) for one joint configuration: the collision-free verdict of SURVEY.md 8f-3
+__global__ void __launch_bounds__(kThreads) clearance_kernel(RobotDev rb, SdfDev sdf, LikDev lk,
+                                                            const double* __restrict__ joints,
+                                                            double* __restrict__ clearance, int64_t n) {
+  const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (c >= n) return;
+  Frame A;
+  frame_from_base(rb, A);
+  double best = 1e300;
+  int p = 0;
+  for (int j = 0; j <= rb.dof; ++j) {
+    if (j > 0) frame_step(rb, j - 1, joints[c * rb.dof + j - 1], A);
+    for (; p < rb.frame_end[j]; ++p) {
+      const double ox = rb.sphere_off[p][0], oy = rb.sphere_off[p][1], oz = rb.sphere_off[p][2];
+      const double x = A.r[0] * ox + A.r[1] * oy + A.r[2] * oz + A.t[0];
+      const double y = A.r[3] * ox + A.r[4] * oy + A.r[5] * oz + A.t[1];
+      const double z = A.r[6] * ox + A.r[7] * oy + A.r[8] * oz + A.t[2];
+      const Voxel v = sdf_voxel(sdf, x - lk.offset[0], y - lk.offset[1], z - lk.offset[2]);
+      best = fmin(best, sdf_value(sdf, v) - rb.sphere_rad[p]);
+    }
+  }
+  clearance[c] = best;
+}
+
 __device__ __forceinline__ double stable_sigmoid(double x) {
   if (x >= 0.0) return 1.0 / (1.0 + exp(-x));
   const double e = exp(x);
@@ -336,6 +360,14 @@ cudaError_t launch_sdf_build(vgpmp_handle* h, const double* raw_dev, cudaStream_
 cudaError_t launch_sdf_lookup(vgpmp_handle* h, const double* pts, double* dist, double* grad, int64_t n, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   sdf_lookup_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, s>>>(h->sdf, pts, dist, grad, n);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_clearance(vgpmp_handle* h, const double* joints, double* clearance, int64_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  clearance_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, s>>>(h->robot, h->sdf, h->lik, joints,
+                                                                                   clearance, n);
   h->launches++;
   return cudaGetLastError();
 }

@@ -161,6 +161,22 @@ class Engine:
                   "loglik_fwd_bwd")
         return logp.reshape(xin.shape[:-1]), (dx.reshape(xin.shape) if need_grad else None)
 
+    def clearance(self, joints) -> torch.Tensor:
+        j = self.dev(joints)
+        flat = j.reshape(-1, self.D)
+        out = self.empty(flat.shape[0])
+        self._chk(self.lib.vgpmp_clearance(self.h, flat.data_ptr(), out.data_ptr(), flat.shape[0], self._stream()), "clearance")
+        return out.reshape(j.shape[:-1])
+
+    def predict_f_mean(self, dims, params: _cabi.Params, Xq) -> torch.Tensor:
+        Xq = self.dev(Xq).reshape(-1, self.D)
+        mean = self.empty(dims.num_problems, Xq.shape[0], self.D)
+        ws = self.workspace(dims)
+        self._chk(self.lib.vgpmp_predict_f_mean(self.h, C.byref(dims), C.byref(params), Xq.data_ptr(), Xq.shape[0],
+                                                mean.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()),
+                  "predict_f_mean")
+        return mean
+
     def kuu(self, Z, lengthscales, variances, jitter=0.0) -> torch.Tensor:
         Zd = self.dev(Z).reshape(-1, self.D)
         ls, var = self.dev(lengthscales).reshape(-1, self.D), self.dev(variances).reshape(-1, self.D)

@@ -322,6 +322,35 @@ class VGPMP:
         f = self._eng.pathwise_sample(dims, self._params(None), self._make_draws(dims, draws), X)
         return self._squeeze(f)
 
+    def predict_f_mean(self, X):
+        """`self.posterior().predict_f(X)[0]`: SVGP posterior mean in latent space, [N,D] (or [Bp,N,D])."""
+        return self._squeeze(self._eng.predict_f_mean(self._dims(1, 1), self._params(None), X))
+
+    def sample_from_posterior(self, X, robot=None, compute_uncertainty=False, num_samples=150):
+        """models/vgpmp.py:312-331: (mean trajectory, best of 150 posterior samples, the first 7 samples,
+        2*sqrt(uncertainty)) in joint space.  `compute_uncertainty` needs the pybullet robot in the reference and is
+        not part of the hot path; the constant 1.0 of its False branch is returned."""
+        if compute_uncertainty:
+            raise NotImplementedError("end-effector uncertainty uses the pybullet robot (models/vgpmp.py:322-327)")
+        sig = self.likelihood.joint_sigmoid
+        mu = sig(self.predict_f_mean(X))
+        samples = sig(self.predict_f_samples(X, num_samples=num_samples))          # [S,N,D] or [Bp,S,N,D]
+        best = self.get_best_sample(samples)
+        if self.num_problems == 1:
+            best_sample = samples[best]
+            first = samples[:7]
+        else:
+            idx = best.view(-1, 1, 1, 1).expand(-1, 1, samples.shape[2], samples.shape[3])
+            best_sample = torch.gather(samples, 1, idx)[:, 0]
+            first = samples[:, :7]
+        return mu, best_sample, first, 2.0 * torch.ones((), dtype=torch.float64, device=samples.device)
+
+    def collision_free(self, trajectory):
+        """Verdict of SURVEY.md 8f-3 on joint-space trajectories [N,D] (or [Bp,N,D]): min over timesteps and spheres of
+        (sdf - radius) > 0.  Returns (verdict, min clearance)."""
+        clr = self._eng.clearance(trajectory).amin(dim=-1)
+        return clr > 0, clr
+
     def debug_likelihood(self, data):
         lp = self.likelihood.log_prob(data)
         return torch.sum(torch.mean(lp, dim=0))
