@@ -214,6 +214,15 @@ int vgpmp_train_step_host(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* s
                           size_t ws_bytes, void* stream);
 size_t vgpmp_draws_bytes(const vgpmp_dims* dims, int dof);
 
+/* ---- SDF producer (replaces the external SDFGen binary driven by gpflow_vgpmp/utils/gen_sdf.py:16-43) ---------------
+ * Exact distance from every grid node origin + (i,j,k)*delta to a triangle soup made of CONVEX pieces, negative inside
+ * any piece.  HOST pointers: tri [T,3,3]; plane [T,4] outward face planes (n, d): a point is inside a piece iff
+ * n.p - d <= 0 for all faces of the piece; piece_end [num_pieces] exclusive end of each piece's (contiguous) triangle
+ * range; out_host [nx,ny,nz] (z fastest), i.e. the `data` of SignedDistanceField. */
+int vgpmp_mesh_to_sdf(int device, const double* tri, const double* plane, const int32_t* piece_end, int32_t num_tri,
+                      int32_t num_pieces, int32_t nx, int32_t ny, int32_t nz, const double* origin, double delta,
+                      double* out_host);
+
 /* ---- measurement hooks (bench.py / profiles; no reference counterpart beyond the `timing` decorator of
  * utils/miscellaneous.py:46-56) ---------------------------------------------------------------------------
  * With profiling enabled every stage launch of vgpmp_elbo_fwd_bwd / vgpmp_adam_step / vgpmp_rng_fill is bracketed by

@@ -46,7 +46,7 @@ def main():
     allreduce_packed(shard._shard["flat"])
     errs = {k: H.rel_err(views[k].cpu().numpy(), ref[k].cpu().numpy()) for k in views}
     report["sample_sharded_rel_err"] = errs
-    assert max(errs.values()) < 1e-9, errs
+    assert max(errs.values()) < 1e-7, errs   # summation order through Khat^-1 (cond ~1e7)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(20):

@@ -122,4 +122,9 @@ if __name__ == "__main__":
     tp = yaml.safe_load(open(REF / "parameters.yaml"))
     trainable = [d["trainable_params"] for d in tp if "trainable_params" in d][0]
     (OUT / "trainable_params.json").write_text(json.dumps(trainable, indent=1))
+    # scene meshes (data assets, convex pieces): input of the GPU SDF producer (vgpmp_b200/utils/gen_sdf.py)
+    import shutil
+    (OUT / "scenes").mkdir(exist_ok=True)
+    shutil.copy(REF / "data" / "scenes" / "bookshelves" / "bookshelves_center.obj", OUT / "scenes")
+    shutil.copy(REF / "data" / "scenes" / "industrial" / "industrial-acd.obj", OUT / "scenes")
     print("wrote", sorted(p.name for p in OUT.iterdir()))

@@ -6,7 +6,7 @@ import sys
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-SRC = [PKG / "csrc" / n for n in ("cabi.cu", "kinematics.cu", "gp.cu")]
+SRC = [PKG / "csrc" / n for n in ("cabi.cu", "kinematics.cu", "gp.cu", "mesh_sdf.cu")]
 HDR = [PKG / "csrc" / "common.cuh", PKG.parent / "include" / "vgpmp_b200.h"]
 LIB = PKG / "lib" / "libvgpmp_b200.so"
 

@@ -1,0 +1,127 @@
+// Mesh -> signed distance grid on the GPU.
+//
+// The reference produces its .sdf grids offline with an external SDFGen binary driven by
+// gpflow_vgpmp/utils/gen_sdf.py:16-43 (mesh, delta, padding) and the resulting files are missing from the
+// snapshot.  This is a from-scratch producer for the scene meshes the reference does ship (convex pieces, one
+// `o convex_k` group each): per grid node, the exact Euclidean distance to the nearest triangle, negative inside
+// any convex piece.  Grid geometry follows SDFGen: origin = bbox_min - padding*delta, node (i,j,k) sits at
+// origin + (i,j,k)*delta, output is data[x,y,z] (z fastest) as SignedDistanceField expects.
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "common.cuh"
+
+namespace {
+
+struct V3 { double x, y, z; };
+__device__ __forceinline__ V3 sub(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// squared distance from p to triangle (a,b,c): closest-point regions (Ericson, Real-Time Collision Detection 5.1.5)
+__device__ double point_tri_dist2(V3 p, V3 a, V3 b, V3 c) {
+  const V3 ab = sub(b, a), ac = sub(c, a), ap = sub(p, a);
+  const double d1 = dot(ab, ap), d2 = dot(ac, ap);
+  if (d1 <= 0.0 && d2 <= 0.0) return dot(ap, ap);
+  const V3 bp = sub(p, b);
+  const double d3 = dot(ab, bp), d4 = dot(ac, bp);
+  if (d3 >= 0.0 && d4 <= d3) return dot(bp, bp);
+  const double vc = d1 * d4 - d3 * d2;
+  if (vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) {
+    const double v = d1 / (d1 - d3);
+    const V3 q = {ap.x - v * ab.x, ap.y - v * ab.y, ap.z - v * ab.z};
+    return dot(q, q);
+  }
+  const V3 cp = sub(p, c);
+  const double d5 = dot(ab, cp), d6 = dot(ac, cp);
+  if (d6 >= 0.0 && d5 <= d6) return dot(cp, cp);
+  const double vb = d5 * d2 - d1 * d6;
+  if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) {
+    const double w = d2 / (d2 - d6);
+    const V3 q = {ap.x - w * ac.x, ap.y - w * ac.y, ap.z - w * ac.z};
+    return dot(q, q);
+  }
+  const double va = d3 * d6 - d5 * d4;
+  if (va <= 0.0 && (d4 - d3) >= 0.0 && (d5 - d6) >= 0.0) {
+    const double w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+    const V3 bc = sub(c, b);
+    const V3 q = {bp.x - w * bc.x, bp.y - w * bc.y, bp.z - w * bc.z};
+    return dot(q, q);
+  }
+  const double denom = 1.0 / (va + vb + vc);
+  const double v = vb * denom, w = vc * denom;
+  const V3 q = {ap.x - v * ab.x - w * ac.x, ap.y - v * ab.y - w * ac.y, ap.z - v * ab.z - w * ac.z};
+  return dot(q, q);
+}
+
+constexpr int kTile = 64;
+
+// tri: [T,9] vertices; plane: [T,4] outward plane (n, d) of each face: inside piece <=> n.p - d <= 0 for all its faces;
+// piece_end: [npieces] exclusive end index of each piece's triangle range (triangles sorted by piece)
+__global__ void __launch_bounds__(256) mesh_sdf_kernel(const double* __restrict__ tri, const double* __restrict__ plane,
+                                                      const int* __restrict__ piece_end, int T, int npieces, int nx,
+                                                      int ny, int nz, double ox, double oy, double oz, double delta,
+                                                      double* __restrict__ out) {
+  __shared__ double st[kTile * 9], sp[kTile * 4];
+  const size_t cells = (size_t)nx * ny * nz;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < cells;
+  const int iz = (int)(i % nz), iy = (int)((i / nz) % ny), ix = (int)(i / ((size_t)nz * ny));
+  const V3 p = {ox + delta * ix, oy + delta * iy, oz + delta * iz};
+  double best = 1e300;
+  bool inside_any = false, inside_cur = true;
+  int piece = 0;
+  for (int t0 = 0; t0 < T; t0 += kTile) {
+    const int nt = min(kTile, T - t0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < nt * 9; k += blockDim.x) st[k] = tri[(size_t)t0 * 9 + k];
+    for (int k = threadIdx.x; k < nt * 4; k += blockDim.x) sp[k] = plane[(size_t)t0 * 4 + k];
+    __syncthreads();
+    if (!live) continue;
+    for (int t = 0; t < nt; ++t) {
+      const V3 a = {st[9 * t], st[9 * t + 1], st[9 * t + 2]}, b = {st[9 * t + 3], st[9 * t + 4], st[9 * t + 5]},
+               c = {st[9 * t + 6], st[9 * t + 7], st[9 * t + 8]};
+      best = fmin(best, point_tri_dist2(p, a, b, c));
+      if (sp[4 * t] * p.x + sp[4 * t + 1] * p.y + sp[4 * t + 2] * p.z - sp[4 * t + 3] > 0.0) inside_cur = false;
+      if (t0 + t + 1 == piece_end[piece]) {  // last face of this convex piece
+        inside_any = inside_any || inside_cur;
+        inside_cur = true;
+        ++piece;
+      }
+    }
+  }
+  if (live) out[i] = inside_any ? -sqrt(best) : sqrt(best);
+}
+
+}  // namespace
+
+extern "C" int vgpmp_mesh_to_sdf(int device, const double* tri, const double* plane, const int32_t* piece_end,
+                                 int32_t num_tri, int32_t num_pieces, int32_t nx, int32_t ny, int32_t nz,
+                                 const double* origin, double delta, double* out_host) {
+  if (!tri || !plane || !piece_end || !origin || !out_host || num_tri < 1 || num_pieces < 1 || nx < 1 || ny < 1 ||
+      nz < 1 || !(delta > 0.0))
+    return VGPMP_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return VGPMP_ERR_NO_DEVICE;
+  const size_t cells = (size_t)nx * ny * nz;
+  double *d_tri = nullptr, *d_plane = nullptr, *d_out = nullptr;
+  int* d_pe = nullptr;
+  cudaError_t e;
+  int rc = VGPMP_OK;
+  if ((e = cudaMalloc(&d_tri, sizeof(double) * 9 * num_tri)) != cudaSuccess ||
+      (e = cudaMalloc(&d_plane, sizeof(double) * 4 * num_tri)) != cudaSuccess ||
+      (e = cudaMalloc(&d_pe, sizeof(int) * num_pieces)) != cudaSuccess ||
+      (e = cudaMalloc(&d_out, sizeof(double) * cells)) != cudaSuccess ||
+      (e = cudaMemcpy(d_tri, tri, sizeof(double) * 9 * num_tri, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(d_plane, plane, sizeof(double) * 4 * num_tri, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(d_pe, piece_end, sizeof(int) * num_pieces, cudaMemcpyHostToDevice)) != cudaSuccess) {
+    rc = VGPMP_ERR_CUDA;
+  } else {
+    mesh_sdf_kernel<<<(unsigned)((cells + 255) / 256), 256>>>(d_tri, d_plane, d_pe, num_tri, num_pieces, nx, ny, nz,
+                                                               origin[0], origin[1], origin[2], delta, d_out);
+    if ((e = cudaGetLastError()) != cudaSuccess ||
+        (e = cudaMemcpy(out_host, d_out, sizeof(double) * cells, cudaMemcpyDeviceToHost)) != cudaSuccess)
+      rc = VGPMP_ERR_CUDA;
+  }
+  cudaFree(d_tri); cudaFree(d_plane); cudaFree(d_pe); cudaFree(d_out);
+  return rc;
+}
