@@ -8,8 +8,8 @@
 A "step" is one pass of the hot path over one batch of synthetic problems: draw the step's randomness, ELBO forward,
 reverse pass to (_q_mu, _q_sqrt, lengthscales, variances), Adam update.  Workload at any N (weak scaling): BASELINE.json
 configs[1] per GPU -- Franka Panda, bookshelves planner_params (S=7, N=70, M=24, B=1024), all 55 start/goal pairs x
-total_runs=5 (benchmarking.py:70) = 275 independent problems in one batch, on a synthetic 256^3 float64 shelf SDF
-(the reference's .sdf grids are missing blobs).  One JSON line on stdout (rank 0).
+total_runs=5 (benchmarking.py:70) = 275 independent problems in one batch; the SDF is regenerated on the GPU from the
+reference's bookshelves mesh (its .sdf grids are missing blobs).  One JSON line on stdout (rank 0).
 """
 import argparse
 import json
@@ -37,8 +37,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--runs", type=int, default=5, help="total_runs of benchmarking.py:70 (copies of the 55 pairs)")
+    ap.add_argument("--sdf", default="bookshelves_mesh", choices=["bookshelves_mesh", "synthetic"],
+                    help="bookshelves_mesh: signed distance to the reference's bookshelves_center.obj, produced on the GPU "
+                         "(delta 1 cm, padding 20 as utils/gen_sdf.py:9); synthetic: analytic union of boxes")
     ap.add_argument("--sdf-dim", type=int, default=256)
-    ap.add_argument("--cpu-problems", type=int, default=8, help="problems per step of the CPU baseline sample")
+    ap.add_argument("--cpu-problems", type=int, default=16, help="problems per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -50,10 +53,14 @@ def workload(runs):
     return ps, queries
 
 
-def bench_sdf(dim):
+def bench_sdf(kind, dim):
+    if kind == "bookshelves_mesh":
+        from vgpmp_b200.utils.gen_sdf import PADDING, mesh_to_sdf, scene_mesh_path
+        return mesh_to_sdf(scene_mesh_path("bookshelves"), 0.01, PADDING), "bookshelves_center.obj -> GPU SDF, delta=0.01, padding=20"
     from vgpmp_b200.utils.sdf_utils import synthetic_shelf_sdf
     # scene frame: robot base sits at -scene_offset = (-0.62, 0.15, -0.834); 2.56 m cube around the reach box
-    return synthetic_shelf_sdf(shape=(dim, dim, dim), delta=2.56 / dim, origin=(-1.6, -1.0, -1.8), seed=0, n_boxes=16)
+    return (synthetic_shelf_sdf(shape=(dim, dim, dim), delta=2.56 / dim, origin=(-1.6, -1.0, -1.8), seed=0, n_boxes=16),
+            f"synthetic shelf {dim}^3")
 
 
 class ClockSampler:
@@ -146,7 +153,7 @@ def run_reference(args):
         note = "tensorflow/gpflow importable but the reference driver also needs pybullet; using the float64 port"
     except Exception:
         note = "tensorflow/gpflow/gpflow_sampling/pybullet not installable here: float64 port of the reference arithmetic"
-    steps = max(1, min(args.steps, 20))
+    steps = max(1, min(args.steps, 60))
     rate, dt = cpu_port_rate(args.cpu_problems, steps, warmup=min(args.warmup, 2))
     cores = os.cpu_count() or 1
     sample = f"{args.cpu_problems} Franka/bookshelves problems per step x {steps} steps ({dt:.1f} s), solved one after another"
@@ -184,7 +191,7 @@ def run_b200(args):
 
     ps, queries = workload(args.runs)
     pp = dict(ps["planner_params"])
-    sdf = bench_sdf(args.sdf_dim)
+    sdf, sdf_desc = bench_sdf(args.sdf, args.sdf_dim)
     robot = Robot.from_tables("franka", "bookshelves")
     sampler = Sampler(None, robot)
     q = np.stack([np.stack(pair) for pair in queries])
@@ -266,26 +273,27 @@ def run_b200(args):
                 stages[name] = {"ms_per_launch": stage_ms[i] / stage_n[i], "share": stage_ms[i] / tot, "launches": int(stage_n[i])}
         dominant = max(stages, key=lambda k: stages[k]["share"])
         sdf_ms = stages["loglik_fwd_bwd"]["ms_per_launch"]
-        sdf_bytes = evals_per_step * 7 * 8                      # 7 float64 grid elements per sphere-SDF eval
+        sdf_bytes = evals_per_step * 32                         # one 32-byte {value, gradient} record per sphere-SDF eval
         achieved = sdf_bytes / (sdf_ms * 1e-3) / 1e9
-        roofline = {"kernel": "loglik_kernel<7,true> (FK + 7-point SDF stencil + hinge + reverse pass)", "bound": "hbm",
+        roofline = {"kernel": "loglik_kernel<7,true,2> (FK + one 256-bit {value,gradient} record load per sphere + hinge + reverse pass)", "bound": "hbm",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": sdf_bytes,
                     "ms_per_launch": sdf_ms, "share_of_step": stages["loglik_fwd_bwd"]["share"],
                     "dominant_stage": dominant}
-        # pathwise stage: fp64 CUDA-core work (features + contraction), reported against the nominal fp64 FMA rate
+        # sampler stage: FP64 CUDA-core work; only the contraction (f0 and d f0/d lengthscale) is counted, 2 flops per FMA
         A = N + M + 2
-        pw_flops = Bp * D * (A * B * (2 * D + 60) + 2 * 2 * S * A * B)
+        pw_flops = Bp * D * 2 * 2 * S * A * B * 2
         pw = stages.get("pathwise_sample")
         if pw:
-            roofline["pathwise_fp64_tflops"] = pw_flops / (pw["ms_per_launch"] * 1e-3) / 1e12
+            roofline["sampler_contraction_fp64_tflops"] = pw_flops / (pw["ms_per_launch"] * 1e-3) / 1e12
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"franka/bookshelves: 55 start-goal pairs x total_runs={args.runs} = {Bp} problems per GPU per step",
                        "S": S, "N": N, "M": M, "B": B, "dof": D, "spheres": P,
-                       "sdf": f"synthetic shelf {args.sdf_dim}^3 float64 ({sdf.data.nbytes / 2**20:.0f} MiB)",
+                       "sdf": f"{sdf_desc}; grid {sdf.data.shape} float64, {sdf.data.nbytes * 4 / 2**20:.0f} MiB of "
+                              "{value,gradient} records in HBM (the reference's own .sdf grids are missing blobs)",
                        "rng": "device Philox4x32-10, fresh draws every step",
                        "l2": "inputs larger than L2 (draws + SDF grid > 126 MB per step); no explicit flush"},
             "sdf_evals_per_s": world * evals_per_step * args.steps / (ms / 1000.0),
@@ -295,7 +303,7 @@ def run_b200(args):
             "gpu_launches": int(launches), "stages": stages, "roofline": roofline, "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
-            steps = 6
+            steps = 40
             rate, dt = cpu_port_rate(args.cpu_problems, steps)
             out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                    "sample": f"{args.cpu_problems} of the {Bp} problems x {steps} steps ({dt:.1f} s), float64 "

@@ -69,6 +69,7 @@ GpScratch carve(void* ws, int D, const vgpmp_dims& d, size_t* total) {
   GpScratch g;
   g.Lc = c.take(Bp * D * Mp * Mp);
   g.Sfull = c.take(Bp * D * Mp * Mp);
+  g.Linv = c.take(Bp * D * Mp * Mp);
   g.kl_l = c.take(Bp * D);
   g.kvec = c.take(Bp * D * (Mp + 4));
   g.v = c.take(Bp * D * S * Mp);
@@ -283,7 +284,7 @@ int vgpmp_predict_f_mean(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_pa
   GpScratch g = carve(ws, h->robot.dof, *dims, &need);
   if (ws_bytes < need) return fail(h, VGPMP_ERR_WORKSPACE, "predict_f_mean: workspace too small");
   cudaStream_t s = (cudaStream_t)stream;
-  if ((rc = check_cuda(h, launch_gp_prepare(h, *dims, *p, g.Lc, g.Sfull, g.kl_l, g.kvec, s), "gp_prepare"))) return rc;
+  if ((rc = check_cuda(h, launch_gp_prepare(h, *dims, *p, g.Lc, g.Sfull, g.kl_l, g.kvec, g.Linv, s), "gp_prepare"))) return rc;
   return check_cuda(h, launch_predict_mean(h, *dims, *p, Xq, num_query, g.Lc, mean, s), "predict_f_mean");
 }
 
@@ -315,7 +316,7 @@ int vgpmp_gp_prepare(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_params
   if (ws_bytes < need) return fail(h, VGPMP_ERR_WORKSPACE, "gp_prepare: workspace too small");
   cudaStream_t s = (cudaStream_t)stream;
   rc = check_cuda(h, launch_gp_prepare(h, *dims, *p, Lc ? Lc : g.Lc, q_sqrt_full ? q_sqrt_full : g.Sfull, g.kl_l,
-                                       g.kvec, s), "gp_prepare");
+                                       g.kvec, g.Linv, s), "gp_prepare");
   if (rc || !kl) return rc;
   // kl[p] = sum_l kl_l: reuse the ELBO reducer with an empty likelihood term
   vgpmp_dims d0 = *dims;
@@ -335,8 +336,8 @@ int vgpmp_pathwise_sample(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_p
   GpScratch g = carve(ws, h->robot.dof, dq, &need);
   if (ws_bytes < need) return fail(h, VGPMP_ERR_WORKSPACE, "pathwise_sample: workspace too small (size it with num_timesteps = num_query)");
   cudaStream_t s = (cudaStream_t)stream;
-  if ((rc = check_cuda(h, launch_gp_prepare(h, dq, *p, g.Lc, g.Sfull, g.kl_l, g.kvec, s), "gp_prepare"))) return rc;
-  return check_cuda(h, launch_pathwise(h, dq, *p, *r, Xq, num_query, g.Lc, g.Sfull, f, nullptr, nullptr, nullptr, g.meta, s),
+  if ((rc = check_cuda(h, launch_gp_prepare(h, dq, *p, g.Lc, g.Sfull, g.kl_l, g.kvec, g.Linv, s), "gp_prepare"))) return rc;
+  return check_cuda(h, launch_pathwise(h, dq, *p, *r, Xq, num_query, g.Lc, g.Sfull, g.Linv, f, nullptr, nullptr, nullptr, g.meta, s),
                     "pathwise_sample");
 }
 
@@ -357,11 +358,11 @@ int vgpmp_elbo_fwd_bwd(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_para
   const bool bwd = gr != nullptr;
   {
     StageSpan sp(h, ST_PREPARE, s);
-    if ((rc = check_cuda(h, launch_gp_prepare(h, *dims, *p, g.Lc, g.Sfull, g.kl_l, g.kvec, s), "gp_prepare"))) return rc;
+    if ((rc = check_cuda(h, launch_gp_prepare(h, *dims, *p, g.Lc, g.Sfull, g.kl_l, g.kvec, g.Linv, s), "gp_prepare"))) return rc;
   }
   {
     StageSpan sp(h, ST_PATHWISE, s);
-    if ((rc = check_cuda(h, launch_pathwise(h, *dims, *p, *r, p->X, dims->num_timesteps, g.Lc, g.Sfull, f,
+    if ((rc = check_cuda(h, launch_pathwise(h, *dims, *p, *r, p->X, dims->num_timesteps, g.Lc, g.Sfull, g.Linv, f,
                                             bwd ? g.v : nullptr, bwd ? g.f0 : nullptr, bwd ? g.h0 : nullptr, g.meta, s),
                          "pathwise")))
       return rc;

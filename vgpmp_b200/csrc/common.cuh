@@ -73,6 +73,7 @@ cudaError_t launch_loglik(vgpmp_handle* h, const double* in, int squash, double 
 struct GpScratch {  // carved from the caller's workspace by cabi.cu
   double* Lc;      // [Bp,D,Mp,Mp]
   double* Sfull;   // [Bp,D,Mp,Mp]
+  double* Linv;    // [Bp,D,Mp,Mp]  explicit inverse of the Cholesky factor
   double* kl_l;    // [Bp,D]
   double* kvec;    // [Bp,D,Mp+4]  saved b = Lc^-1 (mu - p_mu) and c = K22^-1 q
   double* v;       // [Bp,D,S,Mp]
@@ -89,10 +90,10 @@ cudaError_t launch_kuu(vgpmp_handle* h, const double* Z, const double* ls, const
 cudaError_t launch_kuf(vgpmp_handle* h, const double* Z, const double* X, const double* ls, const double* var,
                        double* Kuf, int Bp, int M, int N, cudaStream_t s);
 cudaError_t launch_gp_prepare(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, double* Lc, double* Sfull,
-                              double* kl_l, double* kvec, cudaStream_t s);
+                              double* kl_l, double* kvec, double* Linv, cudaStream_t s);
 cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
-                            const double* Xq, int Nq, const double* Lc, const double* Sfull, double* f, double* v,
-                            double* f0, double* h0, double* meta, cudaStream_t s);
+                            const double* Xq, int Nq, const double* Lc, const double* Sfull, const double* Linv,
+                            double* f, double* v, double* f0, double* h0, double* meta, cudaStream_t s);
 cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
                                const GpScratch& ws, const vgpmp_grads& g, cudaStream_t s);
 cudaError_t launch_predict_mean(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const double* Xq, int Nq,

@@ -42,27 +42,25 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return t;
 }
 
-// In-place Cholesky of the leading Mp x Mp block of A (lower), whole CTA cooperates.  Upper triangle zeroed.
+// In-place Cholesky of the leading Mp x Mp block of A (lower), whole CTA cooperates (warps walk rows, lanes walk
+// columns: no integer division in the index math).  Upper triangle zeroed.
 __device__ void chol_inplace(double* A, int Mp) {
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   for (int k = 0; k < Mp; ++k) {
     __syncthreads();
     const double piv = sqrt(A[k * LDM + k]);
+    const double inv = 1.0 / piv;
     __syncthreads();
     if (tid == 0) A[k * LDM + k] = piv;
-    for (int i = k + 1 + tid; i < Mp; i += nt) A[i * LDM + k] /= piv;
+    if (tid > k && tid < Mp) A[tid * LDM + k] *= inv;
     __syncthreads();
-    const int rem = Mp - k - 1;
-    for (int idx = tid; idx < rem * rem; idx += nt) {
-      const int i = k + 1 + idx / rem, j = k + 1 + idx % rem;
+    const int j = k + 1 + lane;
+    for (int i = k + 1 + warp; i < Mp; i += nw)
       if (j <= i) A[i * LDM + j] -= A[i * LDM + k] * A[j * LDM + k];
-    }
   }
   __syncthreads();
-  for (int idx = tid; idx < Mp * Mp; idx += nt) {
-    const int i = idx / Mp, j = idx % Mp;
-    if (j > i) A[i * LDM + j] = 0.0;
-  }
+  for (int i = warp; i < Mp; i += nw)
+    if (lane > i && lane < Mp) A[i * LDM + lane] = 0.0;
   __syncthreads();
 }
 
@@ -89,6 +87,30 @@ __device__ __forceinline__ double warp_bwd_subst(const double* L, int Mp, double
     if (lane < k) d -= L[k * LDM + lane] * bk;
   }
   return out;
+}
+
+// Products with the explicit inverse factor Li = L^-1 (lower, shared memory): lane i owns component i, the input vector
+// sits in shared memory (all lanes read the same element -> broadcast), no shuffles and no cross-lane dependency chain.
+__device__ __forceinline__ double warp_lower_mv(const double* Li, int Mp, const double* x) {   // (Li x)_lane
+  const int lane = threadIdx.x & 31;
+  double acc = 0.0;
+  if (lane < Mp)
+    for (int k = 0; k <= lane; ++k) acc += Li[lane * LDM + k] * x[k];
+  return acc;
+}
+__device__ __forceinline__ double warp_lowerT_mv(const double* Li, int Mp, const double* x) {  // (Li^T x)_lane
+  const int lane = threadIdx.x & 31;
+  double acc = 0.0;
+  if (lane < Mp)
+    for (int k = lane; k < Mp; ++k) acc += Li[k * LDM + lane] * x[k];
+  return acc;
+}
+
+// single-exp evaluation of the Matern-5/2 profile and its derivative
+__device__ __forceinline__ void matern52_both(double r, double& k, double& dk) {
+  const double a = VG_SQRT5 * r, e = exp(-a);
+  k = (1.0 + a + (5.0 / 3.0) * r * r) * e;
+  dk = -(5.0 / 3.0) * r * (1.0 + a) * e;
 }
 
 __global__ void kuu_kernel(int D, int M, double jitter, const double* __restrict__ Z, const double* __restrict__ ls,
@@ -118,7 +140,8 @@ __global__ void kuf_kernel(int D, int M, int N, const double* __restrict__ Z, co
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, double jitter, vgpmp_params P,
                                                         double* __restrict__ Lc_out, double* __restrict__ S_out,
-                                                        double* __restrict__ kl_l, double* __restrict__ kvec) {
+                                                        double* __restrict__ kl_l, double* __restrict__ kvec,
+                                                        double* __restrict__ Linv_out) {
   __shared__ double zy[32], Ksm[32 * LDM], Lsm[32 * LDM], mu[32], red[8], cvec[2];
   const int pl = blockIdx.x, p = pl / D, l = pl % D, Mp = M + 2, tid = threadIdx.x;
   const double ell = P.lengthscales[pl], s2 = P.variances[pl];
@@ -127,27 +150,55 @@ __global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, double ji
     mu[tid] = tid < 2 ? P.query_latent[((size_t)p * 2 + tid) * D + l] : P.q_mu[((size_t)p * M + tid - 2) * D + l];
   }
   __syncthreads();
-  for (int idx = tid; idx < Mp * Mp; idx += blockDim.x) {
-    const int i = idx / Mp, j = idx % Mp;
-    const double k = s2 * vg_matern52(fabs(zy[i] - zy[j]) / ell) + (i == j ? jitter : 0.0);
-    Ksm[i * LDM + j] = k;
-    Lsm[i * LDM + j] = k;
+  const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  __shared__ double qsm[32 * LDM];   // _q_sqrt of this (problem, latent), zero-padded
+  const double* q = P.q_sqrt + (size_t)pl * M * M;
+  for (int idx = tid; idx < 32 * LDM; idx += blockDim.x) { Lsm[idx] = 0.0; qsm[idx] = 0.0; }
+  __syncthreads();
+  for (int i = warp; i < Mp; i += nw) {
+    if (lane < Mp) {
+      const double k = s2 * vg_matern52(fabs(zy[i] - zy[lane]) / ell) + (i == lane ? jitter : 0.0);
+      Ksm[i * LDM + lane] = k;
+      Lsm[i * LDM + lane] = k;
+    }
+    if (i < M && lane < M) qsm[i * LDM + lane] = q[i * M + lane];
   }
   chol_inplace(Lsm, Mp);
   if (Lc_out != nullptr)
-    for (int idx = tid; idx < Mp * Mp; idx += blockDim.x)
-      Lc_out[(size_t)pl * Mp * Mp + idx] = Lsm[(idx / Mp) * LDM + idx % Mp];
+    for (int i = warp; i < Mp; i += nw)
+      if (lane < Mp) Lc_out[(size_t)pl * Mp * Mp + i * Mp + lane] = Lsm[i * LDM + lane];
+  // explicit inverse factor: thread j holds column j of L^-1 in registers,
+  //   x_i = (delta_ij - sum_{k<i} L[i][k] x_k) / L[i][i]   (x_k = 0 for k < j; L is zero-padded beyond Mp)
+  if (Linv_out != nullptr) {
+    __shared__ double Li[32 * LDM];
+    if (tid < 32) {
+      const int j = tid;
+      double x[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        double acc = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) acc -= Lsm[i * LDM + k] * x[k];
+        x[i] = (i < Mp && i >= j && j < Mp) ? acc / Lsm[i * LDM + i] : 0.0;
+        Li[i * LDM + j] = x[i];
+      }
+    }
+    __syncthreads();
+    for (int i = warp; i < Mp; i += nw)
+      if (lane < Mp) Linv_out[(size_t)pl * Mp * Mp + i * Mp + lane] = Li[i * LDM + lane];
+  }
 
   // q_sqrt property: Lc @ pad(_q_sqrt) + jitter * diag(1,1,0,...)   models/vgpmp.py:208-218
-  const double* q = P.q_sqrt + (size_t)pl * M * M;
   if (S_out != nullptr) {
-    for (int idx = tid; idx < Mp * Mp; idx += blockDim.x) {
-      const int i = idx / Mp, j = idx % Mp;
-      double acc = 0.0;
-      if (i >= 2 && j >= 2 && j <= i)
-        for (int k = j; k <= i; ++k) acc += Lsm[i * LDM + k] * q[(k - 2) * M + (j - 2)];
-      if (i == j && i < 2) acc += jitter;
-      S_out[(size_t)pl * Mp * Mp + idx] = acc;
+    for (int i = warp; i < Mp; i += nw) {
+      const int j = lane;
+      if (j < Mp) {
+        double acc = 0.0;
+        if (i >= 2 && j >= 2 && j <= i)
+          for (int k = j; k <= i; ++k) acc += Lsm[i * LDM + k] * qsm[(k - 2) * LDM + (j - 2)];
+        if (i == j && i < 2) acc += jitter;
+        S_out[(size_t)pl * Mp * Mp + i * Mp + j] = acc;
+      }
     }
   }
 
@@ -171,12 +222,11 @@ __global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, double ji
     if (tid >= 2 && tid < Mp) part = b * b;  // mahalanobis of the whitened difference
   }
   // gauss_kl(white): 0.5 * (maha - M - sum log diag(q)^2 + sum q^2)
-  for (int idx = tid; idx < M * M; idx += blockDim.x) {
-    const int a = idx / M, c = idx % M;
-    if (c <= a) {
-      const double v = q[idx];
+  for (int a_ = warp; a_ < M; a_ += nw) {
+    if (lane <= a_) {
+      const double v = qsm[a_ * LDM + lane];
       part += v * v;
-      if (a == c) part -= log(v * v);
+      if (lane == a_) part -= log(v * v);
     }
   }
   const double tot = block_sum(part, red);
@@ -195,7 +245,7 @@ struct PathwiseArgs {
   double jitter;
   const double *Z, *Xq, *ls, *var, *q_mu, *query_latent;
   const double *omega, *tau, *w, *eps_u, *eps_j;
-  const double *Lc, *Sfull;
+  const double *Lc, *Sfull, *Linv;
   double *f, *v, *f0, *h0;
 };
 
@@ -364,11 +414,12 @@ __global__ void __launch_bounds__(256) analyze_grid_kernel(int D, int M, int Nq,
 constexpr int kGB = 32;   // bases per tile
 
 __device__ __forceinline__ void pathwise_update_tail(const PathwiseArgs& a, int pl, int p, int l, int s0, int ns,
-                                                     const double* f0s, int XP, const double* Lsm, const double* Ssm,
+                                                     const double* f0s, int XP, const double* Lism, const double* Ssm,
                                                      int lds, const double* Kfu, double* vs, const double* mu,
                                                      double sqrtj) {
   // f0s[i*XP + x]: prior draw of sample s0+i at point x (x < Nq: query points, then the Mp inducing points)
-  // Ssm: q_sqrt_full with leading dimension lds (shared or global memory)
+  // Lism: explicit inverse Cholesky factor in shared memory; Ssm: q_sqrt_full with leading dimension lds
+  // v = Khat^-1 r = Li^T (Li r); vs doubles as the per-sample scratch row ([kST][32], one row per warp-sample)
   const int Mp = a.M + 2, Nq = a.Nq, S = a.S, D = a.D;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
   for (int i = warp; i < ns; i += nw) {
@@ -380,9 +431,16 @@ __device__ __forceinline__ void pathwise_update_tail(const PathwiseArgs& a, int 
       for (int k = 0; k <= lane; ++k) u += Ssm[lane * lds + k] * eu[k];
       r = u - f0s[(size_t)i * XP + Nq + lane] - sqrtj * a.eps_j[((size_t)pl * S + s) * Mp + lane];
     }
-    const double y = warp_fwd_subst(Lsm, Mp, r);
-    const double vv = warp_bwd_subst(Lsm, Mp, y);
-    vs[i * 32 + lane] = lane < Mp ? vv : 0.0;
+    double* row = vs + i * 32;
+    row[lane] = r;
+    __syncwarp();
+    const double y = warp_lower_mv(Lism, Mp, row);
+    __syncwarp();
+    row[lane] = y;
+    __syncwarp();
+    const double vv = warp_lowerT_mv(Lism, Mp, row);
+    __syncwarp();
+    row[lane] = lane < Mp ? vv : 0.0;
     if (lane < Mp && a.v != nullptr) a.v[((size_t)pl * S + s) * Mp + lane] = vv;
   }
   __syncthreads();
@@ -557,7 +615,7 @@ __global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, c
     }
     __syncthreads();  // slices 1.. of red are dead from here on: Lsm / Kfu live behind slice 1
     for (int idx = tid; idx < Mp * Mp; idx += nt)
-      Lsm[(idx / Mp) * LDM + idx % Mp] = a.Lc[(size_t)pl * Mp * Mp + idx];
+      Lsm[(idx / Mp) * LDM + idx % Mp] = a.Linv[(size_t)pl * Mp * Mp + idx];   // explicit inverse factor
     for (int idx = tid; idx < Nq * Mp; idx += nt) {
       const int n = idx / Mp, m = idx % Mp;
       Kfu[idx] = s2 * vg_matern52(fabs(a.Xq[(size_t)n * D + l] - zy[m]) / ell);
@@ -575,7 +633,7 @@ struct BackwardArgs {
   double jitter, klw;
   const double *Z, *X, *ls, *var, *q_sqrt;
   const double *eps_u;
-  const double *Lc, *kvec, *v, *f0, *h0, *df;
+  const double *Lc, *Linv, *kvec, *v, *f0, *h0, *df;
   double *d_q_mu, *d_q_sqrt, *d_ls, *d_var;
 };
 
@@ -585,36 +643,39 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
   extern __shared__ double sm[];
   const int D = a.D, M = a.M, Mp = M + 2, N = a.N, S = a.S, A = N + Mp;
   const int pl = blockIdx.x, p = pl / D, l = pl % D;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
-  double* Lsm = sm;                    // [32][LDM] chol factor
-  double* G = Lsm + 32 * LDM;          // [32][LDM] d ELBO / d Khat (general, not symmetrised)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
+  double* Lsm = sm;                    // [32][LDM] chol factor L
+  double* Lism = Lsm + 32 * LDM;       // [32][LDM] explicit inverse L^-1
+  double* G = Lism + 32 * LDM;         // [32][LDM] d ELBO / d Khat (general, not symmetrised)
   double* GS = G + 32 * LDM;           // [32][LDM] d ELBO / d q_sqrt_full
   double* GL = GS + 32 * LDM;          // [32][LDM] d ELBO / d Lc
-  double* Kfu = GL + 32 * LDM;         // [N][Mp]
-  double* gv = Kfu + (size_t)N * Mp;   // [kBT][32]
+  double* Kfu = GL + 32 * LDM;         // [N][32]
+  double* gv = Kfu + (size_t)N * 32;   // [kBT][32]
   double* gr = gv + kBT * 32;          // [kBT][32]
   double* vsm = gr + kBT * 32;         // [kBT][32]
-  double* gmu = vsm + kBT * 32;        // [32]
+  double* epsm = vsm + kBT * 32;       // [kBT][32] this tile's eps_u
+  double* gmu = epsm + kBT * 32;       // [32]
   double* zy = gmu + 32;               // [32]
   double* bvec = zy + 32;              // [32]
   double* gd = bvec + 32;              // [32]
   double* red = gd + 32;               // [8]
   double* dft = red + 8;               // [kBT][N]  this tile's slice of d ELBO / d f
-  double* epsm = dft + (size_t)kBT * N; // [kBT][32] this tile's eps_u
 
-  const double ell = a.ls[pl], s2 = a.var[pl];
+  const double ell = a.ls[pl], s2 = a.var[pl], inv_ell = 1.0 / ell;
   if (tid < 32) {
     zy[tid] = tid < Mp ? zy_at(a.Z, D, l, tid) : 0.0;
     bvec[tid] = tid < Mp ? a.kvec[(size_t)pl * (Mp + 4) + tid] : 0.0;
     gmu[tid] = 0.0;
   }
-  for (int idx = tid; idx < 32 * LDM; idx += nt) { G[idx] = 0.0; GS[idx] = 0.0; GL[idx] = 0.0; Lsm[idx] = 0.0; }
+  for (int idx = tid; idx < 32 * LDM; idx += nt) { G[idx] = 0.0; GS[idx] = 0.0; GL[idx] = 0.0; Lsm[idx] = 0.0; Lism[idx] = 0.0; }
   __syncthreads();
-  for (int idx = tid; idx < Mp * Mp; idx += nt) Lsm[(idx / Mp) * LDM + idx % Mp] = a.Lc[(size_t)pl * Mp * Mp + idx];
-  for (int idx = tid; idx < N * Mp; idx += nt) {
-    const int n = idx / Mp, m = idx % Mp;
-    Kfu[idx] = s2 * vg_matern52(fabs(a.X[(size_t)n * D + l] - zy[m]) / ell);
-  }
+  for (int i = warp; i < Mp; i += nw)
+    if (lane < Mp) {
+      Lsm[i * LDM + lane] = a.Lc[(size_t)pl * Mp * Mp + i * Mp + lane];
+      Lism[i * LDM + lane] = a.Linv[(size_t)pl * Mp * Mp + i * Mp + lane];
+    }
+  for (int n = warp; n < N; n += nw)
+    Kfu[n * 32 + lane] = lane < Mp ? s2 * vg_matern52(fabs(a.X[(size_t)n * D + l] - zy[lane]) * inv_ell) : 0.0;
   __syncthreads();
 
   double acc_ls = 0.0, acc_var = 0.0;  // per-thread partial hyper-parameter gradients
@@ -624,7 +685,7 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
     const int ns = min(kBT, S - s0);
     // stage this tile's df (strided in global: [s,n,D]), v and eps_u in shared memory
     for (int idx = tid; idx < kBT * N; idx += nt) {
-      const int i = idx / N, n = idx % N;
+      const int i = idx / N, n = idx - i * N;
       dft[idx] = i < ns ? dfp[((size_t)(s0 + i) * N + n) * D] : 0.0;
     }
     for (int idx = tid; idx < kBT * 32; idx += nt) {
@@ -640,38 +701,45 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
       double t = 0.0;
       if (i < ns && m < Mp) {
         const double* dfs = dft + (size_t)i * N;
-        for (int n = 0; n < N; ++n) t += Kfu[n * Mp + m] * dfs[n];
+        for (int n = 0; n < N; ++n) t += Kfu[n * 32 + m] * dfs[n];
       }
       gv[idx] = t;
     }
     __syncthreads();
-    // (3) gr = Khat^-1 gv (warp per sample)
-    if (warp < kBT) {
-      const double y = warp_fwd_subst(Lsm, Mp, gv[warp * 32 + lane]);
-      const double z = warp_bwd_subst(Lsm, Mp, y);
-      gr[warp * 32 + lane] = (warp < ns && lane < Mp) ? z : 0.0;
+    // (3) gr = Khat^-1 gv = Li^T (Li gv), one warp per sample, dense products with the explicit inverse factor
+    for (int i = warp; i < kBT; i += nw) {
+      const double y = warp_lower_mv(Lism, Mp, gv + i * 32);
+      gr[i * 32 + lane] = y;                      // scratch
+      __syncwarp();
+      const double z = warp_lowerT_mv(Lism, Mp, gr + i * 32);
+      __syncwarp();
+      gr[i * 32 + lane] = (i < ns && lane < Mp) ? z : 0.0;
     }
     __syncthreads();
-    // (2) Kfu path to the hyper-parameters: sum_{s} df[s,n] v[s,m] dKfu[n,m]/dtheta
-    for (int idx = tid; idx < N * Mp; idx += nt) {
-      const int n = idx / Mp, m = idx % Mp;
-      double t = 0.0;
-      for (int i = 0; i < ns; ++i) t += dft[(size_t)i * N + n] * vsm[i * 32 + m];
-      const double r = fabs(a.X[(size_t)n * D + l] - zy[m]) / ell;
-      acc_var += t * vg_matern52(r);
-      acc_ls += t * s2 * vg_matern52_dr(r) * (-r / ell);
+    // (2) Kfu path to the hyper-parameters: sum_s df[s,n] v[s,m] dKfu[n,m]/dtheta
+    for (int n = warp; n < N; n += nw) {
+      if (lane < Mp) {
+        double t = 0.0;
+        for (int i = 0; i < ns; ++i) t += dft[(size_t)i * N + n] * vsm[i * 32 + lane];
+        const double r = fabs(a.X[(size_t)n * D + l] - zy[lane]) * inv_ell;
+        double k, dk;
+        matern52_both(r, k, dk);
+        acc_var += t * k;
+        acc_ls += t * s2 * dk * (-r * inv_ell);
+      }
     }
     // (4) G -= gr v^T ; (6) GS += gr eps_u^T ; gmu += gr
-    for (int idx = tid; idx < Mp * Mp; idx += nt) {
-      const int i = idx / Mp, j = idx % Mp;
-      double t = 0.0, u = 0.0;
-      for (int k = 0; k < ns; ++k) {
-        const double g = gr[k * 32 + i];
-        t += g * vsm[k * 32 + j];
-        u += g * epsm[k * 32 + j];
+    for (int i = warp; i < Mp; i += nw) {
+      if (lane < Mp) {
+        double t = 0.0, u = 0.0;
+        for (int k = 0; k < ns; ++k) {
+          const double g = gr[k * 32 + i];
+          t += g * vsm[k * 32 + lane];
+          u += g * epsm[k * 32 + lane];
+        }
+        G[i * LDM + lane] -= t;
+        GS[i * LDM + lane] += u;
       }
-      G[i * LDM + j] -= t;
-      GS[i * LDM + j] += u;
     }
     if (tid < Mp) {
       double t = 0.0;
@@ -680,7 +748,7 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
     }
     // (5) prior path: d f0(X) = df, d f0(Zy) = -gr
     for (int idx = tid; idx < ns * A; idx += nt) {
-      const int i = idx / A, xx = idx % A;
+      const int i = idx / A, xx = idx - i * A;
       const double g = xx < N ? dft[(size_t)i * N + xx] : -gr[i * 32 + xx - N];
       const size_t o = ((size_t)pl * S + s0 + i) * A + xx;
       acc_var += g * a.f0[o] / (2.0 * s2);
@@ -692,37 +760,38 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
   // (7) q_sqrt_full = Lc pad(q) + jitter diag  ->  d q = tril((Lc^T GS)[2:,2:]),  GL += GS pad(q)^T
   const double* q = a.q_sqrt + (size_t)pl * M * M;
   double* dq = a.d_q_sqrt + (size_t)pl * M * M;
-  for (int idx = tid; idx < M * M; idx += nt) {
-    const int r_ = idx / M, c_ = idx % M;
-    double t = 0.0;
-    if (c_ <= r_) {
-      for (int i = r_ + 2; i < Mp; ++i) t += Lsm[i * LDM + r_ + 2] * GS[i * LDM + c_ + 2];
-      const double qv = q[idx];
-      t -= a.klw * (qv - (r_ == c_ ? 1.0 / qv : 0.0));  // - d KL / d q_sqrt
+  for (int r_ = warp; r_ < M; r_ += nw) {
+    if (lane < M) {
+      const int c_ = lane;
+      double t = 0.0;
+      if (c_ <= r_) {
+        for (int i = r_ + 2; i < Mp; ++i) t += Lsm[i * LDM + r_ + 2] * GS[i * LDM + c_ + 2];
+        const double qv = q[r_ * M + c_];
+        t -= a.klw * (qv - (r_ == c_ ? 1.0 / qv : 0.0));  // - d KL / d q_sqrt
+      }
+      dq[r_ * M + c_] = t;
     }
-    dq[idx] = t;
   }
-  for (int idx = tid; idx < Mp * Mp; idx += nt) {
-    const int i = idx / Mp, k = idx % Mp;
+  for (int i = warp; i < Mp; i += nw) {
+    const int k = lane;
     if (k >= 2 && k <= i) {
       double t = 0.0;
       for (int j = 2; j <= k; ++j) t += GS[i * LDM + j] * q[(k - 2) * M + (j - 2)];
       GL[i * LDM + k] += t;
     }
   }
-  __syncthreads();
   // (8) KL reverse: b = L^-1 d, KL = 0.5 sum_{i>=2} b_i^2 + ...;  ELBO carries -KL
+  if (warp == 0) gd[lane] = (lane >= 2 && lane < Mp) ? -a.klw * bvec[lane] : 0.0;   // d ELBO / d b
+  __syncthreads();
   if (warp == 0) {
-    const double gb = (lane >= 2 && lane < Mp) ? -a.klw * bvec[lane] : 0.0;
-    const double g = warp_bwd_subst(Lsm, Mp, gb);  // d ELBO / d d
+    const double g = warp_lowerT_mv(Lism, Mp, gd);  // d ELBO / d d = L^-T gb
+    __syncwarp();
     gd[lane] = lane < Mp ? g : 0.0;
   }
   __syncthreads();
   const double c0 = a.kvec[(size_t)pl * (Mp + 4) + Mp], c1 = a.kvec[(size_t)pl * (Mp + 4) + Mp + 1];
-  for (int idx = tid; idx < Mp * Mp; idx += nt) {
-    const int i = idx / Mp, j = idx % Mp;
-    if (j <= i) GL[i * LDM + j] -= gd[i] * bvec[j];
-  }
+  for (int i = warp; i < Mp; i += nw)
+    if (lane <= i) GL[i * LDM + lane] -= gd[i] * bvec[lane];
   if (tid < Mp) {
     gmu[tid] += gd[tid];
     // p_mu = Khat[:, :2] c  ->  d Khat[i, 0:2] += (-gd_i) c
@@ -734,8 +803,8 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
     // gc = Khat[:, :2]^T (-gd);  c = K22^-1 q~  ->  d K22 -= (K22^-1 gc) c^T     (lane i owns row i of Khat[:, :2])
     double gc0 = 0.0, gc1 = 0.0;
     if (lane < Mp) {
-      const double k0 = s2 * vg_matern52(fabs(zy[lane] - zy[0]) / ell) + (lane == 0 ? a.jitter : 0.0);
-      const double k1 = s2 * vg_matern52(fabs(zy[lane] - zy[1]) / ell) + (lane == 1 ? a.jitter : 0.0);
+      const double k0 = s2 * vg_matern52(fabs(zy[lane] - zy[0]) * inv_ell) + (lane == 0 ? a.jitter : 0.0);
+      const double k1 = s2 * vg_matern52(fabs(zy[lane] - zy[1]) * inv_ell) + (lane == 1 ? a.jitter : 0.0);
       gc0 = -k0 * gd[lane];
       gc1 = -k1 * gd[lane];
     }
@@ -753,11 +822,11 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
     }
   }
   __syncthreads();
-  // (9) Cholesky reverse (Murray 2016): Khat_bar = L^-T Phi(L^T L_bar) L^-1, Phi = tril with halved diagonal
-  double* Pm = GS;  // reuse
-  __syncthreads();
-  for (int idx = tid; idx < Mp * Mp; idx += nt) {
-    const int i = idx / Mp, j = idx % Mp;
+  // (9) Cholesky reverse (Murray 2016): Khat_bar = L^-T Phi(L^T L_bar) L^-1, Phi = tril with halved diagonal.
+  //     With the explicit inverse this is three triangular products, no substitutions.
+  double* Pm = GS;  // reuse: P = Phi(L^T GL)
+  for (int i = warp; i < Mp; i += nw) {
+    const int j = lane;
     double t = 0.0;
     if (j <= i) {
       for (int k = i; k < Mp; ++k) t += Lsm[k * LDM + i] * GL[k * LDM + j];
@@ -766,26 +835,34 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
     Pm[i * LDM + j] = t;
   }
   __syncthreads();
-  // Y = L^-T P (column by column), stored back in Pm
-  for (int col = warp; col < Mp; col += (nt >> 5)) {
-    const double y = warp_bwd_subst(Lsm, Mp, lane < Mp ? Pm[lane * LDM + col] : 0.0);
-    __syncwarp();
-    if (lane < Mp) Pm[lane * LDM + col] = y;
+  double* T1 = GL;  // reuse: T1 = P Li  (lower x lower)
+  for (int i = warp; i < Mp; i += nw) {
+    const int j = lane;
+    double t = 0.0;
+    if (j <= i)
+      for (int k = j; k <= i; ++k) t += Pm[i * LDM + k] * Lism[k * LDM + j];
+    T1[i * LDM + j] = t;
   }
   __syncthreads();
-  // Khat_bar = Y L^-1  <=>  rows: solve L^T w = Y[row,:]^T
-  for (int row = warp; row < Mp; row += (nt >> 5)) {
-    const double wv = warp_bwd_subst(Lsm, Mp, lane < Mp ? Pm[row * LDM + lane] : 0.0);
-    if (lane < Mp) G[row * LDM + lane] += wv;
+  for (int i = warp; i < Mp; i += nw) {   // G += Li^T T1
+    const int j = lane;
+    if (j < Mp) {
+      double t = 0.0;
+      for (int k = max(i, j); k < Mp; ++k) t += Lism[k * LDM + i] * T1[k * LDM + j];
+      G[i * LDM + j] += t;
+    }
   }
   __syncthreads();
   // (10) contract with d Khat / d theta
-  for (int idx = tid; idx < Mp * Mp; idx += nt) {
-    const int i = idx / Mp, j = idx % Mp;
-    const double r = fabs(zy[i] - zy[j]) / ell;
-    const double g = G[i * LDM + j];
-    acc_var += g * vg_matern52(r);
-    acc_ls += g * s2 * vg_matern52_dr(r) * (-r / ell);
+  for (int i = warp; i < Mp; i += nw) {
+    if (lane < Mp) {
+      const double r = fabs(zy[i] - zy[lane]) * inv_ell;
+      double k, dk;
+      matern52_both(r, k, dk);
+      const double g = G[i * LDM + lane];
+      acc_var += g * k;
+      acc_ls += g * s2 * dk * (-r * inv_ell);
+    }
   }
   const double tv = block_sum(acc_var, red);
   const double tl = block_sum(acc_ls, red);
@@ -1005,16 +1082,16 @@ cudaError_t launch_kuf(vgpmp_handle* h, const double* Z, const double* X, const 
 }
 
 cudaError_t launch_gp_prepare(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, double* Lc, double* Sfull,
-                              double* kl_l, double* kvec, cudaStream_t s) {
+                              double* kl_l, double* kvec, double* Linv, cudaStream_t s) {
   gp_prepare_kernel<<<d.num_problems * h->robot.dof, 128, 0, s>>>(h->robot.dof, d.num_inducing, h->lik.jitter, p, Lc,
-                                                                  Sfull, kl_l, kvec);
+                                                                  Sfull, kl_l, kvec, Linv);
   h->launches++;
   return cudaGetLastError();
 }
 
 cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
-                            const double* Xq, int Nq, const double* Lc, const double* Sfull, double* f, double* v,
-                            double* f0, double* h0, double* meta, cudaStream_t s) {
+                            const double* Xq, int Nq, const double* Lc, const double* Sfull, const double* Linv,
+                            double* f, double* v, double* f0, double* h0, double* meta, cudaStream_t s) {
   PathwiseArgs a;
   a.D = h->robot.dof; a.M = d.num_inducing; a.Nq = Nq; a.S = d.num_samples; a.B = d.num_bases;
   const int Mp = a.M + 2, A = Nq + Mp;
@@ -1025,7 +1102,7 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
   a.jitter = h->lik.jitter;
   a.Z = p.Z; a.Xq = Xq; a.ls = p.lengthscales; a.var = p.variances; a.q_mu = p.q_mu; a.query_latent = p.query_latent;
   a.omega = r.omega; a.tau = r.tau; a.w = r.w; a.eps_u = r.eps_u; a.eps_j = r.eps_j;
-  a.Lc = Lc; a.Sfull = Sfull; a.f = f; a.v = v; a.f0 = f0; a.h0 = h0;
+  a.Lc = Lc; a.Sfull = Sfull; a.Linv = Linv; a.f = f; a.v = v; a.f0 = f0; a.h0 = h0;
   cudaError_t e;
   // fast path: equispaced rank-1 inputs (decided on the device, see analyze_grid_kernel)
   int XT = 3, threads = 128;
@@ -1080,10 +1157,10 @@ cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp
   a.klw = d.kl_shards > 1 ? 1.0 / (double)d.kl_shards : 1.0;
   a.Z = p.Z; a.X = p.X; a.ls = p.lengthscales; a.var = p.variances; a.q_sqrt = p.q_sqrt;
   a.eps_u = r.eps_u;
-  a.Lc = ws.Lc; a.kvec = ws.kvec; a.v = ws.v; a.f0 = ws.f0; a.h0 = ws.h0; a.df = ws.df;
+  a.Lc = ws.Lc; a.Linv = ws.Linv; a.kvec = ws.kvec; a.v = ws.v; a.f0 = ws.f0; a.h0 = ws.h0; a.df = ws.df;
   a.d_q_mu = g.d_q_mu; a.d_q_sqrt = g.d_q_sqrt; a.d_ls = g.d_lengthscales; a.d_var = g.d_variances;
   const int Mp = a.M + 2;
-  const size_t smem = sizeof(double) * (4 * 32 * LDM + (size_t)a.N * Mp + 4 * kBT * 32 + 4 * 32 + 16 + (size_t)kBT * a.N);
+  const size_t smem = sizeof(double) * (5 * 32 * LDM + (size_t)a.N * 32 + 4 * kBT * 32 + 4 * 32 + 16 + (size_t)kBT * a.N);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(gp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
