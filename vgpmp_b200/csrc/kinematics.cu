@@ -222,11 +222,11 @@ struct SphereBatch {
 };
 
 template <int D, bool BWD, int NB>
-__global__ void __launch_bounds__(kThreads, 4) loglik_kernel(RobotDev rb, SdfDev sdf, LikDev lk,
+__global__ void __launch_bounds__(kThreads, 3) loglik_kernel(RobotDev rb, SdfDev sdf, LikDev lk,
                                                          const double* __restrict__ in, int squash, double upstream,
                                                          double* __restrict__ logp, double* __restrict__ d_in,
                                                          int64_t n) {
-  extern __shared__ double axes[];  // BWD only: [D][7][kThreads]  (axis z, axis x point n, prefix term)
+  extern __shared__ double axes[];  // BWD only: [D][8][kThreads]  (axis z, axis x point n, prefix term, d theta/d in)
   const int tid = threadIdx.x;
   const int64_t c = (int64_t)blockIdx.x * kThreads + tid;
   if (c >= n) return;
@@ -243,7 +243,12 @@ __global__ void __launch_bounds__(kThreads, 4) loglik_kernel(RobotDev rb, SdfDev
     if (k > 0) {
       const int j = k - 1;
       const double xin = in[c * D + j];
-      const double thj = squash ? rb.lo[j] + (rb.hi[j] - rb.lo[j]) * stable_sigmoid(xin) : xin;
+      double thj = xin, dsq = 1.0;
+      if (squash) {
+        const double sg = stable_sigmoid(xin), span = rb.hi[j] - rb.lo[j];
+        thj = rb.lo[j] + span * sg;
+        dsq = span * sg * (1.0 - sg);
+      }
       double zx, zy, zz, ox, oy, oz;
       if (BWD && !rb.craig) {  // Spong: joint j turns about z of frame j-1, through its origin
         zx = A.r[2]; zy = A.r[5]; zz = A.r[8]; ox = A.t[0]; oy = A.t[1]; oz = A.t[2];
@@ -254,7 +259,8 @@ __global__ void __launch_bounds__(kThreads, 4) loglik_kernel(RobotDev rb, SdfDev
           zx = A.r[2]; zy = A.r[5]; zz = A.r[8]; ox = A.t[0]; oy = A.t[1]; oz = A.t[2];
         }
         const double nx = zy * oz - zz * oy, ny = zz * ox - zx * oz, nz = zx * oy - zy * ox;
-        double* slot = axes + (size_t)j * 7 * kThreads + tid;
+        double* slot = axes + (size_t)j * 8 * kThreads + tid;
+        slot[7 * kThreads] = dsq;
         slot[0] = zx; slot[kThreads] = zy; slot[2 * kThreads] = zz;
         slot[3 * kThreads] = nx; slot[4 * kThreads] = ny; slot[5 * kThreads] = nz;
         slot[6 * kThreads] = zx * Tw[0] + zy * Tw[1] + zz * Tw[2] - (nx * Fw[0] + ny * Fw[1] + nz * Fw[2]);
@@ -300,28 +306,23 @@ __global__ void __launch_bounds__(kThreads, 4) loglik_kernel(RobotDev rb, SdfDev
   if (BWD) {
 #pragma unroll
     for (int j = 0; j < D; ++j) {
-      const double* slot = axes + (size_t)j * 7 * kThreads + tid;
+      const double* slot = axes + (size_t)j * 8 * kThreads + tid;
       const double dth = slot[0] * Tw[0] + slot[kThreads] * Tw[1] + slot[2 * kThreads] * Tw[2] -
                          (slot[3 * kThreads] * Fw[0] + slot[4 * kThreads] * Fw[1] + slot[5 * kThreads] * Fw[2]) -
                          slot[6 * kThreads];
-      double dsq = 1.0;
-      if (squash) {
-        const double s = stable_sigmoid(in[c * D + j]);
-        dsq = (rb.hi[j] - rb.lo[j]) * s * (1.0 - s);
-      }
-      d_in[c * D + j] = upstream * dth * dsq;
+      d_in[c * D + j] = upstream * dth * slot[7 * kThreads];
     }
   }
 }
 
-constexpr int kSphereBatch = 2;
+constexpr int kSphereBatch = 4;
 
 template <int D>
 cudaError_t launch_loglik_d(vgpmp_handle* h, const double* in, int squash, double upstream, double* logp, double* d_in,
                             int64_t n, cudaStream_t s) {
   const unsigned blocks = (unsigned)((n + kThreads - 1) / kThreads);
   if (d_in != nullptr) {
-    const size_t smem = sizeof(double) * D * 7 * kThreads;
+    const size_t smem = sizeof(double) * D * 8 * kThreads;
     auto kern = loglik_kernel<D, true, kSphereBatch>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
