@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, double ji
 // ---------------------------------------------------------------------------------------------
 struct PathwiseArgs {
   int D, M, Nq, S, B, XG, KS;
+  int nchunk, chunk;   // the S samples are split into nchunk CTAs per (problem, latent), `chunk` samples each (multiple of kST)
   double jitter;
   const double *Z, *Xq, *ls, *var, *q_mu, *query_latent;
   const double *omega, *tau, *w, *eps_u, *eps_j;
@@ -253,7 +254,8 @@ __global__ void __launch_bounds__(768) pathwise_kernel(PathwiseArgs a, const dou
   if (meta != nullptr && meta[0] != 0.0) return;  // equispaced rank-1 inputs: pathwise_grid_kernel does the work
   extern __shared__ double sm[];
   const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, B = a.B, A = Nq + Mp;
-  const int pl = blockIdx.x, p = pl / D, l = pl % D;
+  const int pl = blockIdx.x / a.nchunk, p = pl / D, l = pl % D;
+  const int s_begin = (blockIdx.x % a.nchunk) * a.chunk, s_end = min(a.S, s_begin + a.chunk);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
   const int XP = a.XG * 32;
   // shared-memory carve-up
@@ -302,11 +304,11 @@ __global__ void __launch_bounds__(768) pathwise_kernel(PathwiseArgs a, const dou
   const double* ta = a.tau + (size_t)pl * B;
   const double* wp = a.w + (size_t)pl * S * B;
 
-  for (int s0 = 0; s0 < S; s0 += kST) {
+  for (int s0 = s_begin; s0 < s_end; s0 += kST) {
     double acc0[kST], acc1[kST];
 #pragma unroll
     for (int i = 0; i < kST; ++i) { acc0[i] = 0.0; acc1[i] = 0.0; }
-    const int ns = min(kST, S - s0);
+    const int ns = min(kST, s_end - s0);
     if (ks < a.KS) {
       for (int b = b0; b < b1; ++b) {
         double pr = 0.0;
@@ -479,14 +481,15 @@ __global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, c
   if (meta[0] == 0.0) return;  // inputs are not an equispaced rank-1 grid: the general kernel does the work
   extern __shared__ __align__(16) double sm[];
   const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, B = a.B, A = Nq + Mp;
-  const int pl = blockIdx.x, p = pl / D, l = pl % D;
+  const int pl = blockIdx.x / a.nchunk, p = pl / D, l = pl % D;
+  const int s_begin = (blockIdx.x % a.nchunk) * a.chunk, s_end = min(a.S, s_begin + a.chunk);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
   const int XG = (A + XT - 1) / XT, XP = XG * XT, AP = XP | 1;   // odd row stride: conflict-free column walks
   // main-loop view of shared memory
   double* feat = sm;                                  // [2][kGB][AP]
   double* Wt = feat + (((size_t)2 * kGB * AP + 1) & ~(size_t)1);   // [2 buffers][kGB][kST], 16-byte aligned
-  double* cb = Wt + 2 * kGB * kST;                    // [2][kGB] c_b = sum_d omega_bd / lengthscale
-  double* tb = cb + 2 * kGB;                          // [2][kGB] tau_b
+  double* osum = Wt + 2 * kGB * kST;                  // [2][4][kGB] partial sums over the input dims of omega_b
+  double* tb = osum + 2 * 4 * kGB;                    // [2][kGB] tau_b
   // tail view (after the base loop the feature tile is dead): red | Lsm | Kfu | vs | mu | zy
   double* red = sm;                                   // [KS][2][kST][XP]
   double* Lsm = red + (size_t)2 * 2 * kST * XP;
@@ -513,24 +516,25 @@ __global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, c
   const int xg = tid % XG, which = (tid / XG) & 1, ks = tid / (2 * XG);
   const int bper = (kGB + KS - 1) / KS;
 
-  for (int s0 = 0; s0 < S; s0 += kST) {
-    const int ns = min(kST, S - s0);
+  for (int s0 = s_begin; s0 < s_end; s0 += kST) {
+    const int ns = min(kST, s_end - s0);
     double acc[XT][kST];
 #pragma unroll
     for (int i = 0; i < XT; ++i)
 #pragma unroll
       for (int j = 0; j < kST; ++j) acc[i][j] = 0.0;
 
-    // staging registers: this thread's share of the next tile's operands (prefetched one tile ahead)
-    double st_c = 0.0, st_t = 0.0, st_w[2] = {0.0, 0.0};
+    // staging registers: this thread's share of the next tile's operands, prefetched one tile ahead with no dependent
+    // arithmetic.  Warp g (< 4) loads omega[base = lane][g] and omega[base][g + 4]; the sum over input dimensions is
+    // folded through shared memory when the tile is staged.
+    double st_o[2] = {0.0, 0.0}, st_t = 0.0, st_w[2] = {0.0, 0.0};
     auto prefetch = [&](int b0) {
       const int nb = min(kGB, B - b0);
-      st_c = 0.0; st_t = 0.0;
-      if (tid < kGB && tid < nb) {
-        for (int d = 0; d < D; ++d) st_c += om[(size_t)(b0 + tid) * D + d];
-        st_c *= inv_ell;
-        st_t = ta[b0 + tid];
+      if (warp < 4) {
+        st_o[0] = (lane < nb && warp < D) ? om[(size_t)(b0 + lane) * D + warp] : 0.0;
+        st_o[1] = (lane < nb && warp + 4 < D) ? om[(size_t)(b0 + lane) * D + warp + 4] : 0.0;
       }
+      st_t = (tid < kGB && tid < nb) ? ta[b0 + tid] : 0.0;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int idx = tid + k * nt;       // kGB*kST = 256 elements, nt >= 128
@@ -541,7 +545,8 @@ __global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, c
     prefetch(0);
     int buf = 0;
     for (int b0 = 0; b0 < B; b0 += kGB, buf ^= 1) {
-      if (tid < kGB) { cb[buf * kGB + tid] = st_c; tb[buf * kGB + tid] = st_t; }
+      if (warp < 4) osum[(buf * 4 + warp) * kGB + lane] = st_o[0] + st_o[1];
+      if (tid < kGB) tb[buf * kGB + tid] = st_t;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int idx = tid + k * nt;
@@ -550,7 +555,8 @@ __global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, c
       if (b0 + kGB < B) prefetch(b0 + kGB);   // lands while this tile is being processed
       __syncthreads();  // staging visible; previous tile's contraction finished -> feature tile is free
       {  // phase 1: features by rotation along the grid
-        const double c = cb[buf * kGB + lane], tau = tb[buf * kGB + lane];
+        const double* os = osum + (size_t)buf * 4 * kGB + lane;
+        const double c = (os[0] + os[kGB] + os[2 * kGB] + os[3 * kGB]) * inv_ell, tau = tb[buf * kGB + lane];
         double* fc = feat + (size_t)lane * AP;
         double* fd = feat + (size_t)(kGB + lane) * AP;
         if (warp < nxc) {
@@ -622,6 +628,165 @@ __global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, c
     }
     __syncthreads();
     pathwise_update_tail(a, pl, p, l, s0, ns, red, XP, Lsm, a.Sfull + (size_t)pl * Mp * Mp, Mp, Kfu, vs, mu, sqrtj);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-synchronous variant of the equispaced sampler (used when N + Mp <= 96): ONE WARP per (problem, latent, sample
+// tile).  No block-level barrier exists anywhere in the kernel, so the FP64 pipe is kept busy by the warp scheduler
+// interleaving ~13 independent warps per SM that sit in different phases:
+//   phase 1  lane = (basis of an 8-basis tile, chunk of points): 2-4 sincos, then one rotation per point;
+//   phase 2  lane = (cos | d/dlengthscale feature, point group): XT points x 8 samples = 8*XT register accumulators.
+// f0 / h0 go to global memory; the pathwise update runs in pathwise_tail_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWB = 8;   // bases per tile of the warp kernel
+
+template <int XT>
+__global__ void __launch_bounds__(32, 12) pathwise_warp_kernel(PathwiseArgs a, const double* __restrict__ meta) {
+  if (meta[0] == 0.0) return;
+  extern __shared__ __align__(16) double sm[];
+  const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, B = a.B, A = Nq + Mp;
+  const int tiles_s = (S + kST - 1) / kST;
+  const int pl = blockIdx.x / tiles_s, l = pl % D;
+  const int s0 = (blockIdx.x % tiles_s) * kST, ns = min(kST, S - s0);
+  const int lane = threadIdx.x;
+  const int XG = (A + XT - 1) / XT, XP = XG * XT, AP = XP | 1;   // XG <= 16
+  const int plane = (kWB * AP + 15) & ~15;                        // second feature plane starts on a 128-byte boundary
+  double* feat = sm;                                  // [2][kWB][AP]
+  double* Wt = feat + 2 * plane;                      // [kWB][kST]
+  double* cb = Wt + kWB * kST;                        // [kWB]
+  double* tb = cb + kWB;                              // [kWB]
+
+  const double ell = a.ls[pl], s2 = a.var[pl];
+  const double amp = sqrt(2.0 * s2 / (double)B), inv_ell = 1.0 / ell;
+  const double t0 = meta[1], dt = meta[2], z0 = meta[3], dz = meta[4];
+  const double* om = a.omega + (size_t)pl * B * D;
+  const double* ta = a.tau + (size_t)pl * B;
+  const double* wp = a.w + (size_t)pl * S * B;
+
+  // phase-1 role
+  const int pb = lane & (kWB - 1), chunk = lane >> 3;           // 8 bases x 4 chunks
+  const int per = (Nq + 2) / 3;                                  // chunks 0..2 walk the query grid, chunk 3 the inducing points
+  // phase-2 role
+  const int which = lane >> 4, xg = lane & 15;
+  const bool worker = xg < XG;
+
+  double acc[XT][kST];
+#pragma unroll
+  for (int i = 0; i < XT; ++i)
+#pragma unroll
+    for (int j = 0; j < kST; ++j) acc[i][j] = 0.0;
+
+  // staging registers, prefetched one tile ahead with no dependent arithmetic: lane (base = lane&7, group = lane>>3)
+  // loads omega[base][group] and omega[base][group+4]; the sum over the input dimensions is folded at store time
+  double st_o[2], st_t = 0.0, st_w[2];
+  auto prefetch = [&](int b0) {
+    const int b = b0 + (lane & 7), g = lane >> 3;
+    st_o[0] = (b < B && g < D) ? om[(size_t)b * D + g] : 0.0;
+    st_o[1] = (b < B && g + 4 < D) ? om[(size_t)b * D + g + 4] : 0.0;
+    st_t = (lane < kWB && b < B) ? ta[b] : 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int idx = lane + 32 * k, i = idx >> 3, bb = idx & 7;   // kWB * kST = 64 weights per tile
+      st_w[k] = (i < ns && b0 + bb < B) ? wp[(size_t)(s0 + i) * B + b0 + bb] : 0.0;
+    }
+  };
+  prefetch(0);
+  for (int b0 = 0; b0 < B; b0 += kWB) {
+    __syncwarp();
+    {
+      double c = st_o[0] + st_o[1];
+      c += __shfl_xor_sync(kFull, c, 8);
+      c += __shfl_xor_sync(kFull, c, 16);
+      if (lane < kWB) { cb[lane] = c * inv_ell; tb[lane] = st_t; }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int idx = lane + 32 * k;
+      Wt[(idx & 7) * kST + (idx >> 3)] = st_w[k];
+    }
+    if (b0 + kWB < B) prefetch(b0 + kWB);
+    __syncwarp();
+    {  // phase 1: every lane runs the same code on lane-dependent run parameters (no divergent paths)
+      const double c = cb[pb], tau = tb[pb];
+      double* fc = feat + (size_t)pb * AP;
+      double* fd = feat + plane + (size_t)pb * AP;
+      const bool onx = chunk < 3;
+      const int first = onx ? chunk * per : 0;
+      const int count = onx ? min(Nq, first + per) - first : M;
+      rotate_run(fc, fd, onx ? 0 : Nq + 2, first, count, onx ? t0 : z0, onx ? dt : dz, c, tau, amp, inv_ell);
+      if (chunk < 2) {  // the two conditioned timesteps Zy[0] = 0, Zy[1] = 1: one point each on chunk-0 / chunk-1 lanes
+        const double t = (double)chunk;
+        double sn, cs;
+        sincos(t * c + tau, &sn, &cs);
+        fc[Nq + chunk] = amp * cs;
+        fd[Nq + chunk] = amp * sn * (t * c * inv_ell);
+      }
+    }
+    __syncwarp();
+    if (worker) {  // phase 2
+      const double* fsrc = feat + which * plane + xg;
+#pragma unroll 2
+      for (int b = 0; b < kWB; ++b) {
+        double fv[XT], wv[kST];
+#pragma unroll
+        for (int i = 0; i < XT; ++i) fv[i] = fsrc[(size_t)b * AP + i * XG];
+#pragma unroll
+        for (int j = 0; j < kST; j += 2) {
+          const double2 w2 = *reinterpret_cast<const double2*>(Wt + b * kST + j);
+          wv[j] = w2.x; wv[j + 1] = w2.y;
+        }
+#pragma unroll
+        for (int i = 0; i < XT; ++i)
+#pragma unroll
+          for (int j = 0; j < kST; ++j) acc[i][j] += fv[i] * wv[j];
+      }
+    }
+  }
+  if (worker) {
+    double* dst = which == 0 ? a.f0 : a.h0;
+#pragma unroll
+    for (int i = 0; i < XT; ++i) {
+      const int x = xg + i * XG;
+      if (x < A)
+#pragma unroll
+        for (int j = 0; j < kST; ++j)
+          if (j < ns) dst[((size_t)pl * S + s0 + j) * A + x] = acc[i][j];
+    }
+  }
+}
+
+// Pathwise update for the warp kernel: v = Khat^-1 (u - f0(Zy) - sqrt(jitter) eps_j), f = f0(X) + Kfu v.
+// One CTA (128 threads) per (problem, latent); samples in tiles of kST.
+__global__ void __launch_bounds__(128) pathwise_tail_kernel(PathwiseArgs a, const double* __restrict__ meta) {
+  if (meta[0] == 0.0) return;
+  extern __shared__ double sm[];
+  const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, A = Nq + Mp;
+  const int pl = blockIdx.x, p = pl / D, l = pl % D;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
+  double* f0s = sm;                                   // [kST][A]
+  double* Lism = f0s + (size_t)kST * A;               // [32][LDM]
+  double* Kfu = Lism + 32 * LDM;                      // [Nq][Mp]
+  double* vs = Kfu + (size_t)Nq * Mp;                 // [kST][32]
+  double* mu = vs + kST * 32;
+  double* zy = mu + 32;
+  const double ell = a.ls[pl], s2 = a.var[pl], sqrtj = sqrt(a.jitter);
+  if (tid < 32) {
+    zy[tid] = tid < Mp ? zy_at(a.Z, D, l, tid) : 0.0;
+    mu[tid] = tid >= Mp ? 0.0 : (tid < 2 ? a.query_latent[((size_t)p * 2 + tid) * D + l]
+                                        : a.q_mu[((size_t)p * M + tid - 2) * D + l]);
+  }
+  for (int i = warp; i < Mp; i += nw)
+    if (lane < Mp) Lism[i * LDM + lane] = a.Linv[(size_t)pl * Mp * Mp + i * Mp + lane];
+  __syncthreads();
+  for (int n = warp; n < Nq; n += nw)
+    if (lane < Mp) Kfu[n * Mp + lane] = s2 * vg_matern52(fabs(a.Xq[(size_t)n * D + l] - zy[lane]) / ell);
+  for (int s0 = 0; s0 < S; s0 += kST) {
+    const int ns = min(kST, S - s0);
+    __syncthreads();
+    for (int idx = tid; idx < ns * A; idx += nt) f0s[idx] = a.f0[((size_t)pl * S + s0) * A + idx];
+    __syncthreads();
+    pathwise_update_tail(a, pl, p, l, s0, ns, f0s, A, Lism, a.Sfull + (size_t)pl * Mp * Mp, Mp, Kfu, vs, mu, sqrtj);
   }
 }
 
@@ -1100,6 +1265,14 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
   a.KS = 24 / a.XG;
   if (a.KS > a.B) a.KS = a.B;
   a.jitter = h->lik.jitter;
+  {
+    // enough CTAs to fill the machine a few times over even for a single problem with many samples
+    const int pairs = d.num_problems * a.D, tiles = (a.S + kST - 1) / kST;
+    int want = (4 * h->num_sms + pairs - 1) / pairs;
+    a.nchunk = std::max(1, std::min(tiles, want));
+    a.chunk = ((tiles + a.nchunk - 1) / a.nchunk) * kST;
+    a.nchunk = (a.S + a.chunk - 1) / a.chunk;
+  }
   a.Z = p.Z; a.Xq = Xq; a.ls = p.lengthscales; a.var = p.variances; a.q_mu = p.q_mu; a.query_latent = p.query_latent;
   a.omega = r.omega; a.tau = r.tau; a.w = r.w; a.eps_u = r.eps_u; a.eps_j = r.eps_j;
   a.Lc = Lc; a.Sfull = Sfull; a.Linv = Linv; a.f = f; a.v = v; a.f0 = f0; a.h0 = h0;
@@ -1123,7 +1296,7 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
   size_t smem_g = 0;
   if (grid_ok) {
     const int XGq = (A + XT - 1) / XT, XP = XGq * XT, AP = XP | 1;
-    const size_t main_view = (((size_t)2 * kGB * AP + 1) & ~(size_t)1) + 2 * kGB * kST + 4 * kGB;
+    const size_t main_view = (((size_t)2 * kGB * AP + 1) & ~(size_t)1) + 2 * kGB * kST + 10 * kGB;
     const size_t tail_view = (size_t)2 * 2 * kST * XP + 32 * LDM + (size_t)Nq * Mp + kST * 32 + 64;
     const int ks = std::max(1, std::min(4, threads / (2 * XGq)));
     const size_t red_view = (size_t)ks * 2 * kST * XP;
@@ -1132,11 +1305,30 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
   }
   if (grid_ok) {
     analyze_grid_kernel<<<1, 256, 0, s>>>(a.D, a.M, Nq, Xq, p.Z, meta);
-    auto kern = XT == 3 ? pathwise_grid_kernel<3> : pathwise_grid_kernel<4>;
-    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g)) != cudaSuccess)
-      return e;
-    kern<<<d.num_problems * a.D, threads, smem_g, s>>>(a, meta);
-    h->launches += 2;
+    h->launches++;
+    const bool warp_path = h->allow_warp_path && A <= 96 && f0 != nullptr && h0 != nullptr && a.M >= 2;
+    if (warp_path) {
+      const int xt = std::max(4, (A + 15) / 16);        // <= 16 point groups per feature plane
+      const int XGq = (A + xt - 1) / xt, XP = XGq * xt, AP = XP | 1;
+      const int plane = (kWB * AP + 15) & ~15;
+      const size_t smem_w = sizeof(double) * ((size_t)2 * plane + kWB * kST + 2 * kWB);
+      const int tiles_s = (a.S + kST - 1) / kST;
+      void (*kern)(PathwiseArgs, const double*) = xt <= 4 ? pathwise_warp_kernel<4>
+                                                : (xt == 5 ? pathwise_warp_kernel<5> : pathwise_warp_kernel<6>);
+      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w)) != cudaSuccess) return e;
+      kern<<<d.num_problems * a.D * tiles_s, 32, smem_w, s>>>(a, meta);
+      const size_t smem_t = sizeof(double) * ((size_t)kST * A + 32 * LDM + (size_t)Nq * Mp + kST * 32 + 64);
+      if ((e = cudaFuncSetAttribute(pathwise_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)) != cudaSuccess)
+        return e;
+      pathwise_tail_kernel<<<d.num_problems * a.D, 128, smem_t, s>>>(a, meta);
+      h->launches += 2;
+    } else {
+      auto kern = XT == 3 ? pathwise_grid_kernel<3> : pathwise_grid_kernel<4>;
+      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g)) != cudaSuccess)
+        return e;
+      kern<<<d.num_problems * a.D * a.nchunk, threads, smem_g, s>>>(a, meta);
+      h->launches++;
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   const int threads_gen = 32 * a.XG * a.KS;
@@ -1144,7 +1336,7 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   e = cudaFuncSetAttribute(pathwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  pathwise_kernel<<<d.num_problems * a.D, threads_gen, smem, s>>>(a, grid_ok ? meta : nullptr);
+  pathwise_kernel<<<d.num_problems * a.D * a.nchunk, threads_gen, smem, s>>>(a, grid_ok ? meta : nullptr);
   h->launches++;
   return cudaGetLastError();
 }
