@@ -69,14 +69,20 @@ __device__ __forceinline__ int clamp_index(double q, int n) {
   return min(max(i, 0), n - 1);
 }
 
-// trunc((a)/delta) exactly as the reference computes it (a correctly rounded float64 division, then truncation), but
-// without paying for a division per axis per sphere: a * (1/delta) is within 2 ulp of a/delta, so the two can only
-// truncate differently when the product sits within a few ulp of an integer -- only then is the true division done.
+// clip(trunc(a / delta), 0, n-1) exactly as the reference computes it (a correctly rounded float64 division, truncation
+// toward zero, clip) without paying for a division per axis per sphere.  q = a * (1/delta) is within 2 ulp of a/delta, so
+// both truncate alike unless q sits next to an integer; only then (fraction within 1e-9 of 0 or 1, i.e. ~1e-9 of all
+// lookups) is the true division evaluated.  Out-of-range values need no care: anything at or beyond an end clips to
+// that end under either rounding.  (cvt.rzi.s32.f64 saturates, so far-away points are safe.)
 __device__ __forceinline__ int voxel_index(double a, double delta, double inv_delta, int n) {
-  double q = a * inv_delta;
-  const double k = rint(q);
-  if (fabs(q - k) <= 8.0 * 2.220446049250313e-16 * fabs(k)) q = a / delta;  // (also taken at k == 0 only if q == 0)
-  return clamp_index(q, n);
+  const double q = a * inv_delta;
+  int i = __double2int_rz(q);
+  if ((unsigned)i < (unsigned)n) {
+    const double frac = q - (double)i;
+    if (!(frac > 1e-9 && frac < 1.0 - 1e-9)) i = clamp_index(a / delta, n);
+    return i;
+  }
+  return min(max(i, 0), n - 1);
 }
 
 struct Voxel {
@@ -237,12 +243,14 @@ __global__ void __launch_bounds__(kThreads, 3) loglik_kernel(RobotDev rb, SdfDev
   double lp = 0.0;
   const double inv_sigma = 1.0 / lk.sigma_obs;
   int p = 0;
+  double xnext = in[c * D];   // joint inputs are fetched one joint ahead of their use
 
 #pragma unroll 1
   for (int k = 0; k <= D; ++k) {
     if (k > 0) {
       const int j = k - 1;
-      const double xin = in[c * D + j];
+      const double xin = xnext;
+      if (k < D) xnext = in[c * D + k];
       double thj = xin, dsq = 1.0;
       if (squash) {
         const double sg = stable_sigmoid(xin), span = rb.hi[j] - rb.lo[j];
