@@ -410,6 +410,56 @@ def test_mesh_to_sdf_vs_bruteforce_oracle(tmp_path):
     assert np.array_equal(back.data, fine.data) and back.delta == fine.delta
 
 
+def test_config5_shapes_vs_oracle():
+    """BASELINE config 5 shapes (S=256 samples, N=64 timesteps, B=1024 bases) on two problems: 32 sample tiles per latent."""
+    case = H.make_case("franka", "bookshelves", num_problems=2, S=256, N=64, B=1024, seed=55)
+    model = H.make_model(case)
+    out = model.elbo_and_grads(case["X"], draws=case["draws_stacked"])
+    for b, p in enumerate(case["oracle"]):
+        ref = O.elbo_and_grads(p, case["q_mu"][b], case["q_sqrt"][b], case["ls"][b], case["var"][b], case["draws"][b])
+        assert abs(float(out["elbo"][b]) - ref["elbo"]) <= 1e-8 * abs(ref["elbo"])
+        for key in ("q_mu", "q_sqrt", "lengthscales", "variances"):
+            assert H.rel_err(_np(out["d_" + key][b]), ref["d_" + key]) < 1e-5, key
+
+
+def test_full_size_batch_properties():
+    """BASELINE config 2 at full size (55 pairs x 5 runs = 275 problems, S=7, N=70, M=24, B=1024), where the oracle would take
+    minutes: size-independent properties of the fused iteration."""
+    from vgpmp_b200.utils.miscellaneous import load_problemset
+    ps = load_problemset("franka", "bookshelves")
+    queries = [q for _ in range(5) for q in ps["queries"]]
+    case = H.make_case("franka", "bookshelves", num_problems=275, B=1024, seed=9, perturb=False)
+    assert len(case["queries"]) == 275 and len(queries) == 275
+    model = H.make_model(case, seed=42)
+    X = case["X"]
+    a = model.elbo_and_grads(X, want_aux=True)
+    b = model.elbo_and_grads(X, want_aux=True)
+    for k in ("elbo", "d_q_mu", "d_q_sqrt", "d_lengthscales", "d_variances", "kl"):          # idempotent / deterministic
+        assert torch.equal(a[k], b[k]), k
+    assert torch.isfinite(a["elbo"]).all() and all(torch.isfinite(a[k]).all() for k in a)
+    # ELBO = alpha/S * sum logp - KL, reassembled from the auxiliary outputs
+    want = model.alpha / model.num_samples * a["logp"].sum(dim=(1, 2)) - a["kl"]
+    assert H.rel_err(_np(a["elbo"]), _np(want)) < 1e-12
+    # problems are independent: problem 137 evaluated alone with its keyed draws reproduces its row of the batch
+    sub = dict(case)
+    for key in ("q_mu", "q_sqrt", "ls", "var"):
+        sub[key] = case[key][137:138]
+    sub["queries"] = case["queries"][137:138]
+    one = H.make_model(sub, seed=42)
+    dims = one._dims(case["N"])
+    draws = one._eng.rng_fill(dims, 42, 0, problem_offset=137)
+    solo = one._eng.elbo_fwd_bwd(dims, one._params(one._eng.dev(X)), draws, need_grad=True)
+    assert torch.equal(solo["elbo"][0], a["elbo"][137])
+    assert torch.equal(solo["d_q_mu"][0], a["d_q_mu"][137]) and torch.equal(solo["d_lengthscales"][0], a["d_lengthscales"][137])
+    # the five copies of a start/goal pair share parameters but not draws: same KL, different Monte-Carlo likelihood
+    assert torch.allclose(a["kl"][:55], a["kl"][55:110], rtol=0, atol=0)
+    assert not torch.equal(a["logp"][:55], a["logp"][55:110])
+    # strict upper triangle of d_q_sqrt is structurally zero; lower triangle is not
+    iu = torch.triu_indices(24, 24, offset=1)
+    assert float(a["d_q_sqrt"][..., iu[0], iu[1]].abs().max()) == 0.0
+    assert float(a["d_q_sqrt"].abs().max()) > 0.0
+
+
 def test_errors_are_reported_not_swallowed():
     from vgpmp_b200 import _cabi
     case = H.make_case(num_problems=1, S=2, N=5, M=5, B=8)

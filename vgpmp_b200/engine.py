@@ -198,12 +198,18 @@ class Engine:
     # ---- GP / fused iteration ------------------------------------------------------------------
     @staticmethod
     def params_struct(q_mu, q_sqrt, ls, var, query_latent, Z, X) -> _cabi.Params:
-        return _cabi.Params(q_mu.data_ptr(), q_sqrt.data_ptr(), ls.data_ptr(), var.data_ptr(), query_latent.data_ptr(),
-                            Z.data_ptr(), X.data_ptr() if X is not None else None)
+        ps = _cabi.Params(q_mu.data_ptr(), q_sqrt.data_ptr(), ls.data_ptr(), var.data_ptr(), query_latent.data_ptr(),
+                          Z.data_ptr(), X.data_ptr() if X is not None else None)
+        # the struct only holds raw addresses: keep the tensors alive as long as it lives, otherwise a temporary (e.g.
+        # `dev(X)`) is returned to the caching allocator and re-used by the very call that still reads it
+        ps._keep = (q_mu, q_sqrt, ls, var, query_latent, Z, X)
+        return ps
 
     @staticmethod
     def draws_struct(d: dict) -> _cabi.Draws:
-        return _cabi.Draws(*(d[k].data_ptr() for k in ("omega", "tau", "w", "eps_u", "eps_j")))
+        ds = _cabi.Draws(*(d[k].data_ptr() for k in ("omega", "tau", "w", "eps_u", "eps_j")))
+        ds._keep = tuple(d[k] for k in ("omega", "tau", "w", "eps_u", "eps_j"))
+        return ds
 
     def alloc_draws(self, dims: _cabi.Dims) -> dict:
         Bp, D, B, S, Mp = dims.num_problems, self.D, dims.num_bases, dims.num_samples, dims.num_inducing + 2
