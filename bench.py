@@ -275,17 +275,31 @@ def run_b200(args):
         sdf_ms = stages["loglik_fwd_bwd"]["ms_per_launch"]
         sdf_bytes = evals_per_step * 32                         # one 32-byte {value, gradient} record per sphere-SDF eval
         achieved = sdf_bytes / (sdf_ms * 1e-3) / 1e9
-        roofline = {"kernel": "loglik_kernel<7,true,2> (FK + one 256-bit {value,gradient} record load per sphere + hinge + reverse pass)", "bound": "hbm",
+        roofline = {"kernel": "loglik_kernel<7,true,4> (FK + one 256-bit {value,gradient} record load per sphere + hinge + reverse pass)", "bound": "hbm",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": sdf_bytes,
                     "ms_per_launch": sdf_ms, "share_of_step": stages["loglik_fwd_bwd"]["share"],
                     "dominant_stage": dominant}
-        # sampler stage: FP64 CUDA-core work; only the contraction (f0 and d f0/d lengthscale) is counted, 2 flops per FMA
+        tr = ROOT / "profiles" / "roofline_traffic.json"
+        if tr.exists():
+            t = json.loads(tr.read_text()).get("loglik_fwd_bwd")
+            if t:
+                roofline["traffic"] = t["dram_bytes_per_launch"]
+                roofline["traffic_source"] = t["source"]
+        # dominant stage by time = the sampler: FP64 CUDA-core bound (the path has no tensor-core-shaped work that holds
+        # the float64 tolerance).  Algorithmic flops = the contraction (f0 and d f0/d lengthscale, 2 flops per FMA) plus
+        # 6 FMA-class ops per generated feature; peak = FP64 FMA rate measured now by vgpmp_probe_fp64_tflops.
         A = N + M + 2
-        pw_flops = Bp * D * 2 * 2 * S * A * B * 2
+        pw_flops = Bp * D * (2 * 2 * S * A * B * 2 + 2 * 6 * A * B)
         pw = stages.get("pathwise_sample")
+        out_dom = None
         if pw:
-            roofline["sampler_contraction_fp64_tflops"] = pw_flops / (pw["ms_per_launch"] * 1e-3) / 1e12
+            peak64 = float(eng.lib.vgpmp_probe_fp64_tflops(local))
+            ach = pw_flops / (pw["ms_per_launch"] * 1e-3) / 1e12
+            out_dom = {"kernel": "pathwise_grid_kernel<3> (rotation-recurrence Fourier features + register-tiled contraction + pathwise update)",
+                       "bound": "fp64", "achieved": ach, "peak": peak64, "unit": "TFLOP/s", "frac": ach / peak64 if peak64 > 0 else None,
+                       "peak_source": "measured now: vgpmp_probe_fp64_tflops (DFMA chains, CUDA events)", "traffic": None,
+                       "algorithmic_flops_per_launch": pw_flops, "ms_per_launch": pw["ms_per_launch"], "share_of_step": pw["share"]}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak",
@@ -300,7 +314,8 @@ def run_b200(args):
             "e2e": {"value": world * Bp * args.steps / (ms_e2e / 1000.0), "unit": UNIT,
                     "h2d_bytes_per_step": int(X.nbytes), "d2h_bytes_per_step": int(Bp * 8),
                     "ms_per_step": ms_e2e / args.steps, "api": "VGPMP.train_step_host -> vgpmp_train_step_host"},
-            "gpu_launches": int(launches), "stages": stages, "roofline": roofline, "clocks": clk,
+            "gpu_launches": int(launches), "stages": stages, "roofline": roofline, "roofline_dominant_stage": out_dom,
+            "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
             steps = 40

@@ -223,6 +223,10 @@ int vgpmp_mesh_to_sdf(int device, const double* tri, const double* plane, const 
                       int32_t num_pieces, int32_t nx, int32_t ny, int32_t nz, const double* origin, double delta,
                       double* out_host);
 
+/* Measured FP64 FMA throughput of `device` in TFLOP/s (dependent-free DFMA chains, CUDA events): the roofline
+ * denominator bench.py uses for the FP64-bound sampler stage.  Negative on error. */
+double vgpmp_probe_fp64_tflops(int device);
+
 /* ---- measurement hooks (bench.py / profiles; no reference counterpart beyond the `timing` decorator of
  * utils/miscellaneous.py:46-56) ---------------------------------------------------------------------------
  * With profiling enabled every stage launch of vgpmp_elbo_fwd_bwd / vgpmp_adam_step / vgpmp_rng_fill is bracketed by

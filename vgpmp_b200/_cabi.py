@@ -86,6 +86,7 @@ SYMBOLS = {
     "vgpmp_draws_bytes": (_SZ, [C.POINTER(Dims), _I]),
     "vgpmp_mesh_to_sdf": (_I, [_I, c_double_p, c_double_p, c_int32_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.c_int32, c_double_p, _D, c_double_p]),
+    "vgpmp_probe_fp64_tflops": (_D, [_I]),
     "vgpmp_set_option": (_I, [_P, C.c_char_p, _I]),
     "vgpmp_profile_enable": (_I, [_P, _I]),
     "vgpmp_profile_collect": (_I, [_P, c_double_p, C.POINTER(C.c_int64)]),

@@ -476,7 +476,9 @@ __device__ __forceinline__ void rotate_run(double* fc, double* fd, int col0, int
   }
 }
 
-template <int XT>
+// ST = live sample accumulators per thread (7 when the whole sample set fits one tile of 7, else 8); all shared-memory
+// layouts keep the tile stride kST = 8.
+template <int XT, int ST>
 __global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, const double* __restrict__ meta) {
   if (meta[0] == 0.0) return;  // inputs are not an equispaced rank-1 grid: the general kernel does the work
   extern __shared__ __align__(16) double sm[];
@@ -518,11 +520,11 @@ __global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, c
 
   for (int s0 = s_begin; s0 < s_end; s0 += kST) {
     const int ns = min(kST, s_end - s0);
-    double acc[XT][kST];
+    double acc[XT][ST];
 #pragma unroll
     for (int i = 0; i < XT; ++i)
 #pragma unroll
-      for (int j = 0; j < kST; ++j) acc[i][j] = 0.0;
+      for (int j = 0; j < ST; ++j) acc[i][j] = 0.0;
 
     // staging registers: this thread's share of the next tile's operands, prefetched one tile ahead with no dependent
     // arithmetic.  Warp g (< 4) loads omega[base = lane][g] and omega[base][g + 4]; the sum over input dimensions is
@@ -591,7 +593,7 @@ __global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, c
 #pragma unroll
           for (int i = 0; i < XT; ++i)
 #pragma unroll
-            for (int j = 0; j < kST; ++j) acc[i][j] += fv[i] * wv[j];
+            for (int j = 0; j < ST; ++j) acc[i][j] += fv[i] * wv[j];
         }
       }
     }
@@ -601,7 +603,7 @@ __global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, c
 #pragma unroll
       for (int i = 0; i < XT; ++i)
 #pragma unroll
-        for (int j = 0; j < kST; ++j) red[((size_t)(ks * 2 + which) * kST + j) * XP + xg + i * XG] = acc[i][j];
+        for (int j = 0; j < kST; ++j) red[((size_t)(ks * 2 + which) * kST + j) * XP + xg + i * XG] = j < ST ? acc[i][j < ST ? j : 0] : 0.0;
     }
     if (tid < 32) {
       zy[tid] = tid < Mp ? zy_at(a.Z, D, l, tid) : 0.0;
@@ -1323,7 +1325,9 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
       pathwise_tail_kernel<<<d.num_problems * a.D, 128, smem_t, s>>>(a, meta);
       h->launches += 2;
     } else {
-      auto kern = XT == 3 ? pathwise_grid_kernel<3> : pathwise_grid_kernel<4>;
+      void (*kern)(PathwiseArgs, const double*);
+      if (a.S <= 7) kern = XT == 3 ? pathwise_grid_kernel<3, 7> : pathwise_grid_kernel<4, 7>;
+      else kern = XT == 3 ? pathwise_grid_kernel<3, 8> : pathwise_grid_kernel<4, 8>;
       if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g)) != cudaSuccess)
         return e;
       kern<<<d.num_problems * a.D * a.nchunk, threads, smem_g, s>>>(a, meta);

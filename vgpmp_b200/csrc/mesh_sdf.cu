@@ -125,3 +125,49 @@ extern "C" int vgpmp_mesh_to_sdf(int device, const double* tri, const double* pl
   cudaFree(d_tri); cudaFree(d_plane); cudaFree(d_pe); cudaFree(d_out);
   return rc;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// FP64 FMA throughput probe: the roofline denominator of the sampler stage (MEASURED_PEAKS.json has HBM and bf16 only).
+// 16 independent DFMA chains per thread, 4 CTAs x 256 threads per SM, timed with CUDA events.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters, double a, double b) {
+  double x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = a + i * 1e-3 + threadIdx.x * 1e-6;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = fma(x[i], b, a);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += x[i];
+  if (s == 123.456) out[0] = s;  // keeps the loop alive without a store in the common case
+}
+}  // namespace
+
+extern "C" double vgpmp_probe_fp64_tflops(int device) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+  double* out = nullptr;
+  if (cudaMalloc(&out, 8) != cudaSuccess) return -1.0;
+  const int blocks = prop.multiProcessorCount * 4, iters = 20000;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0);
+    fp64_probe_kernel<<<blocks, 256>>>(out, iters, 0.999, 1.0000001);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
+    if (rep > 0 && ms > 0.f) best = fmax(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  return best;
+}
