@@ -204,8 +204,21 @@ int vgpmp_rng_fill(vgpmp_handle* h, const vgpmp_dims* dims, uint64_t seed, uint6
                    int64_t sample_offset, double* omega, double* tau, double* w, double* eps_u, double* eps_j,
                    void* stream);
 
+/* Draw prefetch on the handle's internal side stream (two buffer slots), so that generating step t+1's randomness
+ * overlaps with step t's kernels.  Protocol per step t with slot = t & 1:
+ *   vgpmp_rng_join(h, slot, stream)            stream waits until slot's draws are complete
+ *   ... vgpmp_elbo_fwd_bwd / vgpmp_adam_step on `stream` reading slot's buffers ...
+ *   vgpmp_rng_release(h, slot, stream)         marks the point after which slot's buffers may be overwritten
+ *   vgpmp_rng_fill_async(..., slot ^ 1)        fills the other slot for iteration t+1 (waits for its last release) */
+int vgpmp_rng_fill_async(vgpmp_handle* h, const vgpmp_dims* dims, uint64_t seed, uint64_t iteration,
+                         int64_t problem_offset, int64_t sample_offset, double* omega, double* tau, double* w,
+                         double* eps_u, double* eps_j, int slot);
+int vgpmp_rng_join(vgpmp_handle* h, int slot, void* stream);
+int vgpmp_rng_release(vgpmp_handle* h, int slot, void* stream);
+
 /* ---- reference-facing step with HOST buffers (training_loop body, utils/miscellaneous.py:87-103) ---
- * Copies X_host [N,D] to the device, draws the step's randomness on the device, runs ELBO forward+reverse and the Adam
+ * Copies X_host [N,D] to the device, draws the step's randomness on the device (when draws_bytes holds two draw sets,
+ * 2 * vgpmp_draws_bytes, the next step's draws are generated on a side stream while this step computes), runs ELBO forward+reverse and the Adam
  * update on the handle-resident state registered with vgpmp_adam, copies loss = -ELBO [Bp] back to loss_host and
  * synchronises the stream.  Returns after the loss is readable (like `loss = tf_optimization_step(...)`). */
 int vgpmp_train_step_host(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* st, const double* query_latent,

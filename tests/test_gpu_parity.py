@@ -266,6 +266,37 @@ def test_adam_training_steps_vs_oracle():
             assert H.rel_err(_np(model._variances[b]), O.softplus(pr["raw_var"])) < 1e-6
 
 
+def test_pipelined_device_draws_training_vs_oracle():
+    """train_step with device draws (next step's draws generated on the side stream while this step computes) and the
+    host-buffer step `train_step_host` must both follow the oracle's Adam trajectory on the materialised draws of
+    iterations 0..3 -- i.e. the double-buffered prefetch hands every step the right iteration's randomness."""
+    case = H.make_case(num_problems=2, S=5, N=20, M=8, B=32, seed=8)
+    lr = case["pp"]["learning_rate"]
+    tril = np.tril(np.ones((8, 8)))
+    sig = lambda x: 1.0 / (1.0 + np.exp(-x))
+    for mode in ("device", "host"):
+        model = H.make_model(case, seed=31)
+        probe = H.make_model(case, seed=31)
+        states = [O.AdamState() for _ in case["oracle"]]
+        params = [dict(q_mu=case["q_mu"][b].copy(), q_sqrt=case["q_sqrt"][b].copy(),
+                       raw_ls=O.softplus_inv(case["ls"][b]), raw_var=O.softplus_inv(case["var"][b])) for b in range(2)]
+        Xh = torch.from_numpy(case["X"].copy()).pin_memory()
+        for step in range(4):
+            loss = model.train_step(case["X"]) if mode == "device" else model.train_step_host(Xh).clone()
+            d = {k: _np(v) for k, v in probe._eng.rng_fill(probe._dims(20), 31, step).items()}
+            for b, p in enumerate(case["oracle"]):
+                pr = params[b]
+                ref = O.elbo_and_grads(p, pr["q_mu"], pr["q_sqrt"], O.softplus(pr["raw_ls"]), O.softplus(pr["raw_var"]),
+                                       {k: v[b] for k, v in d.items()})
+                assert abs(float(loss[b]) + ref["elbo"]) <= 1e-7 * abs(ref["elbo"]), (mode, step)
+                O.adam_step(pr, dict(q_mu=-ref["d_q_mu"], q_sqrt=-ref["d_q_sqrt"] * tril,
+                                     raw_ls=-ref["d_lengthscales"] * sig(pr["raw_ls"]),
+                                     raw_var=-ref["d_variances"] * sig(pr["raw_var"])), states[b], lr)
+                pr["q_sqrt"] = np.tril(pr["q_sqrt"])
+                assert H.rel_err(_np(model._q_mu[b]), pr["q_mu"]) < 1e-6, (mode, step)
+                assert H.rel_err(_np(model._lengthscales[b]), O.softplus(pr["raw_ls"])) < 1e-6, (mode, step)
+
+
 def test_trainable_flags_freeze_parameters():
     from vgpmp_b200.utils.miscellaneous import disable_param_opt
     case = H.make_case(num_problems=1, S=3, N=10, M=5, B=16)

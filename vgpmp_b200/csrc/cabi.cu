@@ -231,6 +231,11 @@ int vgpmp_destroy(vgpmp_handle* h) {
   cudaSetDevice(h->device);
   for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_filled[i]) cudaEventDestroy(h->ev_filled[i]);
+    if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
+  }
+  if (h->side) cudaStreamDestroy(h->side);
   if (h->rec_dev) cudaFree(h->rec_dev);
   delete h;
   return VGPMP_OK;
@@ -413,6 +418,49 @@ int vgpmp_rng_fill(vgpmp_handle* h, const vgpmp_dims* dims, uint64_t seed, uint6
                                        eps_j, (cudaStream_t)stream), "rng_fill");
 }
 
+static int ensure_side(vgpmp_handle* h) {
+  if (h->side) return VGPMP_OK;
+  cudaError_t e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&h->ev_filled[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming);
+  }
+  return check_cuda(h, e, "side stream");
+}
+
+int vgpmp_rng_fill_async(vgpmp_handle* h, const vgpmp_dims* dims, uint64_t seed, uint64_t iteration,
+                         int64_t problem_offset, int64_t sample_offset, double* omega, double* tau, double* w,
+                         double* eps_u, double* eps_j, int slot) {
+  int rc = check_dims(h, dims);
+  if (rc) return rc;
+  if (slot < 0 || slot > 1 || !omega || !tau || !w || !eps_u || !eps_j)
+    return fail(h, VGPMP_ERR_INVALID, "rng_fill_async: bad argument");
+  if ((rc = ensure_side(h))) return rc;
+  if (h->consumed_valid[slot] &&
+      (rc = check_cuda(h, cudaStreamWaitEvent(h->side, h->ev_consumed[slot], 0), "rng_fill_async wait")))
+    return rc;
+  {
+    StageSpan sp(h, ST_RNG, h->side);
+    if ((rc = check_cuda(h, launch_rng_fill(h, *dims, seed, iteration, problem_offset, sample_offset, omega, tau, w,
+                                            eps_u, eps_j, h->side), "rng_fill_async")))
+      return rc;
+  }
+  return check_cuda(h, cudaEventRecord(h->ev_filled[slot], h->side), "rng_fill_async record");
+}
+
+int vgpmp_rng_join(vgpmp_handle* h, int slot, void* stream) {
+  if (!h || slot < 0 || slot > 1 || !h->side) return fail(h, VGPMP_ERR_INVALID, "rng_join: nothing in flight");
+  return check_cuda(h, cudaStreamWaitEvent((cudaStream_t)stream, h->ev_filled[slot], 0), "rng_join");
+}
+
+int vgpmp_rng_release(vgpmp_handle* h, int slot, void* stream) {
+  if (!h || slot < 0 || slot > 1) return fail(h, VGPMP_ERR_INVALID, "rng_release: bad slot");
+  int rc = ensure_side(h);
+  if (rc) return rc;
+  h->consumed_valid[slot] = true;
+  return check_cuda(h, cudaEventRecord(h->ev_consumed[slot], (cudaStream_t)stream), "rng_release");
+}
+
 int vgpmp_train_step_host(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* st, const double* query_latent,
                           const double* Z, const double* X_host, double* X_dev, uint64_t seed, double* draws_ws,
                           size_t draws_bytes, const vgpmp_grads* g, double* elbo_dev, double* loss_host, void* ws,
@@ -428,17 +476,35 @@ int vgpmp_train_step_host(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* s
   if ((rc = check_cuda(h, cudaMemcpyAsync(X_dev, X_host, sizeof(double) * dims->num_timesteps * D, cudaMemcpyHostToDevice, s),
                        "H2D X")))
     return rc;
-  Carver c(draws_ws);
-  double* omega = c.take(Bp * D * B * D);
-  double* tau = c.take(Bp * D * B);
-  double* w = c.take(Bp * D * S * B);
-  double* eps_u = c.take(Bp * D * S * Mp);
-  double* eps_j = c.take(Bp * D * S * Mp);
-  if ((rc = vgpmp_rng_fill(h, dims, seed, (uint64_t)st->step, 0, 0, omega, tau, w, eps_u, eps_j, stream))) return rc;
+  const size_t one_set = vgpmp_draws_bytes(dims, D);
+  const bool pipelined = draws_bytes >= 2 * one_set;   // two draw sets: step t+1 is drawn on the side stream during step t
+  const int slot = pipelined ? (st->step & 1) : 0;
+  double *omega, *tau, *w, *eps_u, *eps_j;
+  auto carve_set = [&](int which) {
+    Carver c(static_cast<char*>(static_cast<void*>(draws_ws)) + (size_t)which * one_set);
+    omega = c.take(Bp * D * B * D);
+    tau = c.take(Bp * D * B);
+    w = c.take(Bp * D * S * B);
+    eps_u = c.take(Bp * D * S * Mp);
+    eps_j = c.take(Bp * D * S * Mp);
+  };
+  carve_set(slot);
+  if (pipelined && h->prefetched_step == (int64_t)st->step && h->prefetched_seed == seed) {
+    if ((rc = vgpmp_rng_join(h, slot, stream))) return rc;
+  } else {
+    if ((rc = vgpmp_rng_fill(h, dims, seed, (uint64_t)st->step, 0, 0, omega, tau, w, eps_u, eps_j, stream))) return rc;
+  }
   vgpmp_params p{st->q_mu, st->q_sqrt, st->lengthscales, st->variances, query_latent, Z, X_dev};
   vgpmp_draws r{omega, tau, w, eps_u, eps_j};
   if ((rc = vgpmp_elbo_fwd_bwd(h, dims, &p, &r, elbo_dev, g, nullptr, ws, ws_bytes, stream))) return rc;
-  if ((rc = vgpmp_adam_step(h, dims, st, g, stream))) return rc;
+  if ((rc = vgpmp_adam_step(h, dims, st, g, stream))) return rc;   // st->step is now the NEXT step
+  if (pipelined) {
+    if ((rc = vgpmp_rng_release(h, slot, stream))) return rc;
+    carve_set(slot ^ 1);
+    if ((rc = vgpmp_rng_fill_async(h, dims, seed, (uint64_t)st->step, 0, 0, omega, tau, w, eps_u, eps_j, slot ^ 1))) return rc;
+    h->prefetched_step = st->step;
+    h->prefetched_seed = seed;
+  }
   if ((rc = check_cuda(h, cudaMemcpyAsync(loss_host, elbo_dev, sizeof(double) * Bp, cudaMemcpyDeviceToHost, s), "D2H loss")))
     return rc;
   if ((rc = check_cuda(h, cudaStreamSynchronize(s), "sync"))) return rc;

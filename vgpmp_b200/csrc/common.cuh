@@ -50,6 +50,12 @@ struct vgpmp_handle {
   double4* rec_dev = nullptr;
   uint64_t launches = 0;
   std::string err;
+  // draw prefetch: the generator for step t+1 runs on a side stream while step t computes (two buffer slots)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_filled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  bool consumed_valid[2] = {false, false};
+  int64_t prefetched_step = -1;   // vgpmp_train_step_host: which step's draws are in flight / ready
+  uint64_t prefetched_seed = 0;
   // stage profiling (bench.py): event pairs recorded on the launching stream
   bool allow_warp_path = false; // experimental warp-synchronous sampler (N + Mp <= 96); slower than the CTA kernel so far
   bool allow_grid_path = true;  // equispaced rank-1 fast path of the pathwise sampler (vgpmp_set_option)

@@ -225,6 +225,20 @@ class Engine:
                                           self._stream()), "rng_fill")
         return d
 
+    def rng_fill_async(self, dims: _cabi.Dims, seed: int, iteration: int, draws: dict, slot: int, problem_offset: int = 0,
+                       sample_offset: int = 0):
+        """Generate `draws` on the handle's side stream (overlaps with work queued on the current stream)."""
+        self._chk(self.lib.vgpmp_rng_fill_async(self.h, C.byref(dims), int(seed), int(iteration), int(problem_offset),
+                                                int(sample_offset), draws["omega"].data_ptr(), draws["tau"].data_ptr(),
+                                                draws["w"].data_ptr(), draws["eps_u"].data_ptr(), draws["eps_j"].data_ptr(),
+                                                int(slot)), "rng_fill_async")
+
+    def rng_join(self, slot: int):
+        self._chk(self.lib.vgpmp_rng_join(self.h, int(slot), self._stream()), "rng_join")
+
+    def rng_release(self, slot: int):
+        self._chk(self.lib.vgpmp_rng_release(self.h, int(slot), self._stream()), "rng_release")
+
     def gp_prepare(self, dims, params: _cabi.Params):
         Bp, Mp = dims.num_problems, dims.num_inducing + 2
         Lc, Sf, kl = self.empty(Bp, self.D, Mp, Mp), self.empty(Bp, self.D, Mp, Mp), self.empty(Bp)

@@ -91,6 +91,7 @@ class VGPMP:
         self._draw_buf = None
         self.last_aux = None
         self._shard = None          # set by enable_sample_sharding (single-problem large-sample mode)
+        self._pipe = None           # double-buffered device draws of train_step (next step drawn on a side stream)
 
     # ---- construction ------------------------------------------------------------------------------
     @classmethod
@@ -267,13 +268,33 @@ class VGPMP:
         eng = self._eng
         X = eng.dev(X).reshape(-1, self.num_latent_gps)
         dims = self._dims(X.shape[0])
+        slot = None
+        if draws is None:
+            # device draws, double-buffered: this step's set was generated on the side stream during the previous step
+            key = (dims.num_problems, dims.num_samples, dims.num_bases, dims.total_samples)
+            if self._pipe is None or self._pipe["key"] != key:
+                self._pipe = dict(key=key, sets=[eng.alloc_draws(dims), eng.alloc_draws(dims)], ready=None)
+            slot = self._step & 1
+            soff = self._shard["offset"] if self._shard is not None else 0
+            if self._pipe["ready"] == self._step:
+                eng.rng_join(slot)
+            else:
+                eng.rng_fill(dims, self.seed, self._step, self._pipe["sets"][slot], sample_offset=soff)
+            use = self._pipe["sets"][slot]
+        else:
+            use = self._make_draws(dims, draws)
         if self._shard is not None:
             from ..utils.sharding import allreduce_packed, packed_views
             views = packed_views(self._shard["flat"], self.num_problems, self.num_inducing, self.num_latent_gps)
-            out = eng.elbo_fwd_bwd(dims, self._params(X), self._make_draws(dims, draws), need_grad=True, out=views)
+            out = eng.elbo_fwd_bwd(dims, self._params(X), use, need_grad=True, out=views)
             allreduce_packed(self._shard["flat"], self._shard["group"])      # one collective: gradients || ELBO
         else:
-            out = eng.elbo_fwd_bwd(dims, self._params(X), self._make_draws(dims, draws), need_grad=True)
+            out = eng.elbo_fwd_bwd(dims, self._params(X), use, need_grad=True)
+        if slot is not None:
+            eng.rng_release(slot)
+            eng.rng_fill_async(dims, self.seed, self._step + 1, self._pipe["sets"][slot ^ 1], slot ^ 1,
+                               sample_offset=self._shard["offset"] if self._shard is not None else 0)
+            self._pipe["ready"] = self._step + 1
         gs = _cabi.Grads(out["d_q_mu"].data_ptr(), out["d_q_sqrt"].data_ptr(), out["d_lengthscales"].data_ptr(),
                          out["d_variances"].data_ptr())
         st = self._adam_struct()
@@ -294,7 +315,7 @@ class VGPMP:
         dims = self._dims(N)
         hs = getattr(self, "_host_state", None)
         if hs is None or hs["N"] != N:
-            nbytes = int(eng.lib.vgpmp_draws_bytes(C.byref(dims), D))
+            nbytes = 2 * int(eng.lib.vgpmp_draws_bytes(C.byref(dims), D))   # two draw sets: next step drawn on the side stream
             hs = dict(N=N, X_dev=eng.empty(N, D), draws=torch.empty(nbytes, dtype=torch.uint8, device=eng.device),
                       elbo=eng.empty(self.num_problems),
                       loss=torch.empty(self.num_problems, dtype=torch.float64).pin_memory(),
