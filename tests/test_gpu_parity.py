@@ -441,6 +441,20 @@ def test_mesh_to_sdf_vs_bruteforce_oracle(tmp_path):
     assert np.array_equal(back.data, fine.data) and back.delta == fine.delta
 
 
+def test_single_problem_many_samples_split_reverse_pass_vs_oracle():
+    """One problem, S=300: the sampler splits samples over CTAs and the GP reverse pass runs as partial-sum CTAs + a fixed-order
+    fold (config-4 mode on one GPU).  Must match the oracle and be bit-reproducible."""
+    case = H.make_case("franka", "bookshelves", num_problems=1, S=300, N=12, M=5, B=16, seed=77)
+    model = H.make_model(case)
+    out = model.elbo_and_grads(case["X"], draws=case["draws_stacked"])
+    again = model.elbo_and_grads(case["X"], draws=case["draws_stacked"])
+    ref = O.elbo_and_grads(case["oracle"][0], case["q_mu"][0], case["q_sqrt"][0], case["ls"][0], case["var"][0], case["draws"][0])
+    assert abs(float(out["elbo"][0]) - ref["elbo"]) <= 1e-8 * abs(ref["elbo"])
+    for key in ("q_mu", "q_sqrt", "lengthscales", "variances"):
+        assert H.rel_err(_np(out["d_" + key][0]), ref["d_" + key]) < 1e-5, key
+        assert torch.equal(out["d_" + key], again["d_" + key]), key
+
+
 def test_config5_shapes_vs_oracle():
     """BASELINE config 5 shapes (S=256 samples, N=64 timesteps, B=1024 bases) on two problems: 32 sample tiles per latent."""
     case = H.make_case("franka", "bookshelves", num_problems=2, S=256, N=64, B=1024, seed=55)

@@ -62,7 +62,7 @@ struct Carver {
   }
 };
 
-GpScratch carve(void* ws, int D, const vgpmp_dims& d, size_t* total) {
+GpScratch carve(void* ws, int D, const vgpmp_dims& d, size_t* total, int num_sms = 148) {
   const size_t Bp = d.num_problems, M = d.num_inducing, Mp = M + 2, N = d.num_timesteps, S = d.num_samples;
   const size_t A = N + Mp;
   Carver c(ws);
@@ -79,6 +79,8 @@ GpScratch carve(void* ws, int D, const vgpmp_dims& d, size_t* total) {
   g.df = c.take(Bp * S * N * D);
   g.logp = c.take(Bp * S * N);
   g.meta = c.take(8);
+  const size_t np = backward_partial_doubles(num_sms, (int)(Bp * D), (int)S);
+  g.partial = np ? c.take(np) : nullptr;
   *total = c.off;
   return g;
 }
@@ -244,7 +246,7 @@ int vgpmp_destroy(vgpmp_handle* h) {
 size_t vgpmp_workspace_bytes(const vgpmp_handle* h, const vgpmp_dims* dims) {
   if (!h || !dims) return 0;
   size_t total = 0;
-  carve(nullptr, h->robot.dof, *dims, &total);
+  carve(nullptr, h->robot.dof, *dims, &total, h->num_sms);
   return total;
 }
 
@@ -287,7 +289,7 @@ int vgpmp_predict_f_mean(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_pa
   if (rc) return rc;
   if (!p || !Xq || !mean || !ws || num_query < 1) return fail(h, VGPMP_ERR_INVALID, "predict_f_mean: bad argument");
   size_t need = 0;
-  GpScratch g = carve(ws, h->robot.dof, *dims, &need);
+  GpScratch g = carve(ws, h->robot.dof, *dims, &need, h->num_sms);
   if (ws_bytes < need) return fail(h, VGPMP_ERR_WORKSPACE, "predict_f_mean: workspace too small");
   cudaStream_t s = (cudaStream_t)stream;
   if ((rc = check_cuda(h, launch_gp_prepare(h, *dims, *p, g.Lc, g.Sfull, g.kl_l, g.kvec, g.Linv, s), "gp_prepare"))) return rc;
@@ -318,7 +320,7 @@ int vgpmp_gp_prepare(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_params
   if (rc) return rc;
   if (!p || !ws) return fail(h, VGPMP_ERR_INVALID, "gp_prepare: null params or workspace");
   size_t need = 0;
-  GpScratch g = carve(ws, h->robot.dof, *dims, &need);
+  GpScratch g = carve(ws, h->robot.dof, *dims, &need, h->num_sms);
   if (ws_bytes < need) return fail(h, VGPMP_ERR_WORKSPACE, "gp_prepare: workspace too small");
   cudaStream_t s = (cudaStream_t)stream;
   rc = check_cuda(h, launch_gp_prepare(h, *dims, *p, Lc ? Lc : g.Lc, q_sqrt_full ? q_sqrt_full : g.Sfull, g.kl_l,
@@ -339,7 +341,7 @@ int vgpmp_pathwise_sample(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_p
   dq.num_timesteps = num_query;
   if ((rc = check_dims(h, &dq))) return rc;
   size_t need = 0;
-  GpScratch g = carve(ws, h->robot.dof, dq, &need);
+  GpScratch g = carve(ws, h->robot.dof, dq, &need, h->num_sms);
   if (ws_bytes < need) return fail(h, VGPMP_ERR_WORKSPACE, "pathwise_sample: workspace too small (size it with num_timesteps = num_query)");
   cudaStream_t s = (cudaStream_t)stream;
   if ((rc = check_cuda(h, launch_gp_prepare(h, dq, *p, g.Lc, g.Sfull, g.kl_l, g.kvec, g.Linv, s), "gp_prepare"))) return rc;
@@ -354,7 +356,7 @@ int vgpmp_elbo_fwd_bwd(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_para
   if (rc) return rc;
   if (!p || !r || !elbo || !ws) return fail(h, VGPMP_ERR_INVALID, "elbo_fwd_bwd: bad argument");
   size_t need = 0;
-  GpScratch g = carve(ws, h->robot.dof, *dims, &need);
+  GpScratch g = carve(ws, h->robot.dof, *dims, &need, h->num_sms);
   if (ws_bytes < need) return fail(h, VGPMP_ERR_WORKSPACE, "elbo_fwd_bwd: workspace too small");
   cudaStream_t s = (cudaStream_t)stream;
   const int D = h->robot.dof;

@@ -90,7 +90,9 @@ struct GpScratch {  // carved from the caller's workspace by cabi.cu
   double* df;      // [Bp,S,N,D]
   double* logp;    // [Bp,S,N]
   double* meta;    // [8] input-structure probe {grid flag, t0, dt, z0, dz}
+  double* partial; // reverse-pass partial sums when the sample loop is split over CTAs (else nullptr)
 };
+size_t backward_partial_doubles(int num_sms, int pairs, int S);
 
 cudaError_t launch_kuu(vgpmp_handle* h, const double* Z, const double* ls, const double* var, double jitter, double* K,
                        int Bp, int M, cudaStream_t s);

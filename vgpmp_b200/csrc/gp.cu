@@ -797,6 +797,8 @@ __global__ void __launch_bounds__(128) pathwise_tail_kernel(PathwiseArgs a, cons
 // ---------------------------------------------------------------------------------------------
 struct BackwardArgs {
   int D, M, N, S, B;
+  int nchunk, chunk;   // sample-loop split (MODE 1/2 of gp_backward_kernel)
+  double* partial;     // [Bp*D*nchunk][kPartial]
   double jitter, klw;
   const double *Z, *X, *ls, *var, *q_sqrt;
   const double *eps_u;
@@ -806,10 +808,18 @@ struct BackwardArgs {
 
 constexpr int kBT = 8;  // samples per tile (= warps) in the reverse pass
 
+constexpr int kPartial = 2 * 32 * 32 + 32 + 4;   // doubles per (problem, latent, sample chunk) partial: G, GS, gmu, acc_var, acc_ls
+
+// MODE 0: one CTA per (problem, latent) does everything.  For a single problem with very many samples the sample loop
+// is split over CTAs: MODE 1 = sample phase of one chunk -> partial sums in global memory; MODE 2 = fold the partials in
+// fixed order (deterministic) and run the sample-independent phase.
+template <int MODE>
 __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
   extern __shared__ double sm[];
   const int D = a.D, M = a.M, Mp = M + 2, N = a.N, S = a.S, A = N + Mp;
-  const int pl = blockIdx.x, p = pl / D, l = pl % D;
+  const int pl = MODE == 1 ? blockIdx.x / a.nchunk : blockIdx.x, p = pl / D, l = pl % D;
+  const int s_begin = MODE == 1 ? (blockIdx.x % a.nchunk) * a.chunk : 0;
+  const int s_end = MODE == 1 ? min(S, s_begin + a.chunk) : (MODE == 2 ? 0 : S);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
   double* Lsm = sm;                    // [32][LDM] chol factor L
   double* Lism = Lsm + 32 * LDM;       // [32][LDM] explicit inverse L^-1
@@ -848,8 +858,8 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
   double acc_ls = 0.0, acc_var = 0.0;  // per-thread partial hyper-parameter gradients
   const double* dfp = a.df + (size_t)p * S * N * D + l;  // df[s,n] at dfp[(s*N+n)*D]
 
-  for (int s0 = 0; s0 < S; s0 += kBT) {
-    const int ns = min(kBT, S - s0);
+  for (int s0 = s_begin; s0 < s_end; s0 += kBT) {
+    const int ns = min(kBT, s_end - s0);
     // stage this tile's df (strided in global: [s,n,D]), v and eps_u in shared memory
     for (int idx = tid; idx < kBT * N; idx += nt) {
       const int i = idx / N, n = idx - i * N;
@@ -921,6 +931,42 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
       acc_var += g * a.f0[o] / (2.0 * s2);
       acc_ls += g * a.h0[o];
     }
+    __syncthreads();
+  }
+
+  if (MODE == 1) {  // publish this chunk's partial sums
+    double* part = a.partial + (size_t)blockIdx.x * kPartial;
+    for (int idx = tid; idx < 32 * 32; idx += nt) {
+      part[idx] = G[(idx >> 5) * LDM + (idx & 31)];
+      part[1024 + idx] = GS[(idx >> 5) * LDM + (idx & 31)];
+    }
+    if (tid < 32) part[2048 + tid] = gmu[tid];
+    const double tv = block_sum(acc_var, red);
+    const double tl = block_sum(acc_ls, red);
+    if (tid == 0) { part[2080] = tv; part[2081] = tl; }
+    return;
+  }
+  if (MODE == 2) {  // fold the partial sums of all chunks, chunk 0 first
+    for (int idx = tid; idx < 32 * 32; idx += nt) {
+      double g = 0.0, gs = 0.0;
+      for (int c = 0; c < a.nchunk; ++c) {
+        const double* part = a.partial + ((size_t)pl * a.nchunk + c) * kPartial;
+        g += part[idx];
+        gs += part[1024 + idx];
+      }
+      G[(idx >> 5) * LDM + (idx & 31)] = g;
+      GS[(idx >> 5) * LDM + (idx & 31)] = gs;
+    }
+    if (tid < 32) {
+      double t = 0.0;
+      for (int c = 0; c < a.nchunk; ++c) t += a.partial[((size_t)pl * a.nchunk + c) * kPartial + 2048 + tid];
+      gmu[tid] = t;
+    }
+    if (tid == 0)
+      for (int c = 0; c < a.nchunk; ++c) {
+        acc_var += a.partial[((size_t)pl * a.nchunk + c) * kPartial + 2080];
+        acc_ls += a.partial[((size_t)pl * a.nchunk + c) * kPartial + 2081];
+      }
     __syncthreads();
   }
 
@@ -1345,6 +1391,22 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
   return cudaGetLastError();
 }
 
+// split of the reverse pass's sample loop: only when there are too few (problem, latent) pairs to fill the GPU
+void backward_chunks(int num_sms, int pairs, int S, int* nchunk, int* chunk) {
+  const int tiles = (S + kBT - 1) / kBT;
+  int want = (2 * num_sms) / std::max(1, pairs);
+  int n = std::max(1, std::min(tiles / 4, want));      // at least 4 tiles per chunk, else the fused kernel wins
+  const int c = ((tiles + n - 1) / n) * kBT;
+  *chunk = c;
+  *nchunk = (S + c - 1) / c;
+}
+
+size_t backward_partial_doubles(int num_sms, int pairs, int S) {
+  int n, c;
+  backward_chunks(num_sms, pairs, S, &n, &c);
+  return n > 1 ? (size_t)pairs * n * kPartial : 0;
+}
+
 cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
                                const GpScratch& ws, const vgpmp_grads& g, cudaStream_t s) {
   BackwardArgs a;
@@ -1358,10 +1420,23 @@ cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp
   const int Mp = a.M + 2;
   const size_t smem = sizeof(double) * (5 * 32 * LDM + (size_t)a.N * 32 + 4 * kBT * 32 + 4 * 32 + 16 + (size_t)kBT * a.N);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(gp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  gp_backward_kernel<<<d.num_problems * a.D, 256, smem, s>>>(a);
-  h->launches++;
+  const int pairs = d.num_problems * a.D;
+  backward_chunks(h->num_sms, pairs, a.S, &a.nchunk, &a.chunk);
+  a.partial = ws.partial;
+  cudaError_t e;
+  if (a.nchunk <= 1 || ws.partial == nullptr) {
+    if ((e = cudaFuncSetAttribute(gp_backward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+      return e;
+    gp_backward_kernel<0><<<pairs, 256, smem, s>>>(a);
+    h->launches++;
+  } else {
+    if ((e = cudaFuncSetAttribute(gp_backward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(gp_backward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+      return e;
+    gp_backward_kernel<1><<<pairs * a.nchunk, 256, smem, s>>>(a);
+    gp_backward_kernel<2><<<pairs, 256, smem, s>>>(a);
+    h->launches += 2;
+  }
   return cudaGetLastError();
 }
 
