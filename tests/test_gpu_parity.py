@@ -200,7 +200,7 @@ def test_pathwise_sample_irregular_inputs_fall_back_to_general_kernel():
 ])
 @pytest.mark.parametrize("grid", [1, 2, 0])
 def test_elbo_and_gradients_vs_oracle(name, env, kw, grid):
-    """grid: 1 = warp-synchronous equispaced sampler, 2 = CTA-level equispaced sampler, 0 = general sincos sampler."""
+    """grid: 1 = warp-synchronous equispaced sampler, 2 = CTA-level equispaced sampler (default), 0 = general sincos sampler."""
     case = H.make_case(name, env, num_problems=2, seed=4, **kw)
     model = H.make_model(case)
     model._eng.set_option("grid_fast_path", int(grid > 0))

@@ -344,8 +344,7 @@ int vgpmp_pathwise_sample(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_p
   GpScratch g = carve(ws, h->robot.dof, dq, &need, h->num_sms);
   if (ws_bytes < need) return fail(h, VGPMP_ERR_WORKSPACE, "pathwise_sample: workspace too small (size it with num_timesteps = num_query)");
   cudaStream_t s = (cudaStream_t)stream;
-  if ((rc = check_cuda(h, launch_gp_prepare(h, dq, *p, g.Lc, g.Sfull, g.kl_l, g.kvec, g.Linv, s), "gp_prepare"))) return rc;
-  return check_cuda(h, launch_pathwise(h, dq, *p, *r, Xq, num_query, g.Lc, g.Sfull, g.Linv, f, nullptr, nullptr, nullptr, g.meta, s),
+  return check_cuda(h, launch_pathwise(h, dq, *p, *r, Xq, num_query, g.Lc, g.Sfull, g.Linv, g.kl_l, g.kvec, f, nullptr, nullptr, nullptr, g.meta, s),
                     "pathwise_sample");
 }
 
@@ -365,14 +364,11 @@ int vgpmp_elbo_fwd_bwd(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_para
   double* logp = (aux && aux->logp) ? aux->logp : g.logp;
   const bool bwd = gr != nullptr;
   {
-    StageSpan sp(h, ST_PREPARE, s);
-    if ((rc = check_cuda(h, launch_gp_prepare(h, *dims, *p, g.Lc, g.Sfull, g.kl_l, g.kvec, g.Linv, s), "gp_prepare"))) return rc;
-  }
-  {
+    // GP preparation kernel + pathwise sampling kernels (one stage for the profile)
     StageSpan sp(h, ST_PATHWISE, s);
-    if ((rc = check_cuda(h, launch_pathwise(h, *dims, *p, *r, p->X, dims->num_timesteps, g.Lc, g.Sfull, g.Linv, f,
-                                            bwd ? g.v : nullptr, bwd ? g.f0 : nullptr, bwd ? g.h0 : nullptr, g.meta, s),
-                         "pathwise")))
+    if ((rc = check_cuda(h, launch_pathwise(h, *dims, *p, *r, p->X, dims->num_timesteps, g.Lc, g.Sfull, g.Linv, g.kl_l,
+                                            g.kvec, f, bwd ? g.v : nullptr, bwd ? g.f0 : nullptr, bwd ? g.h0 : nullptr,
+                                            g.meta, s), "pathwise")))
       return rc;
   }
   {

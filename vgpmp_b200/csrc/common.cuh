@@ -101,7 +101,7 @@ cudaError_t launch_kuf(vgpmp_handle* h, const double* Z, const double* X, const 
 cudaError_t launch_gp_prepare(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, double* Lc, double* Sfull,
                               double* kl_l, double* kvec, double* Linv, cudaStream_t s);
 cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
-                            const double* Xq, int Nq, const double* Lc, const double* Sfull, const double* Linv,
+                            const double* Xq, int Nq, double* Lc, double* Sfull, double* Linv, double* kl_l, double* kvec,
                             double* f, double* v, double* f0, double* h0, double* meta, cudaStream_t s);
 cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
                                const GpScratch& ws, const vgpmp_grads& g, cudaStream_t s);

@@ -138,12 +138,22 @@ __global__ void kuf_kernel(int D, int M, int N, const double* __restrict__ Z, co
 // ---------------------------------------------------------------------------------------------
 // Kuu + chol + q_sqrt un-whitening + KL, one CTA (128 threads) per (problem, latent)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, double jitter, vgpmp_params P,
-                                                        double* __restrict__ Lc_out, double* __restrict__ S_out,
-                                                        double* __restrict__ kl_l, double* __restrict__ kvec,
-                                                        double* __restrict__ Linv_out) {
-  __shared__ double zy[32], Ksm[32 * LDM], Lsm[32 * LDM], mu[32], red[8], cvec[2];
-  const int pl = blockIdx.x, p = pl / D, l = pl % D, Mp = M + 2, tid = threadIdx.x;
+constexpr int kPrepSmem = 5 * 32 * LDM + 2 * 32 + 16;   // doubles of shared memory gp_prepare_body needs
+
+// Body of the GP preparation for one (problem, latent), working on a caller-provided shared-memory block.
+// `smem` must hold kPrepSmem doubles; needs blockDim.x >= 32 and a multiple of 32.
+__device__ void gp_prepare_body(int D, int M, double jitter, const vgpmp_params& P, int pl, double* __restrict__ Lc_out,
+                                double* __restrict__ S_out, double* __restrict__ kl_l, double* __restrict__ kvec,
+                                double* __restrict__ Linv_out, double* smem) {
+  double* Ksm = smem;
+  double* Lsm = Ksm + 32 * LDM;
+  double* qsm = Lsm + 32 * LDM;
+  double* Li = qsm + 32 * LDM;
+  double* zy = Li + 32 * LDM;
+  double* mu = zy + 32;
+  double* red = mu + 32;
+  double* cvec = red + 8;
+  const int p = pl / D, l = pl % D, Mp = M + 2, tid = threadIdx.x;
   const double ell = P.lengthscales[pl], s2 = P.variances[pl];
   if (tid < Mp) {
     zy[tid] = zy_at(P.Z, D, l, tid);
@@ -151,7 +161,6 @@ __global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, double ji
   }
   __syncthreads();
   const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  __shared__ double qsm[32 * LDM];   // _q_sqrt of this (problem, latent), zero-padded
   const double* q = P.q_sqrt + (size_t)pl * M * M;
   for (int idx = tid; idx < 32 * LDM; idx += blockDim.x) { Lsm[idx] = 0.0; qsm[idx] = 0.0; }
   __syncthreads();
@@ -170,7 +179,6 @@ __global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, double ji
   // explicit inverse factor: thread j holds column j of L^-1 in registers,
   //   x_i = (delta_ij - sum_{k<i} L[i][k] x_k) / L[i][i]   (x_k = 0 for k < j; L is zero-padded beyond Mp)
   if (Linv_out != nullptr) {
-    __shared__ double Li[32 * LDM];
     if (tid < 32) {
       const int j = tid;
       double x[32];
@@ -231,6 +239,14 @@ __global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, double ji
   }
   const double tot = block_sum(part, red);
   if (tid == 0 && kl_l != nullptr) kl_l[pl] = 0.5 * (tot - (double)M);
+}
+
+__global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, double jitter, vgpmp_params P,
+                                                        double* __restrict__ Lc_out, double* __restrict__ S_out,
+                                                        double* __restrict__ kl_l, double* __restrict__ kvec,
+                                                        double* __restrict__ Linv_out) {
+  __shared__ double smem[kPrepSmem];
+  gp_prepare_body(D, M, jitter, P, blockIdx.x, Lc_out, S_out, kl_l, kvec, Linv_out, smem);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -480,7 +496,6 @@ __device__ __forceinline__ void rotate_run(double* fc, double* fd, int col0, int
 // layouts keep the tile stride kST = 8.
 template <int XT, int ST>
 __global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, const double* __restrict__ meta) {
-  if (meta[0] == 0.0) return;  // inputs are not an equispaced rank-1 grid: the general kernel does the work
   extern __shared__ __align__(16) double sm[];
   const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, B = a.B, A = Nq + Mp;
   const int pl = blockIdx.x / a.nchunk, p = pl / D, l = pl % D;
@@ -500,6 +515,7 @@ __global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, c
   double* mu = vs + kST * 32;
   double* zy = mu + 32;
 
+  if (meta[0] == 0.0) return;  // inputs are not an equispaced rank-1 grid: the general kernel does the sampling
   const double ell = a.ls[pl], s2 = a.var[pl];
   const double amp = sqrt(2.0 * s2 / (double)B), sqrtj = sqrt(a.jitter), inv_ell = 1.0 / ell;
   const double t0 = meta[1], dt = meta[2], z0 = meta[3], dz = meta[4];
@@ -1303,8 +1319,10 @@ cudaError_t launch_gp_prepare(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_
 }
 
 cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
-                            const double* Xq, int Nq, const double* Lc, const double* Sfull, const double* Linv,
+                            const double* Xq, int Nq, double* Lc, double* Sfull, double* Linv, double* kl_l, double* kvec,
                             double* f, double* v, double* f0, double* h0, double* meta, cudaStream_t s) {
+  // The GP preparation (Kuu, Cholesky, L^-1, q_sqrt_full, KL) is this launcher's job too.  (Fusing it into the sampler
+  // CTAs was tried: correct but neutral-to-slower, the extra code costs the FP64-bound main loop more than the launch saves.)
   PathwiseArgs a;
   a.D = h->robot.dof; a.M = d.num_inducing; a.Nq = Nq; a.S = d.num_samples; a.B = d.num_bases;
   const int Mp = a.M + 2, A = Nq + Mp;
@@ -1351,10 +1369,11 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
     smem_g = sizeof(double) * std::max(std::max(main_view, tail_view), red_view);
     grid_ok = smem_g <= 200 * 1024;
   }
+  const bool warp_path = grid_ok && h->allow_warp_path && A <= 96 && f0 != nullptr && h0 != nullptr && a.M >= 2;
+  if ((e = launch_gp_prepare(h, d, p, Lc, Sfull, kl_l, kvec, Linv, s)) != cudaSuccess) return e;
   if (grid_ok) {
     analyze_grid_kernel<<<1, 256, 0, s>>>(a.D, a.M, Nq, Xq, p.Z, meta);
     h->launches++;
-    const bool warp_path = h->allow_warp_path && A <= 96 && f0 != nullptr && h0 != nullptr && a.M >= 2;
     if (warp_path) {
       const int xt = std::max(4, (A + 15) / 16);        // <= 16 point groups per feature plane
       const int XGq = (A + xt - 1) / xt, XP = XGq * xt, AP = XP | 1;
