@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--sdf-dim", type=int, default=256)
     ap.add_argument("--cpu-problems", type=int, default=16, help="problems per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--problems", type=int, default=0, help="experiments only: truncate / cycle the batch to this many problems")
     return ap.parse_args()
 
 
@@ -190,6 +191,8 @@ def run_b200(args):
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
 
     ps, queries = workload(args.runs)
+    if args.problems:
+        queries = [queries[i % len(queries)] for i in range(args.problems)]
     pp = dict(ps["planner_params"])
     sdf, sdf_desc = bench_sdf(args.sdf, args.sdf_dim)
     robot = Robot.from_tables("franka", "bookshelves")
