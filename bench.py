@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--sdf-dim", type=int, default=256)
     ap.add_argument("--cpu-problems", type=int, default=16, help="problems per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=INT",
+                    help="experiments only: vgpmp_set_option(NAME, INT) before timing (e.g. mma_sampler=0)")
     ap.add_argument("--problems", type=int, default=0, help="experiments only: truncate / cycle the batch to this many problems")
     return ap.parse_args()
 
@@ -203,6 +205,9 @@ def run_b200(args):
                              seed=1234 + 2 + 1000 * rank, **pp)
     disable_param_opt(model, default_trainable_params())
     eng = model._eng
+    for kv in args.option:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     Bp, S, N, M, B, D, P = model.num_problems, model.num_samples, X.shape[0], model.num_inducing, model.num_bases, robot.dof, robot.num_spheres
     Xd = eng.dev(X)
 

@@ -22,8 +22,42 @@ from oracle import vgpmp_oracle as O  # noqa: E402
 from tests import helpers as H  # noqa: E402
 
 
+def _tf32(x):
+    """round-to-nearest float32 -> tf32 (10 explicit mantissa bits), returned as float32"""
+    u = x.contiguous().view(torch.int32)
+    return ((u + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def _split(x64):
+    hi = _tf32(x64.float())
+    lo = _tf32((x64 - hi.double()).float())
+    return hi, lo
+
+
+MODE = "f32"
+FLUSH = 0          # 3xtf32: bases per float32 accumulation run before the partial sum is added into a float64 total
+
+
+def contract(phi, w):
+    """phi [l,a,b] (float64), w [l,s,b] (float64) -> [l,s,a] float64, computed the way MODE says"""
+    if MODE == "f32":
+        return torch.einsum("lab,lsb->lsa", phi.float(), w.float()).double()
+    exact = torch.einsum("lab,lsb->lsa", phi, w)          # carries the gradient (the kernel's d/dlengthscale contraction
+    ph, pl = _split(phi.detach())                         # would run in the same reduced precision: same error class)
+    wh, wl = _split(w.detach())
+    B = phi.shape[-1]
+    step = FLUSH or B
+    out = torch.zeros(phi.shape[0], w.shape[1], phi.shape[1], dtype=torch.float64)
+    for b0 in range(0, B, step):
+        sl = slice(b0, b0 + step)
+        part = (torch.einsum("lab,lsb->lsa", pl[..., sl], wh[..., sl]) + torch.einsum("lab,lsb->lsa", ph[..., sl], wl[..., sl])
+                + torch.einsum("lab,lsb->lsa", ph[..., sl], wh[..., sl]))
+        out += part.double()
+    return exact + (out - exact).detach()
+
+
 class F32Problem(O.OracleProblem):
-    """OracleProblem whose Fourier contraction runs in float32 (features and weights rounded, float32 accumulate)."""
+    """OracleProblem whose Fourier contraction runs in float32 / emulated 3xTF32 (everything else float64)."""
 
     def sample_paths(self, Xq, q_mu, q_sqrt, lengthscales, variances, draws):
         omega, tau, w = O._t(draws["omega"]), O._t(draws["tau"]), O._t(draws["w"])
@@ -34,7 +68,7 @@ class F32Problem(O.OracleProblem):
         def prior(pts):
             proj = torch.einsum("ad,lbd->lab", pts, omega) / lengthscales[:, None, None]
             phi = torch.sqrt(2.0 * variances / B)[:, None, None] * torch.cos(proj + tau[:, None, :])
-            return torch.einsum("lab,lsb->lsa", phi.float(), w.float()).double()     # <- float32 contraction
+            return contract(phi, w)     # <- reduced-precision contraction
 
         mu = self.q_mu_full(q_mu).T
         Sfull = self.q_sqrt_full(q_sqrt, lengthscales, variances)
@@ -50,7 +84,11 @@ class F32Problem(O.OracleProblem):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--problems", type=int, default=6)
+    ap.add_argument("--mode", choices=["f32", "3xtf32"], default="f32")
+    ap.add_argument("--flush", type=int, default=0, help="3xtf32: float32 accumulation run length in bases (0 = all)")
     a = ap.parse_args()
+    global MODE, FLUSH
+    MODE, FLUSH = a.mode, a.flush
     case = H.make_case("franka", "bookshelves", num_problems=a.problems, B=1024, seed=11, perturb=True)   # perturbed: trajectories touch the obstacles
     worst = dict(f=0.0, elbo=0.0, grad=0.0, flips=0)
     print("problem  max|df|     flipped cells   rel ELBO err   rel grad err (q_mu, q_sqrt, ls, var)")
@@ -64,7 +102,8 @@ def main():
         e = abs(got["elbo"] - ref["elbo"]) / abs(ref["elbo"])
         g = [H.rel_err(got["d_" + k], ref["d_" + k]) for k in ("q_mu", "q_sqrt", "lengthscales", "variances")]
         worst = dict(f=max(worst["f"], df), elbo=max(worst["elbo"], e), grad=max(worst["grad"], max(g)), flips=worst["flips"] + flips)
-        print(f"{b:7d}  {df:9.2e}  {flips:6d}/{ref['logp'].size:<6d}  {e:12.2e}   " + " ".join(f"{x:8.1e}" for x in g))
+        active = int((ref["logp"] != 0).sum())
+        print(f"{b:7d}  {df:9.2e}  {flips:6d}/{ref['logp'].size:<6d} (active {active:4d})  {e:12.2e}   " + " ".join(f"{x:8.1e}" for x in g))
     print(f"worst: max|df| {worst['f']:.2e}, ELBO {worst['elbo']:.2e} (tolerance 1e-4), gradients {worst['grad']:.2e} (tolerance 1e-3), "
           f"{worst['flips']} flipped cells")
 
