@@ -650,6 +650,207 @@ __global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Equispaced sampler with the contraction on the FP64 tensor path (DMMA m8n8k4).
+// Same two phases per tile of 32 bases as pathwise_grid_kernel, but phase 2 is  C[8 points x 8 samples] += A[8 x 4 bases]
+// B[4 x 8]  with A fragments read straight from the feature tile (one 64-bit shared load per 256 FMAs) and C held in
+// 2*PT registers per thread for the whole base loop.  B200 executes DMMA at the DFMA rate (profiles/r1_v9_dmma_probe.txt),
+// so the gain is not flops: the contraction shrinks from ~250 to ~60 issued instructions per warp and tile, the
+// accumulator file from 48 to 2*PT doubles, the kernel fits 3 CTAs per SM (was 2) and the latency-bound feature phase
+// gets 1.5x the warps.  The warps that are light in phase 2 also precompute, for the NEXT tile, everything phase 1 would
+// otherwise recompute per chunk (step phasors of both grids, the two conditioned endpoints): 12 sincos per basis
+// instead of 18, and exactly one on every thread's critical path.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDB = 32;    // bases per tile
+constexpr int kDBP = 36;   // padded basis stride of a feature row: the 4 rows x 4 lanes of an A fragment hit 16 distinct banks
+constexpr int kWS = 12;    // padded sample stride of a staged weight row (same argument for the B fragment)
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// one chunk of an equispaced run written point-major (feature of point n at fc[n * kDBP]); the step phasor comes in
+__device__ __forceinline__ void rotate_run_pm(double* fc, double* fd, int col0, int first, int count, double g0, double dg,
+                                              double c, double tau, double amp, double inv_ell, double cd, double sd) {
+  if (count <= 0) return;
+  double sn, cs;
+  const double tn = g0 + dg * first;
+  sincos(tn * c + tau, &sn, &cs);
+  cs *= amp; sn *= amp;
+  double q = tn * c * inv_ell;
+  const double dq = dg * c * inv_ell;
+  fc += (size_t)(col0 + first) * kDBP;
+  fd += (size_t)(col0 + first) * kDBP;
+  for (int k = 0; k < count; ++k) {
+    fc[k * kDBP] = cs;
+    fd[k * kDBP] = sn * q;
+    const double c2 = cs * cd - sn * sd;
+    sn = sn * cd + cs * sd;
+    cs = c2;
+    q += dq;
+  }
+}
+
+template <int PT>
+__global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, const double* __restrict__ meta) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int ROWS = 32 * PT;                 // padded number of points: 8 warps x PT units = 4*PT point tiles x 2 features
+  constexpr int PLANE = ROWS * kDBP;            // one feature plane [point][basis]
+  const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, B = a.B, A = Nq + Mp;
+  const int pl = blockIdx.x / a.nchunk, p = pl / D, l = pl % D;
+  const int s_begin = (blockIdx.x % a.nchunk) * a.chunk, s_end = min(a.S, s_begin + a.chunk);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
+  const int T = (B + kDB - 1) / kDB;
+  // main-loop view
+  double* feat = sm;                            // [2 features][ROWS][kDBP]
+  double* Wt = feat + 2 * PLANE;                // [3][kDB][kWS]
+  double* osum = Wt + 3 * kDB * kWS;            // [3][4][kDB]  partial sums over the input dims of omega_b
+  double* tb = osum + 3 * 4 * kDB;              // [3][kDB]     tau_b
+  double* stp = tb + 3 * kDB;                   // [2][2][kDB][2]  step phasors (cos, sin) of the query grid | inducing grid
+  double* ept = stp + 2 * 2 * kDB * 2;          // [2][2][kDB][2]  unit phasors of the conditioned endpoints Zy = 0 | 1
+  // tail view over the dead feature tile: red | Lsm | Kfu | vs | mu | zy
+  double* red = sm;                             // [2][kST][ROWS]
+  double* Lsm = red + (size_t)2 * kST * ROWS;
+  double* Kfu = Lsm + 32 * LDM;
+  double* vs = Kfu + (size_t)Nq * Mp;
+  double* mu = vs + kST * 32;
+  double* zy = mu + 32;
+
+  if (meta[0] == 0.0) return;  // not an equispaced rank-1 grid: the general kernel does the sampling
+  const double ell = a.ls[pl], s2 = a.var[pl];
+  const double amp = sqrt(2.0 * s2 / (double)B), sqrtj = sqrt(a.jitter), inv_ell = 1.0 / ell;
+  const double t0 = meta[1], dt = meta[2], z0 = meta[3], dz = meta[4];
+  const double* om = a.omega + (size_t)pl * B * D;
+  const double* ta = a.tau + (size_t)pl * B;
+  const double* wp = a.w + (size_t)pl * S * B;
+
+  // phase-1 roles: lane = basis of the tile; warps 0-5 walk chunks of the query grid, warps 6-7 the two halves of Z
+  const int per = (Nq + 5) / 6, mhalf = (M + 1) / 2;
+  // phase-2 roles: warp owns PT (feature, point tile) units; MMA fragment coordinates g = lane / 4, t4 = lane % 4
+  const int g = lane >> 2, t4 = lane & 3;
+
+  // next-tile tables, filled by warps 0-3 (one sincos per thread): step phasors and endpoint phasors of tile `tile`
+  auto fill_tables = [&](int tile, int ob, int sb) {
+    if (warp >= 4) return;
+    const double* os = osum + (size_t)ob * 4 * kDB + lane;
+    const double c = (os[0] + os[kDB] + os[2 * kDB] + os[3 * kDB]) * inv_ell, tau = tb[ob * kDB + lane];
+    (void)tile;
+    double sn, cs;
+    const double arg = warp == 0 ? dt * c : (warp == 1 ? dz * c : (warp == 2 ? tau : c + tau));
+    sincos(arg, &sn, &cs);
+    double* dst = (warp < 2 ? stp : ept) + (((size_t)sb * 2 + (warp & 1)) * kDB + lane) * 2;
+    dst[0] = cs; dst[1] = sn;
+  };
+
+  for (int s0 = s_begin; s0 < s_end; s0 += kST) {
+    const int ns = min(kST, s_end - s0);
+    double acc[PT][2];
+#pragma unroll
+    for (int j = 0; j < PT; ++j) acc[j][0] = acc[j][1] = 0.0;
+
+    // staging registers: this thread's share of a tile's operands (as in pathwise_grid_kernel), one tile ahead of the
+    // shared-memory copy, which itself is one tile ahead of its use
+    double st_o[2] = {0.0, 0.0}, st_t = 0.0, st_w = 0.0;
+    auto prefetch = [&](int b0) {
+      const int nb = min(kDB, B - b0);
+      if (warp < 4) {
+        st_o[0] = (lane < nb && warp < D) ? om[(size_t)(b0 + lane) * D + warp] : 0.0;
+        st_o[1] = (lane < nb && warp + 4 < D) ? om[(size_t)(b0 + lane) * D + warp + 4] : 0.0;
+      }
+      st_t = (tid < kDB && tid < nb) ? ta[b0 + tid] : 0.0;
+      const int i = tid / kDB, b = tid % kDB;         // kDB * kST = 256 = blockDim.x
+      st_w = (i < ns && b < nb) ? wp[(size_t)(s0 + i) * B + b0 + b] : 0.0;
+    };
+    auto stage = [&](int ob) {
+      if (warp < 4) osum[((size_t)ob * 4 + warp) * kDB + lane] = st_o[0] + st_o[1];
+      if (tid < kDB) tb[ob * kDB + tid] = st_t;
+      Wt[((size_t)ob * kDB + tid % kDB) * kWS + tid / kDB] = st_w;
+    };
+    __syncthreads();          // previous sample tile's tail is done with the shared memory
+    prefetch(0);
+    stage(0);
+    if (kDB < B) prefetch(kDB);
+    __syncthreads();
+    fill_tables(0, 0, 0);
+
+    for (int t = 0; t < T; ++t) {
+      const int cur = t % 3, nxt = (t + 1) % 3, sb = t & 1;
+      if (t + 1 < T) {
+        stage(nxt);
+        if ((t + 2) * kDB < B) prefetch((t + 2) * kDB);
+      }
+      __syncthreads();  // staging and tables visible; previous tile's contraction finished -> feature tile is free
+      {  // phase 1: features by rotation along the grid
+        const double* os = osum + (size_t)cur * 4 * kDB + lane;
+        const double c = (os[0] + os[kDB] + os[2 * kDB] + os[3 * kDB]) * inv_ell, tau = tb[cur * kDB + lane];
+        const double ab = (t * kDB + lane < B) ? amp : 0.0;
+        double* fc = feat + lane;
+        double* fd = fc + PLANE;
+        const double2 sx = *reinterpret_cast<const double2*>(stp + (((size_t)sb * 2 + 0) * kDB + lane) * 2);
+        const double2 sz = *reinterpret_cast<const double2*>(stp + (((size_t)sb * 2 + 1) * kDB + lane) * 2);
+        if (warp < 6) {
+          const int n0 = warp * per;
+          rotate_run_pm(fc, fd, 0, n0, min(Nq, n0 + per) - n0, t0, dt, c, tau, ab, inv_ell, sx.x, sx.y);
+        } else {
+          const double2 e = *reinterpret_cast<const double2*>(ept + (((size_t)sb * 2 + (warp - 6)) * kDB + lane) * 2);
+          const int col = Nq + (warp - 6);
+          fc[(size_t)col * kDBP] = ab * e.x;                                   // Zy[0] = 0, Zy[1] = 1
+          fd[(size_t)col * kDBP] = warp == 6 ? 0.0 : ab * e.y * c * inv_ell;
+          if (warp == 6) rotate_run_pm(fc, fd, Nq + 2, 0, mhalf, z0, dz, c, tau, ab, inv_ell, sz.x, sz.y);
+          else rotate_run_pm(fc, fd, Nq + 2, mhalf, M - mhalf, z0, dz, c, tau, ab, inv_ell, sz.x, sz.y);
+        }
+      }
+      __syncthreads();
+      {  // phase 2: DMMA contraction; warps 0-3 also prepare the next tile's tables
+        if (t + 1 < T) fill_tables(t + 1, nxt, sb ^ 1);
+        const double* wsrc = Wt + (size_t)cur * kDB * kWS + (size_t)t4 * kWS + g;
+        const double* asrc[PT];
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+          const int u = warp * PT + j, f = u / (4 * PT), tile = u % (4 * PT);
+          asrc[j] = feat + (size_t)f * PLANE + (size_t)(tile * 8 + g) * kDBP + t4;
+        }
+#pragma unroll
+        for (int k = 0; k < kDB / 4; ++k) {
+          const double wk = wsrc[(size_t)4 * k * kWS];
+#pragma unroll
+          for (int j = 0; j < PT; ++j) dmma884(acc[j][0], acc[j][1], asrc[j][4 * k], wk);
+        }
+      }
+    }
+    __syncthreads();
+    // publish red[feature][sample][point] over the dead feature tile, load the tail operands behind it
+#pragma unroll
+    for (int j = 0; j < PT; ++j) {
+      const int u = warp * PT + j, f = u / (4 * PT), tile = u % (4 * PT);
+      red[((size_t)f * kST + 2 * t4) * ROWS + tile * 8 + g] = acc[j][0];
+      red[((size_t)f * kST + 2 * t4 + 1) * ROWS + tile * 8 + g] = acc[j][1];
+    }
+    if (tid < 32) {
+      zy[tid] = tid < Mp ? zy_at(a.Z, D, l, tid) : 0.0;
+      mu[tid] = tid >= Mp ? 0.0 : (tid < 2 ? a.query_latent[((size_t)p * 2 + tid) * D + l]
+                                          : a.q_mu[((size_t)p * M + tid - 2) * D + l]);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 2 * kST * ROWS; idx += nt) {
+      const int wh = idx / (kST * ROWS), i = (idx / ROWS) % kST, xx = idx % ROWS;
+      if (i < ns && xx < A) {
+        double* dst = wh == 0 ? a.f0 : a.h0;
+        if (dst != nullptr) dst[((size_t)pl * S + s0 + i) * A + xx] = red[idx];
+      }
+    }
+    for (int idx = tid; idx < Mp * Mp; idx += nt)
+      Lsm[(idx / Mp) * LDM + idx % Mp] = a.Linv[(size_t)pl * Mp * Mp + idx];   // explicit inverse factor
+    for (int idx = tid; idx < Nq * Mp; idx += nt) {
+      const int n = idx / Mp, m = idx % Mp;
+      Kfu[idx] = s2 * vg_matern52(fabs(a.Xq[(size_t)n * D + l] - zy[m]) / ell);
+    }
+    __syncthreads();
+    pathwise_update_tail(a, pl, p, l, s0, ns, red, ROWS, Lsm, a.Sfull + (size_t)pl * Mp * Mp, Mp, Kfu, vs, mu, sqrtj);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Warp-synchronous variant of the equispaced sampler (used when N + Mp <= 96): ONE WARP per (problem, latent, sample
 // tile).  No block-level barrier exists anywhere in the kernel, so the FP64 pipe is kept busy by the warp scheduler
 // interleaving ~13 independent warps per SM that sit in different phases:
@@ -1389,6 +1590,17 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
         return e;
       pathwise_tail_kernel<<<d.num_problems * a.D, 128, smem_t, s>>>(a, meta);
       h->launches += 2;
+    } else if (h->allow_dmma_path && A <= 192) {
+      const int PT = A <= 96 ? 3 : 6, ROWS = 32 * PT;
+      const size_t main_view = (size_t)2 * ROWS * kDBP + 3 * kDB * kWS + 3 * 4 * kDB + 3 * kDB + 2 * (2 * 2 * kDB * 2);
+      const size_t tail_view = (size_t)2 * kST * ROWS + 32 * LDM + (size_t)Nq * Mp + kST * 32 + 64;
+      const size_t smem_m = sizeof(double) * std::max(main_view, tail_view);
+      if (smem_m > 227 * 1024) return cudaErrorInvalidValue;
+      void (*kern)(PathwiseArgs, const double*) = PT == 3 ? pathwise_dmma_kernel<3> : pathwise_dmma_kernel<6>;
+      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m)) != cudaSuccess)
+        return e;
+      kern<<<d.num_problems * a.D * a.nchunk, 256, smem_m, s>>>(a, meta);
+      h->launches++;
     } else {
       void (*kern)(PathwiseArgs, const double*);
       if (a.S <= 7) kern = XT == 3 ? pathwise_grid_kernel<3, 7> : pathwise_grid_kernel<4, 7>;
