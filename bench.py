@@ -294,17 +294,19 @@ def run_b200(args):
             if t:
                 roofline["traffic"] = t["dram_bytes_per_launch"]
                 roofline["traffic_source"] = t["source"]
-        # dominant stage by time = the sampler: FP64 CUDA-core bound (the path has no tensor-core-shaped work that holds
-        # the float64 tolerance).  Algorithmic flops = the contraction (f0 and d f0/d lengthscale, 2 flops per FMA) plus
-        # 6 FMA-class ops per generated feature; peak = FP64 FMA rate measured now by vgpmp_probe_fp64_tflops.
+        # dominant stage by time = the sampler: FP64-pipe bound (B200 runs DMMA on the FP64 pipe at the DFMA rate, see
+        # profiles/r1_v9_dmma_probe.txt).  Algorithmic flops = the two contractions (f0 and d f0/d lengthscale: S*A*B FMAs
+        # each, 2 flops per FMA) plus 6 FP64 operations per generated feature pair; peak = FP64 FMA rate measured now
+        # by vgpmp_probe_fp64_tflops.  (Rounds up to r1_v8 multiplied the contraction by a stray factor 2; their
+        # recorded "0.57" fractions are 0.33 on this count.)  The stage time includes gp_prepare (~0.1 ms).
         A = N + M + 2
-        pw_flops = Bp * D * (2 * 2 * S * A * B * 2 + 2 * 6 * A * B)
+        pw_flops = Bp * D * (2 * 2 * S * A * B + 6 * A * B)
         pw = stages.get("pathwise_sample")
         out_dom = None
         if pw:
             peak64 = float(eng.lib.vgpmp_probe_fp64_tflops(local))
             ach = pw_flops / (pw["ms_per_launch"] * 1e-3) / 1e12
-            out_dom = {"kernel": "pathwise_grid_kernel<3> (rotation-recurrence Fourier features + register-tiled contraction + pathwise update)",
+            out_dom = {"kernel": "gp_prepare_kernel + pathwise_dmma_kernel<3> (rotation-recurrence Fourier features, DMMA m8n8k4 contraction, pathwise update)",
                        "bound": "fp64", "achieved": ach, "peak": peak64, "unit": "TFLOP/s", "frac": ach / peak64 if peak64 > 0 else None,
                        "peak_source": "measured now: vgpmp_probe_fp64_tflops (DFMA chains, CUDA events)", "traffic": None,
                        "algorithmic_flops_per_launch": pw_flops, "ms_per_launch": pw["ms_per_launch"], "share_of_step": pw["share"]}

@@ -94,6 +94,15 @@ static void run(const char* name, double fma_per_thread_iter, double mma_fma_per
 }
 
 int main() {
+  // dependent-issue latency: ONE warp per SM sub-partition (128 threads, 1 CTA/SM), 1..4 independent chains per thread
+  printf("-- latency: 1 CTA/SM x 256 threads = 2 warps per sub-partition; TFLOP/s scales with chains until the pipe saturates\n");
+  run<0, 1, 0>("dfma x1", 1, 0, 1);
+  run<0, 2, 0>("dfma x2", 2, 0, 1);
+  run<0, 4, 0>("dfma x4", 4, 0, 1);
+  run<1, 0, 1>("dmma m8n8k4 x1", 0, 1 * 256.0, 1);
+  run<1, 0, 2>("dmma m8n8k4 x2", 0, 2 * 256.0, 1);
+  run<1, 0, 3>("dmma m8n8k4 x3", 0, 3 * 256.0, 1);
+  run<1, 0, 4>("dmma m8n8k4 x4", 0, 4 * 256.0, 1);
   for (int c = 1; c <= 4; c *= 2) {
     run<0, 8, 0>("dfma x8", 8, 0, c);
     run<1, 0, 8>("dmma m8n8k4 x8", 0, 8 * 256.0, c);

@@ -15,6 +15,7 @@
 // shared memory; triangular solves are warp-per-right-hand-side with the running vector in registers and the pivot
 // broadcast by shuffle.  Matrices in shared memory use a row stride of 33 doubles so that both row and column walks
 // are bank-conflict free.
+#include <cstdlib>
 #include <algorithm>
 
 #include "common.cuh"
@@ -669,14 +670,12 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// one chunk of an equispaced run written point-major (feature of point n at fc[n * kDBP]); the step phasor comes in
+// one chunk of an equispaced run written point-major (feature of point n at fc[n * kDBP]); start phasor (amplitude
+// folded in) and step phasor come from the tables the previous tile's contraction phase prepared
 __device__ __forceinline__ void rotate_run_pm(double* fc, double* fd, int col0, int first, int count, double g0, double dg,
-                                              double c, double tau, double amp, double inv_ell, double cd, double sd) {
+                                              double c, double inv_ell, double cs, double sn, double cd, double sd) {
   if (count <= 0) return;
-  double sn, cs;
   const double tn = g0 + dg * first;
-  sincos(tn * c + tau, &sn, &cs);
-  cs *= amp; sn *= amp;
   double q = tn * c * inv_ell;
   const double dq = dg * c * inv_ell;
   fc += (size_t)(col0 + first) * kDBP;
@@ -706,8 +705,10 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
   double* Wt = feat + 2 * PLANE;                // [3][kDB][kWS]
   double* osum = Wt + 3 * kDB * kWS;            // [3][4][kDB]  partial sums over the input dims of omega_b
   double* tb = osum + 3 * 4 * kDB;              // [3][kDB]     tau_b
-  double* stp = tb + 3 * kDB;                   // [2][2][kDB][2]  step phasors (cos, sin) of the query grid | inducing grid
-  double* ept = stp + 2 * 2 * kDB * 2;          // [2][2][kDB][2]  unit phasors of the conditioned endpoints Zy = 0 | 1
+  // tables for the tile about to be generated, written during the previous tile's contraction phase
+  double* stt = tb + 3 * kDB;                   // [8 chunks][kDB][2]  chunk-start phasors, amplitude folded in
+  double* stp = stt + 8 * kDB * 2;              // [2][kDB][2]  step phasors (cos, sin) of the query grid | inducing grid
+  double* ept = stp + 2 * kDB * 2;              // [2][kDB][2]  unit phasors of the conditioned endpoints Zy = 0 | 1
   // tail view over the dead feature tile: red | Lsm | Kfu | vs | mu | zy
   double* red = sm;                             // [2][kST][ROWS]
   double* Lsm = red + (size_t)2 * kST * ROWS;
@@ -729,17 +730,24 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
   // phase-2 roles: warp owns PT (feature, point tile) units; MMA fragment coordinates g = lane / 4, t4 = lane % 4
   const int g = lane >> 2, t4 = lane & 3;
 
-  // next-tile tables, filled by warps 0-3 (one sincos per thread): step phasors and endpoint phasors of tile `tile`
-  auto fill_tables = [&](int tile, int ob, int sb) {
-    if (warp >= 4) return;
+  // tables of tile `tile` (operands staged in buffer ob): every warp evaluates its chunk's start phasor, warps 0-3 one
+  // more sincos each (the two step phasors, the two endpoint phasors).  Runs inside the previous tile's contraction
+  // phase, where its latency hides behind the DMMAs of the same warp.
+  auto fill_tables = [&](int tile, int ob) {
     const double* os = osum + (size_t)ob * 4 * kDB + lane;
     const double c = (os[0] + os[kDB] + os[2 * kDB] + os[3 * kDB]) * inv_ell, tau = tb[ob * kDB + lane];
-    (void)tile;
+    const double ab = (tile * kDB + lane < B) ? amp : 0.0;
+    const double tn = warp < 6 ? t0 + dt * (warp * per) : z0 + dz * (warp == 6 ? 0 : mhalf);
     double sn, cs;
-    const double arg = warp == 0 ? dt * c : (warp == 1 ? dz * c : (warp == 2 ? tau : c + tau));
-    sincos(arg, &sn, &cs);
-    double* dst = (warp < 2 ? stp : ept) + (((size_t)sb * 2 + (warp & 1)) * kDB + lane) * 2;
-    dst[0] = cs; dst[1] = sn;
+    sincos(tn * c + tau, &sn, &cs);
+    double* d0 = stt + ((size_t)warp * kDB + lane) * 2;
+    d0[0] = ab * cs; d0[1] = ab * sn;
+    if (warp < 4) {
+      const double arg = warp == 0 ? dt * c : (warp == 1 ? dz * c : (warp == 2 ? tau : c + tau));
+      sincos(arg, &sn, &cs);
+      double* d1 = (warp < 2 ? stp : ept) + ((size_t)(warp & 1) * kDB + lane) * 2;
+      d1[0] = cs; d1[1] = sn;
+    }
   };
 
   for (int s0 = s_begin; s0 < s_end; s0 += kST) {
@@ -771,38 +779,38 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
     stage(0);
     if (kDB < B) prefetch(kDB);
     __syncthreads();
-    fill_tables(0, 0, 0);
+    fill_tables(0, 0);
 
     for (int t = 0; t < T; ++t) {
-      const int cur = t % 3, nxt = (t + 1) % 3, sb = t & 1;
+      const int cur = t % 3, nxt = (t + 1) % 3;
       if (t + 1 < T) {
         stage(nxt);
         if ((t + 2) * kDB < B) prefetch((t + 2) * kDB);
       }
       __syncthreads();  // staging and tables visible; previous tile's contraction finished -> feature tile is free
-      {  // phase 1: features by rotation along the grid
+      {  // phase 1: features by rotation along the grid (no transcendental on this path)
         const double* os = osum + (size_t)cur * 4 * kDB + lane;
-        const double c = (os[0] + os[kDB] + os[2 * kDB] + os[3 * kDB]) * inv_ell, tau = tb[cur * kDB + lane];
-        const double ab = (t * kDB + lane < B) ? amp : 0.0;
+        const double c = (os[0] + os[kDB] + os[2 * kDB] + os[3 * kDB]) * inv_ell;
         double* fc = feat + lane;
         double* fd = fc + PLANE;
-        const double2 sx = *reinterpret_cast<const double2*>(stp + (((size_t)sb * 2 + 0) * kDB + lane) * 2);
-        const double2 sz = *reinterpret_cast<const double2*>(stp + (((size_t)sb * 2 + 1) * kDB + lane) * 2);
+        const double2 st = *reinterpret_cast<const double2*>(stt + ((size_t)warp * kDB + lane) * 2);
+        const double2 sp = *reinterpret_cast<const double2*>(stp + ((size_t)(warp < 6 ? 0 : 1) * kDB + lane) * 2);
         if (warp < 6) {
           const int n0 = warp * per;
-          rotate_run_pm(fc, fd, 0, n0, min(Nq, n0 + per) - n0, t0, dt, c, tau, ab, inv_ell, sx.x, sx.y);
+          rotate_run_pm(fc, fd, 0, n0, min(Nq, n0 + per) - n0, t0, dt, c, inv_ell, st.x, st.y, sp.x, sp.y);
         } else {
-          const double2 e = *reinterpret_cast<const double2*>(ept + (((size_t)sb * 2 + (warp - 6)) * kDB + lane) * 2);
+          const double2 e = *reinterpret_cast<const double2*>(ept + ((size_t)(warp - 6) * kDB + lane) * 2);
+          const double ab = (t * kDB + lane < B) ? amp : 0.0;
           const int col = Nq + (warp - 6);
           fc[(size_t)col * kDBP] = ab * e.x;                                   // Zy[0] = 0, Zy[1] = 1
           fd[(size_t)col * kDBP] = warp == 6 ? 0.0 : ab * e.y * c * inv_ell;
-          if (warp == 6) rotate_run_pm(fc, fd, Nq + 2, 0, mhalf, z0, dz, c, tau, ab, inv_ell, sz.x, sz.y);
-          else rotate_run_pm(fc, fd, Nq + 2, mhalf, M - mhalf, z0, dz, c, tau, ab, inv_ell, sz.x, sz.y);
+          if (warp == 6) rotate_run_pm(fc, fd, Nq + 2, 0, mhalf, z0, dz, c, inv_ell, st.x, st.y, sp.x, sp.y);
+          else rotate_run_pm(fc, fd, Nq + 2, mhalf, M - mhalf, z0, dz, c, inv_ell, st.x, st.y, sp.x, sp.y);
         }
       }
       __syncthreads();
-      {  // phase 2: DMMA contraction; warps 0-3 also prepare the next tile's tables
-        if (t + 1 < T) fill_tables(t + 1, nxt, sb ^ 1);
+      {  // phase 2: DMMA contraction, and the next tile's tables in its shadow
+        if (t + 1 < T) fill_tables(t + 1, nxt);
         const double* wsrc = Wt + (size_t)cur * kDB * kWS + (size_t)t4 * kWS + g;
         const double* asrc[PT];
 #pragma unroll
@@ -1592,9 +1600,10 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
       h->launches += 2;
     } else if (h->allow_dmma_path && A <= 192) {
       const int PT = A <= 96 ? 3 : 6, ROWS = 32 * PT;
-      const size_t main_view = (size_t)2 * ROWS * kDBP + 3 * kDB * kWS + 3 * 4 * kDB + 3 * kDB + 2 * (2 * 2 * kDB * 2);
+      const size_t main_view = (size_t)2 * ROWS * kDBP + 3 * kDB * kWS + 3 * 4 * kDB + 3 * kDB + 8 * kDB * 2 + 2 * (2 * kDB * 2);
       const size_t tail_view = (size_t)2 * kST * ROWS + 32 * LDM + (size_t)Nq * Mp + kST * 32 + 64;
-      const size_t smem_m = sizeof(double) * std::max(main_view, tail_view);
+      size_t smem_m = sizeof(double) * std::max(main_view, tail_view);
+      if (const char* pad = std::getenv("VGPMP_DMMA_PAD_KB")) smem_m += (size_t)std::atoi(pad) * 1024;   // occupancy experiments
       if (smem_m > 227 * 1024) return cudaErrorInvalidValue;
       void (*kern)(PathwiseArgs, const double*) = PT == 3 ? pathwise_dmma_kernel<3> : pathwise_dmma_kernel<6>;
       if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m)) != cudaSuccess)
