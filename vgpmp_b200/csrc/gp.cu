@@ -139,13 +139,15 @@ __global__ void kuf_kernel(int D, int M, int N, const double* __restrict__ Z, co
 // ---------------------------------------------------------------------------------------------
 // Kuu + chol + q_sqrt un-whitening + KL, one CTA (128 threads) per (problem, latent)
 // ---------------------------------------------------------------------------------------------
-constexpr int kPrepSmem = 5 * 32 * LDM + 2 * 32 + 16;   // doubles of shared memory gp_prepare_body needs
+constexpr int kPrepSmem = 4 * 32 * LDM + 2 * 32 + 32;   // doubles of shared memory gp_prepare_body needs: K | L | q | L^-1 | zy | mu | scratch
 
 // Body of the GP preparation for one (problem, latent), working on a caller-provided shared-memory block.
 // `smem` must hold kPrepSmem doubles; needs blockDim.x >= 32 and a multiple of 32.
 __device__ void gp_prepare_body(int D, int M, double jitter, const vgpmp_params& P, int pl, double* __restrict__ Lc_out,
                                 double* __restrict__ S_out, double* __restrict__ kl_l, double* __restrict__ kvec,
-                                double* __restrict__ Linv_out, double* smem) {
+                                double* __restrict__ Linv_out, double* smem, double* Ssm = nullptr) {
+  // Ssm (optional, [32][LDM] in shared memory, may alias smem = the K block): a copy of q_sqrt_full for a caller that
+  // continues with the pathwise update in the same CTA; the explicit inverse factor then stays in smem + 3*32*LDM.
   double* Ksm = smem;
   double* Lsm = Ksm + 32 * LDM;
   double* qsm = Lsm + 32 * LDM;
@@ -179,7 +181,7 @@ __device__ void gp_prepare_body(int D, int M, double jitter, const vgpmp_params&
       if (lane < Mp) Lc_out[(size_t)pl * Mp * Mp + i * Mp + lane] = Lsm[i * LDM + lane];
   // explicit inverse factor: thread j holds column j of L^-1 in registers,
   //   x_i = (delta_ij - sum_{k<i} L[i][k] x_k) / L[i][i]   (x_k = 0 for k < j; L is zero-padded beyond Mp)
-  if (Linv_out != nullptr) {
+  if (Linv_out != nullptr || Ssm != nullptr) {
     if (tid < 32) {
       const int j = tid;
       double x[32];
@@ -193,22 +195,9 @@ __device__ void gp_prepare_body(int D, int M, double jitter, const vgpmp_params&
       }
     }
     __syncthreads();
-    for (int i = warp; i < Mp; i += nw)
-      if (lane < Mp) Linv_out[(size_t)pl * Mp * Mp + i * Mp + lane] = Li[i * LDM + lane];
-  }
-
-  // q_sqrt property: Lc @ pad(_q_sqrt) + jitter * diag(1,1,0,...)   models/vgpmp.py:208-218
-  if (S_out != nullptr) {
-    for (int i = warp; i < Mp; i += nw) {
-      const int j = lane;
-      if (j < Mp) {
-        double acc = 0.0;
-        if (i >= 2 && j >= 2 && j <= i)
-          for (int k = j; k <= i; ++k) acc += Lsm[i * LDM + k] * qsm[(k - 2) * LDM + (j - 2)];
-        if (i == j && i < 2) acc += jitter;
-        S_out[(size_t)pl * Mp * Mp + i * Mp + j] = acc;
-      }
-    }
+    if (Linv_out != nullptr)
+      for (int i = warp; i < Mp; i += nw)
+        if (lane < Mp) Linv_out[(size_t)pl * Mp * Mp + i * Mp + lane] = Li[i * LDM + lane];
   }
 
   // prior_kl: p_mu = K[:, :2] chol_solve(L[:2,:2], q~);  a = (L^-1 (mu - p_mu))[2:]   prior_kl.py:24-34
@@ -240,6 +229,23 @@ __device__ void gp_prepare_body(int D, int M, double jitter, const vgpmp_params&
   }
   const double tot = block_sum(part, red);
   if (tid == 0 && kl_l != nullptr) kl_l[pl] = 0.5 * (tot - (double)M);
+  // q_sqrt property: Lc @ pad(_q_sqrt) + jitter * diag(1,1,0,...)   models/vgpmp.py:208-218
+  // (last: K is dead by now, so a caller may pass Ssm == smem and have q_sqrt_full overwrite it)
+  __syncthreads();
+  if (S_out != nullptr || Ssm != nullptr) {
+    for (int i = warp; i < Mp; i += nw) {
+      const int j = lane;
+      if (j < Mp) {
+        double acc = 0.0;
+        if (i >= 2 && j >= 2 && j <= i)
+          for (int k = j; k <= i; ++k) acc += Lsm[i * LDM + k] * qsm[(k - 2) * LDM + (j - 2)];
+        if (i == j && i < 2) acc += jitter;
+        if (S_out != nullptr) S_out[(size_t)pl * Mp * Mp + i * Mp + j] = acc;
+        if (Ssm != nullptr) Ssm[i * LDM + j] = acc;
+      }
+    }
+  }
+
 }
 
 __global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, double jitter, vgpmp_params P,
@@ -259,6 +265,8 @@ __global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, double ji
 // ---------------------------------------------------------------------------------------------
 struct PathwiseArgs {
   int D, M, Nq, S, B, XG, KS;
+  int split_tail;      // 1: the sampler stops at f0/h0; gp_prepare_update_kernel finishes the sample paths
+  int ablate;          // experiments only (VGPMP_ABLATE): bit 0 skip sincos tables, bit 1 skip rotations, bit 2 skip DMMAs
   int nchunk, chunk;   // the S samples are split into nchunk CTAs per (problem, latent), `chunk` samples each (multiple of kST)
   double jitter;
   const double *Z, *Xq, *ls, *var, *q_mu, *query_latent;
@@ -781,14 +789,14 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
     __syncthreads();
     fill_tables(0, 0);
 
-    for (int t = 0; t < T; ++t) {
+    for (int t = 0; t < ((a.ablate & 16) ? 0 : T); ++t) {
       const int cur = t % 3, nxt = (t + 1) % 3;
       if (t + 1 < T) {
         stage(nxt);
         if ((t + 2) * kDB < B) prefetch((t + 2) * kDB);
       }
       __syncthreads();  // staging and tables visible; previous tile's contraction finished -> feature tile is free
-      {  // phase 1: features by rotation along the grid (no transcendental on this path)
+      if (!(a.ablate & 2)) {  // phase 1: features by rotation along the grid (no transcendental on this path)
         const double* os = osum + (size_t)cur * 4 * kDB + lane;
         const double c = (os[0] + os[kDB] + os[2 * kDB] + os[3 * kDB]) * inv_ell;
         double* fc = feat + lane;
@@ -810,7 +818,7 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
       }
       __syncthreads();
       {  // phase 2: DMMA contraction, and the next tile's tables in its shadow
-        if (t + 1 < T) fill_tables(t + 1, nxt);
+        if (t + 1 < T && !(a.ablate & 1)) fill_tables(t + 1, nxt);
         const double* wsrc = Wt + (size_t)cur * kDB * kWS + (size_t)t4 * kWS + g;
         const double* asrc[PT];
 #pragma unroll
@@ -818,15 +826,18 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
           const int u = warp * PT + j, f = u / (4 * PT), tile = u % (4 * PT);
           asrc[j] = feat + (size_t)f * PLANE + (size_t)(tile * 8 + g) * kDBP + t4;
         }
+        if (!(a.ablate & 4)) {
 #pragma unroll
         for (int k = 0; k < kDB / 4; ++k) {
           const double wk = wsrc[(size_t)4 * k * kWS];
 #pragma unroll
           for (int j = 0; j < PT; ++j) dmma884(acc[j][0], acc[j][1], asrc[j][4 * k], wk);
         }
+        }
       }
     }
     __syncthreads();
+    if (a.ablate & 8) { if (tid == 0 && acc[0][0] == 12345.678) a.f[0] = acc[0][1]; continue; }
     // publish red[feature][sample][point] over the dead feature tile, load the tail operands behind it
 #pragma unroll
     for (int j = 0; j < PT; ++j) {
@@ -847,6 +858,7 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
         if (dst != nullptr) dst[((size_t)pl * S + s0 + i) * A + xx] = red[idx];
       }
     }
+    if (a.split_tail) continue;   // gp_prepare_update_kernel takes it from f0
     for (int idx = tid; idx < Mp * Mp; idx += nt)
       Lsm[(idx / Mp) * LDM + idx % Mp] = a.Linv[(size_t)pl * Mp * Mp + idx];   // explicit inverse factor
     for (int idx = tid; idx < Nq * Mp; idx += nt) {
@@ -855,6 +867,79 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
     }
     __syncthreads();
     pathwise_update_tail(a, pl, p, l, s0, ns, red, ROWS, Lsm, a.Sfull + (size_t)pl * Mp * Mp, Mp, Kfu, vs, mu, sqrtj);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GP preparation fused with the pathwise update (used behind the DMMA sampler, which only needs the draws and the
+// lengthscale): one CTA of 128 threads per (problem, latent[, sample chunk]).  gp_prepare_body leaves L, L^-1, q_sqrt_full,
+// mu and Zy in shared memory; every warp then finishes whole samples on its own, no CTA barrier between them:
+//   u = mu + S eps_u;  r = u - f0(Zy) - sqrt(jitter) eps_j;  v = L^-T L^-1 r;  f = f0(X) + Kfu v.
+// Small CTAs, latency hidden by occupancy - the job the 256-thread sampler CTAs did badly in their tails.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 6) gp_prepare_update_kernel(PathwiseArgs a, vgpmp_params P, double* __restrict__ Lc_out,
+                                                                  double* __restrict__ S_out, double* __restrict__ kl_l,
+                                                                  double* __restrict__ kvec, double* __restrict__ Linv_out,
+                                                                  const double* __restrict__ meta) {
+  __shared__ __align__(16) double prep[kPrepSmem];    // gp_prepare_body's block: K -> q_sqrt_full | L | q | L^-1 | zy | mu | ...
+  __shared__ double vsm[kST * 32];                    // v of one tile of samples
+  const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, A = Nq + Mp;
+  const int pl = blockIdx.x / a.nchunk, chunk = blockIdx.x % a.nchunk, p = pl / D, l = pl % D;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
+  const bool first = chunk == 0;                      // chunk 0 publishes the factors for the reverse pass
+  gp_prepare_body(D, M, a.jitter, P, pl, first ? Lc_out : nullptr, first ? S_out : nullptr, first ? kl_l : nullptr,
+                  first ? kvec : nullptr, first ? Linv_out : nullptr, prep, prep);
+  if (meta[0] == 0.0) return;                         // general sampler runs after this kernel and does its own update
+  const double* Ssm = prep;
+  const double* Lism = prep + 3 * 32 * LDM;
+  const double* zy = prep + 4 * 32 * LDM;
+  const double* mu = zy + 32;
+  const double ell = a.ls[pl], s2 = a.var[pl], sqrtj = sqrt(a.jitter);
+  const int s_begin = chunk * a.chunk, s_end = min(S, s_begin + a.chunk);
+  for (int s0 = s_begin; s0 < s_end; s0 += kST) {
+    const int ns = min(kST, s_end - s0);
+    __syncthreads();   // q_sqrt_full complete / previous tile's vsm consumed
+    // warp per sample: u = mu + S eps_u;  r = u - f0(Zy) - sqrt(jitter) eps_j;  v = L^-T (L^-1 r)
+    for (int i = warp; i < ns; i += nw) {
+      const int s = s0 + i;
+      double* row = vsm + i * 32;
+      row[lane] = lane < Mp ? a.eps_u[((size_t)pl * S + s) * Mp + lane] : 0.0;
+      __syncwarp();
+      double r = 0.0;
+      if (lane < Mp) {
+        double u = mu[lane];
+        for (int k = 0; k <= lane; ++k) u += Ssm[lane * LDM + k] * row[k];
+        r = u - a.f0[((size_t)pl * S + s) * A + Nq + lane] - sqrtj * a.eps_j[((size_t)pl * S + s) * Mp + lane];
+      }
+      __syncwarp();
+      row[lane] = r;
+      __syncwarp();
+      const double y = warp_lower_mv(Lism, Mp, row);
+      __syncwarp();
+      row[lane] = y;
+      __syncwarp();
+      const double vv = warp_lowerT_mv(Lism, Mp, row);
+      __syncwarp();
+      row[lane] = lane < Mp ? vv : 0.0;
+      if (lane < Mp && a.v != nullptr) a.v[((size_t)pl * S + s) * Mp + lane] = vv;
+    }
+    __syncthreads();
+    // thread per query point: f[s][n] = f0[s][n] + sum_m k(x_n, z_m) v[s][m]; each kernel value is formed once and
+    // used by every sample of the tile
+    for (int n = tid; n < Nq; n += nt) {
+      const double xn = a.Xq[(size_t)n * D + l];
+      double acc[kST];
+#pragma unroll
+      for (int i = 0; i < kST; ++i) acc[i] = i < ns ? a.f0[((size_t)pl * S + s0 + i) * A + n] : 0.0;
+      for (int m = 0; m < Mp; ++m) {
+        const double kv = s2 * vg_matern52(fabs(xn - zy[m]) / ell);
+#pragma unroll
+        for (int i = 0; i < kST; ++i) acc[i] += kv * vsm[i * 32 + m];
+      }
+#pragma unroll
+      for (int i = 0; i < kST; ++i)
+        if (i < ns) a.f[(((size_t)p * S + s0 + i) * Nq + n) * D + l] = acc[i];
+    }
   }
 }
 
@@ -1548,6 +1633,7 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
     a.chunk = ((tiles + a.nchunk - 1) / a.nchunk) * kST;
     a.nchunk = (a.S + a.chunk - 1) / a.chunk;
   }
+  a.ablate = std::getenv("VGPMP_ABLATE") ? std::atoi(std::getenv("VGPMP_ABLATE")) : 0;
   a.Z = p.Z; a.Xq = Xq; a.ls = p.lengthscales; a.var = p.variances; a.q_mu = p.q_mu; a.query_latent = p.query_latent;
   a.omega = r.omega; a.tau = r.tau; a.w = r.w; a.eps_u = r.eps_u; a.eps_j = r.eps_j;
   a.Lc = Lc; a.Sfull = Sfull; a.Linv = Linv; a.f = f; a.v = v; a.f0 = f0; a.h0 = h0;
@@ -1579,7 +1665,11 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
     grid_ok = smem_g <= 200 * 1024;
   }
   const bool warp_path = grid_ok && h->allow_warp_path && A <= 96 && f0 != nullptr && h0 != nullptr && a.M >= 2;
-  if ((e = launch_gp_prepare(h, d, p, Lc, Sfull, kl_l, kvec, Linv, s)) != cudaSuccess) return e;
+  // split schedule (default): the DMMA sampler needs none of the GP factors, so it runs first and stops at f0 / h0; the
+  // preparation and the pathwise update then share one small-CTA kernel (gp_prepare_update_kernel).
+  const bool split = grid_ok && !warp_path && h->allow_dmma_path && h->allow_split_tail && A <= 192 && f0 != nullptr;
+  a.split_tail = split ? 1 : 0;
+  if (!split && (e = launch_gp_prepare(h, d, p, Lc, Sfull, kl_l, kvec, Linv, s)) != cudaSuccess) return e;
   if (grid_ok) {
     analyze_grid_kernel<<<1, 256, 0, s>>>(a.D, a.M, Nq, Xq, p.Z, meta);
     h->launches++;
@@ -1610,6 +1700,10 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
         return e;
       kern<<<d.num_problems * a.D * a.nchunk, 256, smem_m, s>>>(a, meta);
       h->launches++;
+      if (split) {
+        gp_prepare_update_kernel<<<d.num_problems * a.D * a.nchunk, 128, 0, s>>>(a, p, Lc, Sfull, kl_l, kvec, Linv, meta);
+        h->launches++;
+      }
     } else {
       void (*kern)(PathwiseArgs, const double*);
       if (a.S <= 7) kern = XT == 3 ? pathwise_grid_kernel<3, 7> : pathwise_grid_kernel<4, 7>;
