@@ -151,19 +151,21 @@ def test_gp_prepare_chol_qsqrt_kl_vs_oracle(M):
     assert abs(got - klo) <= 1e-7 * abs(klo)
 
 
-@pytest.mark.parametrize("grid", [3, 4, 2, 0])
+@pytest.mark.parametrize("grid", [5, 3, 4, 2, 0])
 @pytest.mark.parametrize("S,N,M,B", [(7, 70, 24, 64), (3, 5, 1, 3), (20, 50, 7, 40), (9, 150, 12, 33), (8, 2, 2, 32),
                                      (17, 300, 30, 70), (203, 12, 5, 16), (7, 70, 24, 1024), (5, 150, 30, 100)])
 def test_pathwise_sample_vs_oracle(S, N, M, B, grid):
-    """grid=3: equispaced fast path with the DMMA contraction, preparation + pathwise update in their own kernel
-    (default; N+M+2 <= 192, else the FMA kernel); grid=4: same sampler with the update fused into its tail;
+    """grid=5: equispaced fast path, register-resident warp-specialised DMMA sampler (default when the points fit 12 row
+    tiles, else grid=3); grid=3: shared-memory DMMA sampler, preparation + pathwise update in their own kernel
+    (N+M+2 <= 192, else the FMA kernel); grid=4: same sampler with the update fused into its tail;
     grid=2: equispaced fast path, FMA contraction; grid=0: general per-point sincos kernel.
     (203, 12, 5, 16): samples split over several CTAs."""
     case = H.make_case(num_problems=2, S=S, N=N, M=M, B=B, seed=S + N)
     model = H.make_model(case)
     model._eng.set_option("grid_fast_path", int(grid > 0))
     model._eng.set_option("dmma_sampler", int(grid >= 3))
-    model._eng.set_option("split_tail", int(grid == 3))
+    model._eng.set_option("split_tail", int(grid in (3, 5)))
+    model._eng.set_option("rr_sampler", int(grid == 5))
     f = _np(model.predict_f_samples(case["X"], draws=case["draws_stacked"]))
     for b, p in enumerate(case["oracle"]):
         want = p.sample_paths(p.X, O._t(case["q_mu"][b]), O._t(case["q_sqrt"][b]), O._t(case["ls"][b]),
@@ -203,9 +205,10 @@ def test_pathwise_sample_irregular_inputs_fall_back_to_general_kernel():
     ("kuka", "industrial", dict(B=96)),                           # config 3 shapes: S=20, N=50, M=7
     ("ur10", "bookshelves", dict(B=64, S=33)),                    # config 4 robot (D=6), more samples than one tile
 ])
-@pytest.mark.parametrize("grid", [3, 4, 1, 2, 0])
+@pytest.mark.parametrize("grid", [5, 3, 4, 1, 2, 0])
 def test_elbo_and_gradients_vs_oracle(name, env, kw, grid):
-    """grid: 3 = equispaced sampler with the DMMA contraction + split preparation/update kernel (default), 4 = DMMA sampler
+    """grid: 5 = register-resident warp-specialised DMMA sampler (default), 3 = shared-memory DMMA sampler + split
+    preparation/update kernel, 4 = DMMA sampler
     with the fused tail, 1 = warp-synchronous equispaced sampler, 2 = equispaced sampler with the FMA contraction,
     0 = general sincos sampler."""
     case = H.make_case(name, env, num_problems=2, seed=4, **kw)
@@ -213,7 +216,8 @@ def test_elbo_and_gradients_vs_oracle(name, env, kw, grid):
     model._eng.set_option("grid_fast_path", int(grid > 0))
     model._eng.set_option("warp_sampler", int(grid == 1))
     model._eng.set_option("dmma_sampler", int(grid >= 3))
-    model._eng.set_option("split_tail", int(grid == 3))
+    model._eng.set_option("split_tail", int(grid in (3, 5)))
+    model._eng.set_option("rr_sampler", int(grid == 5))
     out = model.elbo_and_grads(case["X"], draws=case["draws_stacked"], want_aux=True)
     for b, p in enumerate(case["oracle"]):
         ref = O.elbo_and_grads(p, case["q_mu"][b], case["q_sqrt"][b], case["ls"][b], case["var"][b], case["draws"][b])

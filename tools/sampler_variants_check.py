@@ -18,12 +18,13 @@ def main():
     eng = model._eng
     out = {}
     for name, opts in {"general": dict(grid_fast_path=0), "cta_fma": dict(grid_fast_path=1, dmma_sampler=0),
-                       "dmma": dict(grid_fast_path=1, dmma_sampler=1)}.items():
+                       "dmma": dict(grid_fast_path=1, dmma_sampler=1, rr_sampler=0),
+                       "rr": dict(grid_fast_path=1, dmma_sampler=1, rr_sampler=1)}.items():
         for k, v in opts.items():
             eng.set_option(k, v)
         out[name] = model.predict_f_samples(case["X"], draws=case["draws_stacked"]).cpu().numpy()
     ref = out["general"]
-    for k in ("cta_fma", "dmma"):
+    for k in ("cta_fma", "dmma", "rr"):
         print(f"{k:8s} vs general: max|df| {np.abs(out[k] - ref).max():.3e}   rel {H.rel_err(out[k], ref):.3e}")
 
 

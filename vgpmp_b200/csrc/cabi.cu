@@ -197,6 +197,7 @@ int vgpmp_set_option(vgpmp_handle* h, const char* name, int value) {
   if (std::strcmp(name, "grid_fast_path") == 0) { h->allow_grid_path = value != 0; return VGPMP_OK; }
   if (std::strcmp(name, "dmma_sampler") == 0) { h->allow_dmma_path = value != 0; return VGPMP_OK; }
   if (std::strcmp(name, "split_tail") == 0) { h->allow_split_tail = value != 0; return VGPMP_OK; }
+  if (std::strcmp(name, "rr_sampler") == 0) { h->allow_rr_path = value != 0; return VGPMP_OK; }
   if (std::strcmp(name, "warp_sampler") == 0) { h->allow_warp_path = value != 0; return VGPMP_OK; }
   return fail(h, VGPMP_ERR_INVALID, std::string("set_option: unknown option ") + name);
 }

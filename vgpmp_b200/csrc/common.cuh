@@ -60,6 +60,7 @@ struct vgpmp_handle {
   bool allow_warp_path = false; // experimental warp-synchronous sampler (N + Mp <= 96); slower than the CTA kernel so far
   bool allow_dmma_path = true;  // DMMA contraction in the equispaced sampler (N + M + 2 <= 192), else the FMA kernel
   bool allow_split_tail = true; // DMMA sampler stops at f0/h0; preparation + pathwise update share gp_prepare_update_kernel
+  bool allow_rr_path = true;    // register-resident warp-specialised DMMA sampler (<= 12 point tiles), else the shared-memory one
   bool allow_grid_path = true;  // equispaced rank-1 fast path of the pathwise sampler (vgpmp_set_option)
   bool profiling = false;
   struct Span { int stage; cudaEvent_t a, b; };

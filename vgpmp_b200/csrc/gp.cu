@@ -266,7 +266,6 @@ __global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, double ji
 struct PathwiseArgs {
   int D, M, Nq, S, B, XG, KS;
   int split_tail;      // 1: the sampler stops at f0/h0; gp_prepare_update_kernel finishes the sample paths
-  int ablate;          // experiments only (VGPMP_ABLATE): bit 0 skip sincos tables, bit 1 skip rotations, bit 2 skip DMMAs
   int nchunk, chunk;   // the S samples are split into nchunk CTAs per (problem, latent), `chunk` samples each (multiple of kST)
   double jitter;
   const double *Z, *Xq, *ls, *var, *q_mu, *query_latent;
@@ -789,14 +788,14 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
     __syncthreads();
     fill_tables(0, 0);
 
-    for (int t = 0; t < ((a.ablate & 16) ? 0 : T); ++t) {
+    for (int t = 0; t < T; ++t) {
       const int cur = t % 3, nxt = (t + 1) % 3;
       if (t + 1 < T) {
         stage(nxt);
         if ((t + 2) * kDB < B) prefetch((t + 2) * kDB);
       }
       __syncthreads();  // staging and tables visible; previous tile's contraction finished -> feature tile is free
-      if (!(a.ablate & 2)) {  // phase 1: features by rotation along the grid (no transcendental on this path)
+      {  // phase 1: features by rotation along the grid (no transcendental on this path)
         const double* os = osum + (size_t)cur * 4 * kDB + lane;
         const double c = (os[0] + os[kDB] + os[2 * kDB] + os[3 * kDB]) * inv_ell;
         double* fc = feat + lane;
@@ -818,7 +817,7 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
       }
       __syncthreads();
       {  // phase 2: DMMA contraction, and the next tile's tables in its shadow
-        if (t + 1 < T && !(a.ablate & 1)) fill_tables(t + 1, nxt);
+        if (t + 1 < T) fill_tables(t + 1, nxt);
         const double* wsrc = Wt + (size_t)cur * kDB * kWS + (size_t)t4 * kWS + g;
         const double* asrc[PT];
 #pragma unroll
@@ -826,18 +825,15 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
           const int u = warp * PT + j, f = u / (4 * PT), tile = u % (4 * PT);
           asrc[j] = feat + (size_t)f * PLANE + (size_t)(tile * 8 + g) * kDBP + t4;
         }
-        if (!(a.ablate & 4)) {
 #pragma unroll
         for (int k = 0; k < kDB / 4; ++k) {
           const double wk = wsrc[(size_t)4 * k * kWS];
 #pragma unroll
           for (int j = 0; j < PT; ++j) dmma884(acc[j][0], acc[j][1], asrc[j][4 * k], wk);
         }
-        }
       }
     }
     __syncthreads();
-    if (a.ablate & 8) { if (tid == 0 && acc[0][0] == 12345.678) a.f[0] = acc[0][1]; continue; }
     // publish red[feature][sample][point] over the dead feature tile, load the tail operands behind it
 #pragma unroll
     for (int j = 0; j < PT; ++j) {
@@ -867,6 +863,248 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
     }
     __syncthreads();
     pathwise_update_tail(a, pl, p, l, s0, ns, red, ROWS, Lsm, a.Sfull + (size_t)pl * Mp * Mp, Mp, Kfu, vs, mu, sqrtj);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Equispaced sampler, register-resident features (N + 2 and M each padded to tiles of 8 rows, <= 12 tiles in total).
+// The DMMA A fragment of thread (g = lane/4, t = lane%4) is the feature of row g at basis t of a 4-basis step - exactly
+// the state of one rotation chain.  So a consumer warp keeps the chain of (row g, basis t) in registers, walks it from
+// point tile to point tile with the 8-step phasor E^8, and feeds the cos / sin registers straight into two DMMAs per
+// tile: the feature matrix never exists in memory, the main loop has no CTA-wide barrier and no shared-memory feature
+// traffic, and one warp alone keeps its sub-partition's FP64 pipe busy (32 pipe cycles of DMMA hide the 2-level
+// rotation dependency).  d f0 / d lengthscale uses the separable form  h0[s,x] = t_x sum_b sin(theta_xb) (w_sb c_b / l):
+// same chain registers, weights scaled once per step, rows scaled by their coordinate at the end.
+//   warps 0-5  consumers: 4-basis steps round-robin; accumulators C[12 tiles][cos|sin][2] for the whole basis loop;
+//   warps 6-7  producers: lane = basis of a 32-basis slot; 6 branch-free sincos (start, step of both grids, the two
+//              conditioned endpoints), then the 8 row starts S E^g and E^8 by complex products; 42 doubles per basis
+//              into a 4-slot ring handed over with named barriers.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRB = 32;        // bases per table slot
+constexpr int kRE = 42;        // doubles per basis in a slot: Sx[8] | E8x | Sz[8] | E8z | e0 | e1 | c | pad
+constexpr int kRS = 4;         // ring slots
+constexpr int kRC = 6;         // consumer warps
+constexpr int kRT = 12;        // point tiles (rows / 8) a consumer carries
+
+// shared-memory mbarrier helpers (producer/consumer hand-over without coupling the consumers to each other)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+  } while (!ok);
+}
+
+// branch-free double sincos for |x| < 2^20 (the caller checks and falls back): three-term Cody-Waite reduction by pi/2,
+// Taylor kernels on [-pi/4, pi/4] truncated below 1e-17.  Straight-line code, so several calls interleave.
+__device__ __forceinline__ void sincos_bf(double x, double* sn, double* cs) {
+  const double n = rint(x * 0.63661977236758134308);
+  const int q = __double2int_rn(n);
+  double r = fma(-n, 1.5707963267948966, x);
+  r = fma(-n, 6.123233995736766e-17, r);
+  const double z = r * r;
+  double ps = 1.0 / 1307674368000.0;
+  ps = fma(ps, -z, 1.0 / 6227020800.0);
+  ps = fma(ps, -z, 1.0 / 39916800.0);
+  ps = fma(ps, -z, 1.0 / 362880.0);
+  ps = fma(ps, -z, 1.0 / 5040.0);
+  ps = fma(ps, -z, 1.0 / 120.0);
+  ps = fma(ps, -z, 1.0 / 6.0);
+  const double s = fma(-z * r, ps, r);
+  double pc = 1.0 / 20922789888000.0;
+  pc = fma(pc, -z, 1.0 / 87178291200.0);
+  pc = fma(pc, -z, 1.0 / 479001600.0);
+  pc = fma(pc, -z, 1.0 / 3628800.0);
+  pc = fma(pc, -z, 1.0 / 40320.0);
+  pc = fma(pc, -z, 1.0 / 720.0);
+  pc = fma(pc, -z, 1.0 / 24.0);
+  pc = fma(pc, -z, 0.5);
+  const double c = fma(-z, pc, 1.0);
+  const double a = (q & 1) ? c : s, b = (q & 1) ? s : c;
+  *sn = (q & 2) ? -a : a;
+  *cs = ((q + 1) & 2) ? -b : b;
+}
+
+template <int JX>   // JX = tiles of 8 rows holding the query grid and the two conditioned endpoints; inducing rows follow
+__global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, const double* __restrict__ meta) {
+  extern __shared__ __align__(16) double sm[];
+  const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, B = a.B, A = Nq + Mp;
+  const int pl = blockIdx.x / a.nchunk;
+  const int s_begin = (blockIdx.x % a.nchunk) * a.chunk, s_end = min(a.S, s_begin + a.chunk);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
+  const int T = (B + kRB - 1) / kRB;            // table slots to produce per sample tile
+  constexpr int ROWS = kRT * 8;
+  constexpr size_t kFold = (size_t)kRC * 2 * kST * ROWS, kRing = (size_t)kRS * kRB * kRE;
+  double* tab = sm;                             // [kRS][kRB][kRE]
+  double* red = sm;                             // after the basis loop: [kRC][2][kST][ROWS]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + (kFold > kRing ? kFold : kRing));   // [kRS] slot filled
+  uint64_t* empty = full + kRS;                                                          // [kRS] slot drained
+
+  if (meta[0] == 0.0) return;  // not an equispaced rank-1 grid: the general kernel does the sampling
+  if (tid == 0) {
+    for (int i = 0; i < kRS; ++i) { mbar_init(full + i, 32); mbar_init(empty + i, kRC * 32); }
+  }
+  const double ell = a.ls[pl], s2 = a.var[pl];
+  const double amp = sqrt(2.0 * s2 / (double)B), inv_ell = 1.0 / ell;
+  const double t0 = meta[1], dt = meta[2], z0 = meta[3], dz = meta[4];
+  const double* om = a.omega + (size_t)pl * B * D;
+  const double* ta = a.tau + (size_t)pl * B;
+  const double* wp = a.w + (size_t)pl * S * B;
+  const int g = lane >> 2, t4 = lane & 3;
+
+  int it = 0;                                   // sample-tile iteration: slot sequence numbers keep counting across tiles
+  for (int s0 = s_begin; s0 < s_end; s0 += kST, ++it) {
+    const int ns = min(kST, s_end - s0);
+    __syncthreads();   // barriers initialised / previous sample tile's fold is done with the shared memory
+    if (warp >= kRC) {
+      // ---------------- producer: slots n = pw, pw + 2, ... ----------------
+      const int pw = warp - kRC;
+      double c = 0.0, tau = 0.0;
+      auto fetch = [&](int n) {                 // operands of slot n, one slot ahead of their use
+        const int b = n * kRB + lane;
+        c = 0.0; tau = 0.0;
+        if (n < T && b < B) {
+          for (int d = 0; d < D; ++d) c += om[(size_t)b * D + d];
+          tau = ta[b];
+        }
+      };
+      fetch(pw);
+      for (int n = pw; n < T; n += 2) {
+        const int N = it * T + n, slot = N % kRS, use = N / kRS;
+        const bool live = n * kRB + lane < B;
+        const double cb = c * inv_ell, taub = tau;
+        fetch(n + 2);
+        const double ab = live ? amp : 0.0;
+        const double ax0 = t0 * cb + taub, ax1 = dt * cb, az0 = z0 * cb + taub, az1 = dz * cb, ae1 = cb + taub;
+        double sx, cx, sdx, cdx, sz, cz, sdz, cdz, se0, ce0, se1, ce1;
+        const double big = fmax(fmax(fabs(ax0), fabs(ax1)), fmax(fmax(fabs(az0), fabs(az1)), fmax(fabs(taub), fabs(ae1))));
+        if (big < 1048576.0) {
+          sincos_bf(ax0, &sx, &cx); sincos_bf(ax1, &sdx, &cdx);
+          sincos_bf(az0, &sz, &cz); sincos_bf(az1, &sdz, &cdz);
+          sincos_bf(taub, &se0, &ce0); sincos_bf(ae1, &se1, &ce1);
+        } else {
+          sincos(ax0, &sx, &cx); sincos(ax1, &sdx, &cdx);
+          sincos(az0, &sz, &cz); sincos(az1, &sdz, &cdz);
+          sincos(taub, &se0, &ce0); sincos(ae1, &se1, &ce1);
+        }
+        mbar_wait(empty + slot, (use & 1) ^ 1);            // consumers are done with the slot's previous contents
+        double* e = tab + ((size_t)slot * kRB + lane) * kRE;
+        double c1 = ab * cx, s1 = ab * sx, c2 = ab * cz, s2z = ab * sz;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          *reinterpret_cast<double2*>(e + 2 * r) = make_double2(c1, s1);
+          *reinterpret_cast<double2*>(e + 18 + 2 * r) = make_double2(c2, s2z);
+          const double n1 = c1 * cdx - s1 * sdx, n2 = c2 * cdz - s2z * sdz;
+          s1 = s1 * cdx + c1 * sdx; s2z = s2z * cdz + c2 * sdz;
+          c1 = n1; c2 = n2;
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {   // E^8 by three squarings
+          const double n1 = cdx * cdx - sdx * sdx, n2 = cdz * cdz - sdz * sdz;
+          sdx = 2.0 * cdx * sdx; sdz = 2.0 * cdz * sdz;
+          cdx = n1; cdz = n2;
+        }
+        *reinterpret_cast<double2*>(e + 16) = make_double2(cdx, sdx);
+        *reinterpret_cast<double2*>(e + 34) = make_double2(cdz, sdz);
+        *reinterpret_cast<double2*>(e + 36) = make_double2(ab * ce0, ab * se0);
+        *reinterpret_cast<double2*>(e + 38) = make_double2(ab * ce1, ab * se1);
+        *reinterpret_cast<double2*>(e + 40) = make_double2(cb * inv_ell, 0.0);
+        mbar_arrive(full + slot);                          // slot filled (release)
+      }
+    } else {
+      // ---------------- consumer: 4-basis steps q = warp, warp + kRC, ... ----------------
+      double acc[kRT][2][2];
+#pragma unroll
+      for (int j = 0; j < kRT; ++j) acc[j][0][0] = acc[j][0][1] = acc[j][1][0] = acc[j][1][1] = 0.0;
+      const int Q = T * (kRB / 4);
+      int cur = -1;                                         // slot number (within this sample tile) this warp holds
+      auto loadw = [&](int q) {
+        const int b = 4 * q + t4;
+        return (g < ns && b < B) ? __ldg(wp + (size_t)(s0 + g) * B + b) : 0.0;
+      };
+      double wnext = loadw(warp);
+      // rows Nq and Nq+1 (the conditioned endpoints) live in tile JX-1, or JX-2 and JX-1; this lane's role there:
+      const int xa = 8 * (JX - 2) + g, xb = 8 * (JX - 1) + g;       // its row index in those two tiles
+      const int ea = xa - Nq, eb = xb - Nq;                        // < 0: chain value, 0 / 1: endpoint, > 1: padding
+      for (int q = warp; q < Q; q += kRC) {
+        const int n = q / (kRB / 4);
+        if (n != cur) {
+          if (cur >= 0) mbar_arrive(empty + (it * T + cur) % kRS);       // done with the previous slot
+          const int N = it * T + n;
+          mbar_wait(full + N % kRS, (N / kRS) & 1);                     // this slot is filled (acquire)
+          cur = n;
+        }
+        const double wk = wnext;
+        if (q + kRC < Q) wnext = loadw(q + kRC);
+        const double* e = tab + ((size_t)((it * T + n) % kRS) * kRB + (q % (kRB / 4)) * 4 + t4) * kRE;
+        double2 ph = *reinterpret_cast<const double2*>(e + 2 * g);          // chain state: (cos, sin) of row g, amplitude in
+        double2 st = *reinterpret_cast<const double2*>(e + 16);             // E^8 of the query grid
+        const double wq = wk * e[40];                                       // w c / l for the d/dlengthscale contraction
+#pragma unroll
+        for (int j = 0; j < kRT; ++j) {
+          if (j == JX) {                                                    // inducing grid starts here
+            ph = *reinterpret_cast<const double2*>(e + 18 + 2 * g);
+            st = *reinterpret_cast<const double2*>(e + 34);
+          }
+          double ac = ph.x, as = ph.y;
+          if (j == JX - 2 && JX >= 2) {
+            if (ea >= 0) {
+              const double2 ep = ea < 2 ? *reinterpret_cast<const double2*>(e + 36 + 2 * ea) : make_double2(0.0, 0.0);
+              ac = ep.x; as = ep.y;
+            }
+          }
+          if (j == JX - 1) {
+            if (eb >= 0) {
+              const double2 ep = eb < 2 ? *reinterpret_cast<const double2*>(e + 36 + 2 * eb) : make_double2(0.0, 0.0);
+              ac = ep.x; as = ep.y;
+            }
+          }
+          dmma884(acc[j][0][0], acc[j][0][1], ac, wk);
+          dmma884(acc[j][1][0], acc[j][1][1], as, wq);
+          const double c2 = ph.x * st.x - ph.y * st.y;
+          ph.y = ph.y * st.x + ph.x * st.y;
+          ph.x = c2;
+        }
+      }
+      if (cur >= 0) mbar_arrive(empty + (it * T + cur) % kRS);
+      // the ring is dead only after ALL consumers left the loop: consumer-only barrier, then the partial sums of this
+      // warp go to red[warp][feature][sample][row] over it
+      asm volatile("bar.sync 1, %0;" ::"r"(kRC * 32) : "memory");
+#pragma unroll
+      for (int j = 0; j < kRT; ++j)
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+          for (int e2 = 0; e2 < 2; ++e2)
+            red[(((size_t)warp * 2 + f) * kST + 2 * t4 + e2) * ROWS + j * 8 + g] = acc[j][f][e2];
+    }
+    __syncthreads();
+    // fold the consumer slices in fixed order; rows -> points: query rows x < Nq, endpoints Nq, Nq+1, inducing rows after
+    for (int idx = tid; idx < 2 * kST * ROWS; idx += nt) {
+      const int wh = idx / (kST * ROWS), i = (idx / ROWS) % kST, row = idx % ROWS;
+      double tsum = red[idx];
+      for (int k = 1; k < kRC; ++k) tsum += red[(size_t)k * 2 * kST * ROWS + idx];
+      int point = -1;
+      double coord = 0.0;
+      if (row < JX * 8) {
+        if (row < Nq) { point = row; coord = t0 + dt * row; }
+        else if (row < Nq + 2) { point = row; coord = (double)(row - Nq); }
+      } else {
+        const int m = row - JX * 8;
+        if (m < M) { point = Nq + 2 + m; coord = z0 + dz * m; }
+      }
+      if (i < ns && point >= 0) {
+        if (wh == 0) { if (a.f0 != nullptr) a.f0[((size_t)pl * S + s0 + i) * A + point] = tsum; }
+        else if (a.h0 != nullptr) a.h0[((size_t)pl * S + s0 + i) * A + point] = tsum * coord;
+      }
+    }
   }
 }
 
@@ -1633,7 +1871,6 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
     a.chunk = ((tiles + a.nchunk - 1) / a.nchunk) * kST;
     a.nchunk = (a.S + a.chunk - 1) / a.chunk;
   }
-  a.ablate = std::getenv("VGPMP_ABLATE") ? std::atoi(std::getenv("VGPMP_ABLATE")) : 0;
   a.Z = p.Z; a.Xq = Xq; a.ls = p.lengthscales; a.var = p.variances; a.q_mu = p.q_mu; a.query_latent = p.query_latent;
   a.omega = r.omega; a.tau = r.tau; a.w = r.w; a.eps_u = r.eps_u; a.eps_j = r.eps_j;
   a.Lc = Lc; a.Sfull = Sfull; a.Linv = Linv; a.f = f; a.v = v; a.f0 = f0; a.h0 = h0;
@@ -1688,12 +1925,32 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
         return e;
       pathwise_tail_kernel<<<d.num_problems * a.D, 128, smem_t, s>>>(a, meta);
       h->launches += 2;
+    } else if (h->allow_dmma_path && h->allow_rr_path && split && (Nq + 2 + 7) / 8 + (a.M + 7) / 8 <= kRT) {
+      const size_t ring = (size_t)kRS * kRB * kRE, fold = (size_t)kRC * 2 * kST * kRT * 8;
+      const size_t smem_r = sizeof(double) * (std::max(ring, fold) + 2 * kRS);
+      void (*kern)(PathwiseArgs, const double*) = nullptr;
+      switch ((Nq + 2 + 7) / 8) {
+        case 1: kern = pathwise_rr_kernel<1>; break;
+        case 2: kern = pathwise_rr_kernel<2>; break;
+        case 3: kern = pathwise_rr_kernel<3>; break;
+        case 4: kern = pathwise_rr_kernel<4>; break;
+        case 5: kern = pathwise_rr_kernel<5>; break;
+        case 6: kern = pathwise_rr_kernel<6>; break;
+        case 7: kern = pathwise_rr_kernel<7>; break;
+        case 8: kern = pathwise_rr_kernel<8>; break;
+        case 9: kern = pathwise_rr_kernel<9>; break;
+        case 10: kern = pathwise_rr_kernel<10>; break;
+        default: kern = pathwise_rr_kernel<11>; break;
+      }
+      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)) != cudaSuccess) return e;
+      kern<<<d.num_problems * a.D * a.nchunk, 256, smem_r, s>>>(a, meta);
+      gp_prepare_update_kernel<<<d.num_problems * a.D * a.nchunk, 128, 0, s>>>(a, p, Lc, Sfull, kl_l, kvec, Linv, meta);
+      h->launches += 2;
     } else if (h->allow_dmma_path && A <= 192) {
       const int PT = A <= 96 ? 3 : 6, ROWS = 32 * PT;
       const size_t main_view = (size_t)2 * ROWS * kDBP + 3 * kDB * kWS + 3 * 4 * kDB + 3 * kDB + 8 * kDB * 2 + 2 * (2 * kDB * 2);
       const size_t tail_view = (size_t)2 * kST * ROWS + 32 * LDM + (size_t)Nq * Mp + kST * 32 + 64;
       size_t smem_m = sizeof(double) * std::max(main_view, tail_view);
-      if (const char* pad = std::getenv("VGPMP_DMMA_PAD_KB")) smem_m += (size_t)std::atoi(pad) * 1024;   // occupancy experiments
       if (smem_m > 227 * 1024) return cudaErrorInvalidValue;
       void (*kern)(PathwiseArgs, const double*) = PT == 3 ? pathwise_dmma_kernel<3> : pathwise_dmma_kernel<6>;
       if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m)) != cudaSuccess)
