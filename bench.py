@@ -306,7 +306,7 @@ def run_b200(args):
         if pw:
             peak64 = float(eng.lib.vgpmp_probe_fp64_tflops(local))
             ach = pw_flops / (pw["ms_per_launch"] * 1e-3) / 1e12
-            out_dom = {"kernel": "gp_prepare_kernel + pathwise_dmma_kernel<3> (rotation-recurrence Fourier features, DMMA m8n8k4 contraction, pathwise update)",
+            out_dom = {"kernel": "pathwise_rr_kernel<9> + gp_prepare_update_kernel (register-resident rotation chains feeding DMMA m8n8k4, then GP preparation + pathwise update)",
                        "bound": "fp64", "achieved": ach, "peak": peak64, "unit": "TFLOP/s", "frac": ach / peak64 if peak64 > 0 else None,
                        "peak_source": "measured now: vgpmp_probe_fp64_tflops (DFMA chains, CUDA events)", "traffic": None,
                        "algorithmic_flops_per_launch": pw_flops, "ms_per_launch": pw["ms_per_launch"], "share_of_step": pw["share"]}

@@ -16,7 +16,8 @@ for r in rows:
     try:
         smp=int(r[ix['# Samples']]); ins=int(r[ix['Instructions Executed']])
     except: continue
-    if r[0].strip().isdigit(): last=(cur_file,int(r[0])); agg[last][3]=r[1]
+    if not r[0].strip().isdigit(): continue      # SASS rows repeat what their source row already aggregates
+    last=(cur_file,int(r[0])); agg[last][3]=r[1]
     key=last
     a=agg[key]; a[0]+=smp; a[1]+=ins
     for h in ('stall_barrier','stall_long_sb','stall_short_sb','stall_wait','stall_math','stall_mio','stall_lg','stall_branch_resolving','stall_no_inst'):
