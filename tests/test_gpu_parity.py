@@ -1,6 +1,8 @@
 """GPU parity tests: every stage kernel and the fused iteration, through the C-ABI, against the float64 oracle on
 identical seeded inputs, plus the reference-derived golden fixtures.  Tolerances are BASELINE.json's north_star:
 FK poses / SDF values 1e-5 rel, ELBO 1e-4 rel, gradients 1e-3 rel (the float64 kernels land far inside them)."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 import torch
@@ -525,3 +527,12 @@ def test_errors_are_reported_not_swallowed():
     eng = model._eng
     with pytest.raises(_cabi.VgpmpError, match="num_inducing"):
         eng.gp_prepare(eng.dims(1, 31, 5, 2, 8), model._params(None))
+
+
+def test_device_rng_key_layout_is_pinned():
+    """The Philox key layout (seed, iteration, problem, latent, sample, basis) is part of the reproducibility contract:
+    SHA-256 of the draws for a few shapes / offsets against tests/golden/rng_sha256.json (tools/rng_checksum.py)."""
+    import json
+    from tools import rng_checksum
+    want = json.loads((Path(__file__).parent / "golden" / "rng_sha256.json").read_text())
+    assert rng_checksum.checksums() == want

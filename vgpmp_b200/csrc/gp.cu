@@ -1764,16 +1764,20 @@ struct RngArgs {
   double *omega, *tau, *w, *eps_u, *eps_j;
 };
 
-__global__ void __launch_bounds__(256) rng_fill_kernel(RngArgs a) {
-  const size_t B4 = (a.B + 3) / 4, M2 = (a.Mp + 1) / 2;
-  const size_t n_om = (size_t)a.Bp * a.D * a.B;            // one thread per basis row (gamma shared by the row)
-  const size_t n_w = (size_t)a.Bp * a.D * a.S * B4;        // one thread per 4 consecutive bases
-  const size_t n_e = (size_t)a.Bp * a.D * a.S * M2;        // one thread per 2 consecutive inducing rows (eps_u, eps_j)
-  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid < n_om) {
+// Blocks are grouped per (problem, latent) pair: `bpp` blocks of 256 threads walk the pair's B basis rows, then its
+// S*ceil(B/4) weight quads, then its S*ceil(Mp/2) eps pairs.  All index arithmetic is 32-bit (the flat 64-bit div/mod
+// of the first version was half of the kernel's instructions); the Philox keys are unchanged.
+__global__ void __launch_bounds__(256) rng_fill_kernel(RngArgs a, uint32_t bpp) {
+  const uint32_t B = a.B, S = a.S, D = a.D, Mp = a.Mp, B4 = (B + 3) / 4, M2 = (Mp + 1) / 2;
+  const uint32_t pair = blockIdx.x / bpp;                       // local (problem, latent)
+  uint32_t t = (blockIdx.x - pair * bpp) * 256u + threadIdx.x;   // index inside the pair
+  const uint32_t pl_ = pair / D, l = pair - pl_ * D;
+  const uint64_t p = (uint64_t)pl_ + (uint64_t)a.problem_offset;
+  if (t < B) {
     if (a.omega == nullptr) return;
-    const size_t b = gid % a.B, l = (gid / a.B) % a.D, p = gid / ((size_t)a.B * a.D) + a.problem_offset;
-    const uint64_t key = (p * a.D + l) * a.B + b;
+    const uint32_t b = t;
+    const uint64_t key = (p * D + l) * B + b;
+    const size_t gid = (size_t)pair * B + b;
     // Gamma(5/2, rate 5/2) = chi^2_5 / 5  -> omega = z / sqrt(gamma): Matern-5/2 spectral density (Student-t_5)
     double z[16];
     const int ncall = (5 + a.D + 3) / 4;                    // <= 4 for D <= 8
@@ -1790,36 +1794,36 @@ __global__ void __launch_bounds__(256) rng_fill_kernel(RngArgs a) {
     a.tau[gid] = 6.283185307179586476925 * u01(c[0], c[1]);
     return;
   }
-  size_t e = gid - n_om;
-  if (e < n_w) {
+  t -= B;
+  if (t < S * B4) {
     if (a.w == nullptr) return;
-    const size_t b4 = e % B4, sl = (e / B4) % a.S, l = (e / (B4 * a.S)) % a.D, pl_ = e / (B4 * a.S * a.D);
-    const size_t s = sl + a.sample_offset, p = pl_ + a.problem_offset;
-    const uint64_t key = ((p * a.D + l) * (uint64_t)(1u << 24) + s) * B4 + b4;  // sample index < 2^24
+    const uint32_t sl = t / B4, b4 = t - sl * B4;
+    const uint64_t s = (uint64_t)sl + (uint64_t)a.sample_offset;
+    const uint64_t key = ((p * D + l) * (uint64_t)(1u << 24) + s) * B4 + b4;  // sample index < 2^24
     double z[4];
     normal4(a.seed, a.iteration, 4u, key, z);
-    double* dst = a.w + ((pl_ * a.D + l) * a.S + sl) * a.B + b4 * 4;
-    if (b4 * 4 + 4 <= (size_t)a.B && (a.B & 1) == 0) {
+    double* dst = a.w + ((size_t)pair * S + sl) * B + (size_t)b4 * 4;
+    if (b4 * 4 + 4 <= B && (B & 1) == 0) {
       reinterpret_cast<double2*>(dst)[0] = make_double2(z[0], z[1]);
       reinterpret_cast<double2*>(dst)[1] = make_double2(z[2], z[3]);
     } else {
-      for (int k = 0; k < 4; ++k)
-        if (b4 * 4 + k < (size_t)a.B) dst[k] = z[k];
+      for (uint32_t k = 0; k < 4; ++k)
+        if (b4 * 4 + k < B) dst[k] = z[k];
     }
     return;
   }
-  e -= n_w;
-  if (e < n_e) {
+  t -= S * B4;
+  if (t < S * M2) {
     if (a.eps_u == nullptr) return;
-    const size_t m2 = e % M2, sl = (e / M2) % a.S, l = (e / (M2 * a.S)) % a.D, pl_ = e / (M2 * a.S * a.D);
-    const size_t s = sl + a.sample_offset, p = pl_ + a.problem_offset;
-    const uint64_t key = ((p * a.D + l) * (uint64_t)(1u << 24) + s) * 16 + m2;
+    const uint32_t sl = t / M2, m2 = t - sl * M2;
+    const uint64_t s = (uint64_t)sl + (uint64_t)a.sample_offset;
+    const uint64_t key = ((p * D + l) * (uint64_t)(1u << 24) + s) * 16 + m2;
     double z[4];
     normal4(a.seed, a.iteration, 5u, key, z);
-    const size_t o = ((pl_ * a.D + l) * a.S + sl) * a.Mp + m2 * 2;
+    const size_t o = ((size_t)pair * S + sl) * Mp + (size_t)m2 * 2;
     a.eps_u[o] = z[0];
     a.eps_j[o] = z[2];
-    if (m2 * 2 + 1 < (size_t)a.Mp) { a.eps_u[o + 1] = z[1]; a.eps_j[o + 1] = z[3]; }
+    if (m2 * 2 + 1 < Mp) { a.eps_u[o + 1] = z[1]; a.eps_j[o + 1] = z[3]; }
   }
 }
 
@@ -2065,10 +2069,10 @@ cudaError_t launch_rng_fill(vgpmp_handle* h, const vgpmp_dims& d, uint64_t seed,
   a.D = h->robot.dof; a.B = d.num_bases; a.S = d.num_samples; a.Mp = d.num_inducing + 2; a.Bp = d.num_problems;
   a.problem_offset = problem_offset; a.sample_offset = sample_offset; a.seed = seed; a.iteration = iteration;
   a.omega = omega; a.tau = tau; a.w = w; a.eps_u = eps_u; a.eps_j = eps_j;
-  const size_t n_om = (size_t)a.Bp * a.D * a.B, n_w = (size_t)a.Bp * a.D * a.S * ((a.B + 3) / 4),
-               n_e = (size_t)a.Bp * a.D * a.S * ((a.Mp + 1) / 2);
-  const size_t total = n_om + n_w + n_e;
-  rng_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a);
+  const size_t per_pair = (size_t)a.B + (size_t)a.S * ((a.B + 3) / 4) + (size_t)a.S * ((a.Mp + 1) / 2);
+  const size_t bpp = (per_pair + 255) / 256, blocks = bpp * (size_t)a.Bp * a.D;
+  if (per_pair >= (1ull << 32) || blocks >= (1ull << 31)) return cudaErrorInvalidValue;
+  rng_fill_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, (uint32_t)bpp);
   h->launches++;
   return cudaGetLastError();
 }
