@@ -1362,20 +1362,23 @@ constexpr int kPartial = 2 * 32 * 32 + 32 + 4;   // doubles per (problem, latent
 // is split over CTAs: MODE 1 = sample phase of one chunk -> partial sums in global memory; MODE 2 = fold the partials in
 // fixed order (deterministic) and run the sample-independent phase.
 template <int MODE>
-__global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
+__global__ void __launch_bounds__(256, 4) gp_backward_kernel(BackwardArgs a) {
   extern __shared__ double sm[];
   const int D = a.D, M = a.M, Mp = M + 2, N = a.N, S = a.S, A = N + Mp;
   const int pl = MODE == 1 ? blockIdx.x / a.nchunk : blockIdx.x, p = pl / D, l = pl % D;
   const int s_begin = MODE == 1 ? (blockIdx.x % a.nchunk) * a.chunk : 0;
   const int s_end = MODE == 1 ? min(S, s_begin + a.chunk) : (MODE == 2 ? 0 : S);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
-  double* Lsm = sm;                    // [32][LDM] chol factor L
-  double* Lism = Lsm + 32 * LDM;       // [32][LDM] explicit inverse L^-1
+  // Kfu is only live inside the sample loop, L and d ELBO / d Lc only after it: they share one region (one matrix
+  // less resident -> 4 CTAs per SM instead of 3, i.e. 4 waves of the 13 CTAs per SM instead of 5).
+  const size_t kreg = (size_t)N * Mp > (size_t)2 * 32 * LDM ? (size_t)N * Mp : (size_t)2 * 32 * LDM;
+  double* Lism = sm;                   // [32][LDM] explicit inverse L^-1
   double* G = Lism + 32 * LDM;         // [32][LDM] d ELBO / d Khat (general, not symmetrised)
   double* GS = G + 32 * LDM;           // [32][LDM] d ELBO / d q_sqrt_full
-  double* GL = GS + 32 * LDM;          // [32][LDM] d ELBO / d Lc
-  double* Kfu = GL + 32 * LDM;         // [N][32]
-  double* gv = Kfu + (size_t)N * 32;   // [kBT][32]
+  double* Lsm = GS + 32 * LDM;         // [32][LDM] chol factor L            (after the sample loop)
+  double* GL = Lsm + 32 * LDM;         // [32][LDM] d ELBO / d Lc            (after the sample loop)
+  double* Kfu = Lsm;                   // [N][Mp]                            (inside the sample loop)
+  double* gv = Lsm + kreg;             // [kBT][32]
   double* gr = gv + kBT * 32;          // [kBT][32]
   double* vsm = gr + kBT * 32;         // [kBT][32]
   double* epsm = vsm + kBT * 32;       // [kBT][32] this tile's eps_u
@@ -1392,15 +1395,13 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
     bvec[tid] = tid < Mp ? a.kvec[(size_t)pl * (Mp + 4) + tid] : 0.0;
     gmu[tid] = 0.0;
   }
-  for (int idx = tid; idx < 32 * LDM; idx += nt) { G[idx] = 0.0; GS[idx] = 0.0; GL[idx] = 0.0; Lsm[idx] = 0.0; Lism[idx] = 0.0; }
+  for (int idx = tid; idx < 32 * LDM; idx += nt) { G[idx] = 0.0; GS[idx] = 0.0; Lism[idx] = 0.0; }
   __syncthreads();
   for (int i = warp; i < Mp; i += nw)
-    if (lane < Mp) {
-      Lsm[i * LDM + lane] = a.Lc[(size_t)pl * Mp * Mp + i * Mp + lane];
-      Lism[i * LDM + lane] = a.Linv[(size_t)pl * Mp * Mp + i * Mp + lane];
-    }
-  for (int n = warp; n < N; n += nw)
-    Kfu[n * 32 + lane] = lane < Mp ? s2 * vg_matern52(fabs(a.X[(size_t)n * D + l] - zy[lane]) * inv_ell) : 0.0;
+    if (lane < Mp) Lism[i * LDM + lane] = a.Linv[(size_t)pl * Mp * Mp + i * Mp + lane];
+  if (s_begin < s_end)
+    for (int n = warp; n < N; n += nw)
+      if (lane < Mp) Kfu[n * Mp + lane] = s2 * vg_matern52(fabs(a.X[(size_t)n * D + l] - zy[lane]) * inv_ell);
   __syncthreads();
 
   double acc_ls = 0.0, acc_var = 0.0;  // per-thread partial hyper-parameter gradients
@@ -1426,7 +1427,7 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
       double t = 0.0;
       if (i < ns && m < Mp) {
         const double* dfs = dft + (size_t)i * N;
-        for (int n = 0; n < N; ++n) t += Kfu[n * 32 + m] * dfs[n];
+        for (int n = 0; n < N; ++n) t += Kfu[n * Mp + m] * dfs[n];
       }
       gv[idx] = t;
     }
@@ -1518,6 +1519,13 @@ __global__ void __launch_bounds__(256) gp_backward_kernel(BackwardArgs a) {
     __syncthreads();
   }
 
+  // the sample loop is over: its Kfu region becomes L | d ELBO / d Lc
+  __syncthreads();
+  for (int idx = tid; idx < 2 * 32 * LDM; idx += nt) Lsm[idx] = 0.0;
+  __syncthreads();
+  for (int i = warp; i < Mp; i += nw)
+    if (lane < Mp) Lsm[i * LDM + lane] = a.Lc[(size_t)pl * Mp * Mp + i * Mp + lane];
+  __syncthreads();
   // (7) q_sqrt_full = Lc pad(q) + jitter diag  ->  d q = tril((Lc^T GS)[2:,2:]),  GL += GS pad(q)^T
   const double* q = a.q_sqrt + (size_t)pl * M * M;
   double* dq = a.d_q_sqrt + (size_t)pl * M * M;
@@ -2013,7 +2021,8 @@ cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp
   a.Lc = ws.Lc; a.Linv = ws.Linv; a.kvec = ws.kvec; a.v = ws.v; a.f0 = ws.f0; a.h0 = ws.h0; a.df = ws.df;
   a.d_q_mu = g.d_q_mu; a.d_q_sqrt = g.d_q_sqrt; a.d_ls = g.d_lengthscales; a.d_var = g.d_variances;
   const int Mp = a.M + 2;
-  const size_t smem = sizeof(double) * (5 * 32 * LDM + (size_t)a.N * 32 + 4 * kBT * 32 + 4 * 32 + 16 + (size_t)kBT * a.N);
+  const size_t kreg = std::max((size_t)a.N * Mp, (size_t)2 * 32 * LDM);   // Kfu inside the sample loop, L | GL after it
+  const size_t smem = sizeof(double) * (3 * 32 * LDM + kreg + 4 * kBT * 32 + 4 * 32 + 16 + (size_t)kBT * a.N);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   const int pairs = d.num_problems * a.D;
   backward_chunks(h->num_sms, pairs, a.S, &a.nchunk, &a.chunk);
