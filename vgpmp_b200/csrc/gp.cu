@@ -49,12 +49,16 @@ __device__ void chol_inplace(double* A, int Mp) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   for (int k = 0; k < Mp; ++k) {
     __syncthreads();
-    const double piv = sqrt(A[k * LDM + k]);
-    const double inv = 1.0 / piv;
+    // pivot: 1/sqrt by the hardware seed + Newton, sqrt from it with one correction step (residual in FMA): the sqrt /
+    // divide pair of the first version was half of this routine's instructions, and every thread runs it
+    const double akk = A[k * LDM + k];
+    double inv = rsqrt(akk);
+    double piv = akk * inv;
+    piv = fma(0.5 * inv, fma(-piv, piv, akk), piv);        // piv += (a - piv^2) / (2 piv)
+    inv = fma(inv, fma(-piv, inv, 1.0), inv);              // inv += inv (1 - piv inv)
+    if (tid > k && tid < Mp) A[tid * LDM + k] *= inv;      // own element only: no hazard with the a_kk reads
     __syncthreads();
-    if (tid == 0) A[k * LDM + k] = piv;
-    if (tid > k && tid < Mp) A[tid * LDM + k] *= inv;
-    __syncthreads();
+    if (tid == 0) A[k * LDM + k] = piv;                    // nobody reads a_kk any more; the update touches j > k
     const int j = k + 1 + lane;
     for (int i = k + 1 + warp; i < Mp; i += nw)
       if (j <= i) A[i * LDM + j] -= A[i * LDM + k] * A[j * LDM + k];
@@ -139,7 +143,7 @@ __global__ void kuf_kernel(int D, int M, int N, const double* __restrict__ Z, co
 // ---------------------------------------------------------------------------------------------
 // Kuu + chol + q_sqrt un-whitening + KL, one CTA (128 threads) per (problem, latent)
 // ---------------------------------------------------------------------------------------------
-constexpr int kPrepSmem = 4 * 32 * LDM + 2 * 32 + 32;   // doubles of shared memory gp_prepare_body needs: K | L | q | L^-1 | zy | mu | scratch
+constexpr int kPrepSmem = 3 * 32 * LDM + 2 * 32 + 64;   // doubles of shared memory gp_prepare_body needs: K (later q, then q_sqrt_full) | L | L^-1 | zy | mu | scratch
 
 // Body of the GP preparation for one (problem, latent), working on a caller-provided shared-memory block.
 // `smem` must hold kPrepSmem doubles; needs blockDim.x >= 32 and a multiple of 32.
@@ -148,14 +152,14 @@ __device__ void gp_prepare_body(int D, int M, double jitter, const vgpmp_params&
                                 double* __restrict__ Linv_out, double* smem, double* Ssm = nullptr) {
   // Ssm (optional, [32][LDM] in shared memory, may alias smem = the K block): a copy of q_sqrt_full for a caller that
   // continues with the pathwise update in the same CTA; the explicit inverse factor then stays in smem + 3*32*LDM.
-  double* Ksm = smem;
+  double* Ksm = smem;              // K until the KL term is done, then pad(q), then q_sqrt_full
   double* Lsm = Ksm + 32 * LDM;
-  double* qsm = Lsm + 32 * LDM;
-  double* Li = qsm + 32 * LDM;
+  double* Li = Lsm + 32 * LDM;
+  double* qsm = Ksm;
   double* zy = Li + 32 * LDM;
   double* mu = zy + 32;
-  double* red = mu + 32;
-  double* cvec = red + 8;
+  double* red = mu + 32;           // [8] block_sum scratch, then [32] reciprocal diagonal of L
+  double* cvec = red + 8 + 32;
   const int p = pl / D, l = pl % D, Mp = M + 2, tid = threadIdx.x;
   const double ell = P.lengthscales[pl], s2 = P.variances[pl];
   if (tid < Mp) {
@@ -165,7 +169,7 @@ __device__ void gp_prepare_body(int D, int M, double jitter, const vgpmp_params&
   __syncthreads();
   const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const double* q = P.q_sqrt + (size_t)pl * M * M;
-  for (int idx = tid; idx < 32 * LDM; idx += blockDim.x) { Lsm[idx] = 0.0; qsm[idx] = 0.0; }
+  for (int idx = tid; idx < 32 * LDM; idx += blockDim.x) Lsm[idx] = 0.0;
   __syncthreads();
   for (int i = warp; i < Mp; i += nw) {
     if (lane < Mp) {
@@ -173,7 +177,6 @@ __device__ void gp_prepare_body(int D, int M, double jitter, const vgpmp_params&
       Ksm[i * LDM + lane] = k;
       Lsm[i * LDM + lane] = k;
     }
-    if (i < M && lane < M) qsm[i * LDM + lane] = q[i * M + lane];
   }
   chol_inplace(Lsm, Mp);
   if (Lc_out != nullptr)
@@ -182,6 +185,11 @@ __device__ void gp_prepare_body(int D, int M, double jitter, const vgpmp_params&
   // explicit inverse factor: thread j holds column j of L^-1 in registers,
   //   x_i = (delta_ij - sum_{k<i} L[i][k] x_k) / L[i][i]   (x_k = 0 for k < j; L is zero-padded beyond Mp)
   if (Linv_out != nullptr || Ssm != nullptr) {
+    if (tid >= 32 && tid < 64) {                          // reciprocal diagonal, off the critical path of warp 0
+      const int i = tid - 32;
+      red[8 + i] = i < Mp ? 1.0 / Lsm[i * LDM + i] : 0.0;  // (red has 8 + 32 doubles of scratch behind it: cvec starts later)
+    }
+    __syncthreads();
     if (tid < 32) {
       const int j = tid;
       double x[32];
@@ -190,7 +198,7 @@ __device__ void gp_prepare_body(int D, int M, double jitter, const vgpmp_params&
         double acc = (i == j) ? 1.0 : 0.0;
 #pragma unroll
         for (int k = 0; k < i; ++k) acc -= Lsm[i * LDM + k] * x[k];
-        x[i] = (i < Mp && i >= j && j < Mp) ? acc / Lsm[i * LDM + i] : 0.0;
+        x[i] = (i < Mp && i >= j && j < Mp) ? acc * red[8 + i] : 0.0;
         Li[i * LDM + j] = x[i];
       }
     }
@@ -222,26 +230,38 @@ __device__ void gp_prepare_body(int D, int M, double jitter, const vgpmp_params&
   // gauss_kl(white): 0.5 * (maha - M - sum log diag(q)^2 + sum q^2)
   for (int a_ = warp; a_ < M; a_ += nw) {
     if (lane <= a_) {
-      const double v = qsm[a_ * LDM + lane];
+      const double v = q[a_ * M + lane];
       part += v * v;
       if (lane == a_) part -= log(v * v);
     }
   }
-  const double tot = block_sum(part, red);
+  const double tot = block_sum(part, red);   // (its barriers also retire the last readers of K)
   if (tid == 0 && kl_l != nullptr) kl_l[pl] = 0.5 * (tot - (double)M);
   // q_sqrt property: Lc @ pad(_q_sqrt) + jitter * diag(1,1,0,...)   models/vgpmp.py:208-218
-  // (last: K is dead by now, so a caller may pass Ssm == smem and have q_sqrt_full overwrite it)
-  __syncthreads();
+  // K is dead: its block takes q, and then (through registers) q_sqrt_full itself when the caller passes Ssm == smem
   if (S_out != nullptr || Ssm != nullptr) {
-    for (int i = warp; i < Mp; i += nw) {
-      const int j = lane;
-      if (j < Mp) {
-        double acc = 0.0;
+    for (int i = warp; i < M; i += nw)
+      if (lane < M) qsm[i * LDM + lane] = lane <= i ? q[i * M + lane] : 0.0;
+    __syncthreads();
+    double sreg[8];                    // rows warp, warp + nw, ... (nw >= 4 -> at most 8 rows of 32)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int i = warp + r * nw, j = lane;
+      double acc = 0.0;
+      if (i < Mp && j < Mp) {
         if (i >= 2 && j >= 2 && j <= i)
           for (int k = j; k <= i; ++k) acc += Lsm[i * LDM + k] * qsm[(k - 2) * LDM + (j - 2)];
         if (i == j && i < 2) acc += jitter;
-        if (S_out != nullptr) S_out[(size_t)pl * Mp * Mp + i * Mp + j] = acc;
-        if (Ssm != nullptr) Ssm[i * LDM + j] = acc;
+      }
+      sreg[r] = acc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int i = warp + r * nw, j = lane;
+      if (i < Mp && j < Mp) {
+        if (S_out != nullptr) S_out[(size_t)pl * Mp * Mp + i * Mp + j] = sreg[r];
+        if (Ssm != nullptr) Ssm[i * LDM + j] = sreg[r];
       }
     }
   }
@@ -1115,11 +1135,11 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
 //   u = mu + S eps_u;  r = u - f0(Zy) - sqrt(jitter) eps_j;  v = L^-T L^-1 r;  f = f0(X) + Kfu v.
 // Small CTAs, latency hidden by occupancy - the job the 256-thread sampler CTAs did badly in their tails.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 6) gp_prepare_update_kernel(PathwiseArgs a, vgpmp_params P, double* __restrict__ Lc_out,
+__global__ void __launch_bounds__(128, 7) gp_prepare_update_kernel(PathwiseArgs a, vgpmp_params P, double* __restrict__ Lc_out,
                                                                   double* __restrict__ S_out, double* __restrict__ kl_l,
                                                                   double* __restrict__ kvec, double* __restrict__ Linv_out,
                                                                   const double* __restrict__ meta) {
-  __shared__ __align__(16) double prep[kPrepSmem];    // gp_prepare_body's block: K -> q_sqrt_full | L | q | L^-1 | zy | mu | ...
+  __shared__ __align__(16) double prep[kPrepSmem];    // gp_prepare_body's block: K -> q -> q_sqrt_full | L | L^-1 | zy | mu | ...
   __shared__ double vsm[kST * 32];                    // v of one tile of samples
   const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, A = Nq + Mp;
   const int pl = blockIdx.x / a.nchunk, chunk = blockIdx.x % a.nchunk, p = pl / D, l = pl % D;
@@ -1129,8 +1149,8 @@ __global__ void __launch_bounds__(128, 6) gp_prepare_update_kernel(PathwiseArgs 
                   first ? kvec : nullptr, first ? Linv_out : nullptr, prep, prep);
   if (meta[0] == 0.0) return;                         // general sampler runs after this kernel and does its own update
   const double* Ssm = prep;
-  const double* Lism = prep + 3 * 32 * LDM;
-  const double* zy = prep + 4 * 32 * LDM;
+  const double* Lism = prep + 2 * 32 * LDM;
+  const double* zy = prep + 3 * 32 * LDM;
   const double* mu = zy + 32;
   const double ell = a.ls[pl], s2 = a.var[pl], sqrtj = sqrt(a.jitter);
   const int s_begin = chunk * a.chunk, s_end = min(S, s_begin + a.chunk);
