@@ -23,7 +23,7 @@ __device__ __forceinline__ void dmma16816(double* c, const double* a, const doub
 }
 
 // MODE 0: DFMA only (NF independent chains)   1: m8n8k4 only (NM independent accumulators)   2: both interleaved
-// MODE 3: m16n8k8    4: m16n8k16   5: m16n8k8 + DFMA
+// MODE 3: m16n8k8    4: m16n8k16   5: m16n8k8 + DFMA   6: DMMA and DFMA alternating instruction by instruction
 template <int MODE, int NF, int NM>
 __global__ void __launch_bounds__(256) probe(double* out, int iters, double seed) {
   double f[NF > 0 ? NF : 1];
@@ -54,6 +54,14 @@ __global__ void __launch_bounds__(256) probe(double* out, int iters, double seed
     if (MODE == 4) {
 #pragma unroll
       for (int i = 0; i < NM; ++i) dmma16816(c[i], av, bv);
+    }
+    if (MODE == 6) {   // fine-grained alternation: NF/NM vector ops after every DMMA (the register-resident sampler's pattern)
+#pragma unroll
+      for (int i = 0; i < NM; ++i) {
+        dmma884(c[i][0], c[i][1], a, b);
+#pragma unroll
+        for (int k = 0; k < NF / NM; ++k) f[i * (NF / NM) + k] = fma(f[i * (NF / NM) + k], a, b);
+      }
     }
   }
   double s = 0.0;
@@ -103,6 +111,11 @@ int main() {
   run<1, 0, 2>("dmma m8n8k4 x2", 0, 2 * 256.0, 1);
   run<1, 0, 3>("dmma m8n8k4 x3", 0, 3 * 256.0, 1);
   run<1, 0, 4>("dmma m8n8k4 x4", 0, 4 * 256.0, 1);
+  printf("-- alternation granularity, 2 CTAs/SM: same instruction counts, grouped vs interleaved\n");
+  run<2, 16, 8>("grouped: dfma x16, then dmma x8", 16, 8 * 256.0, 2);
+  run<6, 16, 8>("interleaved: (dmma, dfma, dfma) x8", 16, 8 * 256.0, 2);
+  run<2, 8, 8>("grouped: dfma x8, then dmma x8", 8, 8 * 256.0, 2);
+  run<6, 8, 8>("interleaved: (dmma, dfma) x8", 8, 8 * 256.0, 2);
   for (int c = 1; c <= 4; c *= 2) {
     run<0, 8, 0>("dfma x8", 8, 0, c);
     run<1, 0, 8>("dmma m8n8k4 x8", 0, 8 * 256.0, c);

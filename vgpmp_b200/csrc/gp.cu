@@ -901,7 +901,7 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
 //              into a 4-slot ring handed over with named barriers.
 // ---------------------------------------------------------------------------------------------
 constexpr int kRB = 32;        // bases per table slot
-constexpr int kRE = 42;        // doubles per basis in a slot: Sx[8] | E8x | Sz[8] | E8z | e0 | e1 | c | pad
+constexpr int kRE = 50;        // doubles per basis in a slot: Sx[8] | E8x | Sz[8] | E8z | e0 | e1 | c/l | pad | w[8 samples]
 constexpr int kRS = 4;         // ring slots
 constexpr int kRC = 6;         // consumer warps
 constexpr int kRT = 12;        // point tiles (rows / 8) a consumer carries
@@ -922,34 +922,41 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
   } while (!ok);
 }
 
-// branch-free double sincos for |x| < 2^20 (the caller checks and falls back): three-term Cody-Waite reduction by pi/2,
-// Taylor kernels on [-pi/4, pi/4] truncated below 1e-17.  Straight-line code, so several calls interleave.
-__device__ __forceinline__ void sincos_bf(double x, double* sn, double* cs) {
-  const double n = rint(x * 0.63661977236758134308);
-  const int q = __double2int_rn(n);
-  double r = fma(-n, 1.5707963267948966, x);
-  r = fma(-n, 6.123233995736766e-17, r);
-  const double z = r * r;
-  double ps = 1.0 / 1307674368000.0;
-  ps = fma(ps, -z, 1.0 / 6227020800.0);
-  ps = fma(ps, -z, 1.0 / 39916800.0);
-  ps = fma(ps, -z, 1.0 / 362880.0);
-  ps = fma(ps, -z, 1.0 / 5040.0);
-  ps = fma(ps, -z, 1.0 / 120.0);
-  ps = fma(ps, -z, 1.0 / 6.0);
-  const double s = fma(-z * r, ps, r);
-  double pc = 1.0 / 20922789888000.0;
-  pc = fma(pc, -z, 1.0 / 87178291200.0);
-  pc = fma(pc, -z, 1.0 / 479001600.0);
-  pc = fma(pc, -z, 1.0 / 3628800.0);
-  pc = fma(pc, -z, 1.0 / 40320.0);
-  pc = fma(pc, -z, 1.0 / 720.0);
-  pc = fma(pc, -z, 1.0 / 24.0);
-  pc = fma(pc, -z, 0.5);
-  const double c = fma(-z, pc, 1.0);
-  const double a = (q & 1) ? c : s, b = (q & 1) ? s : c;
-  *sn = (q & 2) ? -a : a;
-  *cs = ((q + 1) & 2) ? -b : b;
+// Six branch-free double sincos evaluated in lock-step (|x| < 2^20, the caller checks and falls back): three-term
+// Cody-Waite reduction by pi/2, Taylor kernels on [-pi/4, pi/4] truncated below 1e-17.  Written as loops over the six
+// arguments so every Horner step issues six independent FMAs: a lone producer warp otherwise crawls through six
+// back-to-back dependency chains at one instruction per FP64 latency (measured: the producers, not the DMMAs, set the
+// kernel time before this).
+__device__ __forceinline__ void sincos_bf6(const double (&x)[6], double (&sn)[6], double (&cs)[6]) {
+  double r[6], z[6], ps[6], pc[6];
+  int q[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double n = rint(x[k] * 0.63661977236758134308);
+    q[k] = __double2int_rn(n);
+    r[k] = fma(-n, 6.123233995736766e-17, fma(-n, 1.5707963267948966, x[k]));
+    z[k] = r[k] * r[k];
+    ps[k] = 1.0 / 1307674368000.0;
+    pc[k] = 1.0 / 20922789888000.0;
+  }
+  const double S[6] = {1.0 / 6227020800.0, 1.0 / 39916800.0, 1.0 / 362880.0, 1.0 / 5040.0, 1.0 / 120.0, 1.0 / 6.0};
+  const double C[7] = {1.0 / 87178291200.0, 1.0 / 479001600.0, 1.0 / 3628800.0, 1.0 / 40320.0, 1.0 / 720.0, 1.0 / 24.0, 0.5};
+#pragma unroll
+  for (int t = 0; t < 6; ++t)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      ps[k] = fma(ps[k], -z[k], S[t]);
+      pc[k] = fma(pc[k], -z[k], C[t]);
+    }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    pc[k] = fma(pc[k], -z[k], C[6]);
+    const double s = fma(-z[k] * r[k], ps[k], r[k]);
+    const double c = fma(-z[k], pc[k], 1.0);
+    const double a = (q[k] & 1) ? c : s, b = (q[k] & 1) ? s : c;
+    sn[k] = (q[k] & 2) ? -a : a;
+    cs[k] = ((q[k] + 1) & 2) ? -b : b;
+  }
 }
 
 template <int JX>   // JX = tiles of 8 rows holding the query grid and the two conditioned endpoints; inducing rows follow
@@ -986,34 +993,52 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
     if (warp >= kRC) {
       // ---------------- producer: slots n = pw, pw + 2, ... ----------------
       const int pw = warp - kRC;
-      double c = 0.0, tau = 0.0;
-      auto fetch = [&](int n) {                 // operands of slot n, one slot ahead of their use
+      // operands of slot n are loaded one slot ahead of their use; `ld.volatile`-style asm pins the loads where they
+      // are written (the compiler otherwise sinks them next to their first use and the warp eats the DRAM latency)
+      double ov[VGPMP_MAX_DOF], wv[kST], tau = 0.0;
+      auto fetch = [&](int n) {
         const int b = n * kRB + lane;
-        c = 0.0; tau = 0.0;
-        if (n < T && b < B) {
-          for (int d = 0; d < D; ++d) c += om[(size_t)b * D + d];
-          tau = ta[b];
+        const bool ok = n < T && b < B;
+#pragma unroll
+        for (int d = 0; d < VGPMP_MAX_DOF; ++d) {
+          ov[d] = 0.0;
+          if (ok && d < D) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(ov[d]) : "l"(om + (size_t)b * D + d));
+        }
+        tau = 0.0;
+        if (ok) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(tau) : "l"(ta + b));
+        // this basis' weights of the sample tile: 32 consecutive bases per row = one coalesced 256-byte request per sample
+        // (the consumers used to gather them 8 sectors at a time, one step ahead, and sat on the DRAM latency)
+#pragma unroll
+        for (int i = 0; i < kST; ++i) {
+          wv[i] = 0.0;
+          if (ok && i < ns) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(wv[i]) : "l"(wp + (size_t)(s0 + i) * B + b));
         }
       };
       fetch(pw);
       for (int n = pw; n < T; n += 2) {
         const int N = it * T + n, slot = N % kRS, use = N / kRS;
         const bool live = n * kRB + lane < B;
+        double c = 0.0;
+#pragma unroll
+        for (int d = 0; d < VGPMP_MAX_DOF; ++d) c += ov[d];
         const double cb = c * inv_ell, taub = tau;
+        double wcur[kST];
+#pragma unroll
+        for (int i = 0; i < kST; ++i) wcur[i] = wv[i];
         fetch(n + 2);
         const double ab = live ? amp : 0.0;
         const double ax0 = t0 * cb + taub, ax1 = dt * cb, az0 = z0 * cb + taub, az1 = dz * cb, ae1 = cb + taub;
-        double sx, cx, sdx, cdx, sz, cz, sdz, cdz, se0, ce0, se1, ce1;
+        const double arg[6] = {ax0, ax1, az0, az1, taub, ae1};
+        double sv[6], cv[6];
         const double big = fmax(fmax(fabs(ax0), fabs(ax1)), fmax(fmax(fabs(az0), fabs(az1)), fmax(fabs(taub), fabs(ae1))));
         if (big < 1048576.0) {
-          sincos_bf(ax0, &sx, &cx); sincos_bf(ax1, &sdx, &cdx);
-          sincos_bf(az0, &sz, &cz); sincos_bf(az1, &sdz, &cdz);
-          sincos_bf(taub, &se0, &ce0); sincos_bf(ae1, &se1, &ce1);
+          sincos_bf6(arg, sv, cv);
         } else {
-          sincos(ax0, &sx, &cx); sincos(ax1, &sdx, &cdx);
-          sincos(az0, &sz, &cz); sincos(az1, &sdz, &cdz);
-          sincos(taub, &se0, &ce0); sincos(ae1, &se1, &ce1);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) sincos(arg[k], &sv[k], &cv[k]);
         }
+        double sx = sv[0], cx = cv[0], sdx = sv[1], cdx = cv[1], sz = sv[2], cz = cv[2], sdz = sv[3], cdz = cv[3];
+        const double se0 = sv[4], ce0 = cv[4], se1 = sv[5], ce1 = cv[5];
         mbar_wait(empty + slot, (use & 1) ^ 1);            // consumers are done with the slot's previous contents
         double* e = tab + ((size_t)slot * kRB + lane) * kRE;
         double c1 = ab * cx, s1 = ab * sx, c2 = ab * cz, s2z = ab * sz;
@@ -1036,6 +1061,8 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
         *reinterpret_cast<double2*>(e + 36) = make_double2(ab * ce0, ab * se0);
         *reinterpret_cast<double2*>(e + 38) = make_double2(ab * ce1, ab * se1);
         *reinterpret_cast<double2*>(e + 40) = make_double2(cb * inv_ell, 0.0);
+#pragma unroll
+        for (int i = 0; i < kST; i += 2) *reinterpret_cast<double2*>(e + 42 + i) = make_double2(wcur[i], wcur[i + 1]);
         mbar_arrive(full + slot);                          // slot filled (release)
       }
     } else {
@@ -1045,11 +1072,6 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
       for (int j = 0; j < kRT; ++j) acc[j][0][0] = acc[j][0][1] = acc[j][1][0] = acc[j][1][1] = 0.0;
       const int Q = T * (kRB / 4);
       int cur = -1;                                         // slot number (within this sample tile) this warp holds
-      auto loadw = [&](int q) {
-        const int b = 4 * q + t4;
-        return (g < ns && b < B) ? __ldg(wp + (size_t)(s0 + g) * B + b) : 0.0;
-      };
-      double wnext = loadw(warp);
       // rows Nq and Nq+1 (the conditioned endpoints) live in tile JX-1, or JX-2 and JX-1; this lane's role there:
       const int xa = 8 * (JX - 2) + g, xb = 8 * (JX - 1) + g;       // its row index in those two tiles
       const int ea = xa - Nq, eb = xb - Nq;                        // < 0: chain value, 0 / 1: endpoint, > 1: padding
@@ -1061,9 +1083,8 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
           mbar_wait(full + N % kRS, (N / kRS) & 1);                     // this slot is filled (acquire)
           cur = n;
         }
-        const double wk = wnext;
-        if (q + kRC < Q) wnext = loadw(q + kRC);
         const double* e = tab + ((size_t)((it * T + n) % kRS) * kRB + (q % (kRB / 4)) * 4 + t4) * kRE;
+        const double wk = e[42 + g];                                        // w[sample g][basis], staged by the producer
         double2 ph = *reinterpret_cast<const double2*>(e + 2 * g);          // chain state: (cos, sin) of row g, amplitude in
         double2 st = *reinterpret_cast<const double2*>(e + 16);             // E^8 of the query grid
         const double wq = wk * e[40];                                       // w c / l for the d/dlengthscale contraction
