@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--option", action="append", default=[], metavar="NAME=INT",
                     help="experiments only: vgpmp_set_option(NAME, INT) before timing (e.g. mma_sampler=0)")
+    ap.add_argument("--bases", type=int, default=0, help="experiments only: number of random Fourier bases (default 1024)")
     ap.add_argument("--problems", type=int, default=0, help="experiments only: truncate / cycle the batch to this many problems")
     return ap.parse_args()
 
@@ -201,8 +202,9 @@ def run_b200(args):
     sampler = Sampler(None, robot)
     q = np.stack([np.stack(pair) for pair in queries])
     X, _, _ = init_trainset(pp["time_spacing_X"], pp["time_spacing_Xnew"], robot.dof, robot.dof, q[0, 0], q[0, 1], scale=1)
+    extra = {"num_bases": args.bases} if args.bases else {}
     model = VGPMP.initialize(sdf=sdf, robot=robot, sampler=sampler, query_states=q, scene_offset=ps["scene_offset"],
-                             seed=1234 + 2 + 1000 * rank, **pp)
+                             seed=1234 + 2 + 1000 * rank, **pp, **extra)
     disable_param_opt(model, default_trainable_params())
     eng = model._eng
     for kv in args.option:

@@ -898,7 +898,7 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
 //   warps 0-5  consumers: 4-basis steps round-robin; accumulators C[12 tiles][cos|sin][2] for the whole basis loop;
 //   warps 6-7  producers: lane = basis of a 32-basis slot; 6 branch-free sincos (start, step of both grids, the two
 //              conditioned endpoints), then the 8 row starts S E^g and E^8 by complex products; 42 doubles per basis
-//              into a 4-slot ring handed over with named barriers.
+//              into a 4-slot ring handed over with mbarriers (one arrival per warp).
 // ---------------------------------------------------------------------------------------------
 constexpr int kRB = 32;        // bases per table slot
 constexpr int kRE = 50;        // doubles per basis in a slot: Sx[8] | E8x | Sz[8] | E8z | e0 | e1 | c/l | pad | w[8 samples]
@@ -976,7 +976,7 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
 
   if (meta[0] == 0.0) return;  // not an equispaced rank-1 grid: the general kernel does the sampling
   if (tid == 0) {
-    for (int i = 0; i < kRS; ++i) { mbar_init(full + i, 32); mbar_init(empty + i, kRC * 32); }
+    for (int i = 0; i < kRS; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, kRC); }   // one arrival per warp
   }
   const double ell = a.ls[pl], s2 = a.var[pl];
   const double amp = sqrt(2.0 * s2 / (double)B), inv_ell = 1.0 / ell;
@@ -1063,7 +1063,9 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
         *reinterpret_cast<double2*>(e + 40) = make_double2(cb * inv_ell, 0.0);
 #pragma unroll
         for (int i = 0; i < kST; i += 2) *reinterpret_cast<double2*>(e + 42 + i) = make_double2(wcur[i], wcur[i + 1]);
-        mbar_arrive(full + slot);                          // slot filled (release)
+        __syncwarp();                                      // all 32 bases written ...
+        if (lane == 0) mbar_arrive(full + slot);           // ... one release for the warp (32 lanes arriving on one
+                                                           // mbarrier serialise: that was most of the kernel's time)
       }
     } else {
       // ---------------- consumer: 4-basis steps q = warp, warp + kRC, ... ----------------
@@ -1078,7 +1080,10 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
       for (int q = warp; q < Q; q += kRC) {
         const int n = q / (kRB / 4);
         if (n != cur) {
-          if (cur >= 0) mbar_arrive(empty + (it * T + cur) % kRS);       // done with the previous slot
+          if (cur >= 0) {                                                // done with the previous slot
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + (it * T + cur) % kRS);
+          }
           const int N = it * T + n;
           mbar_wait(full + N % kRS, (N / kRS) & 1);                     // this slot is filled (acquire)
           cur = n;
@@ -1114,7 +1119,8 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
           ph.x = c2;
         }
       }
-      if (cur >= 0) mbar_arrive(empty + (it * T + cur) % kRS);
+      __syncwarp();
+      if (cur >= 0 && lane == 0) mbar_arrive(empty + (it * T + cur) % kRS);
       // the ring is dead only after ALL consumers left the loop: consumer-only barrier, then the partial sums of this
       // warp go to red[warp][feature][sample][row] over it
       asm volatile("bar.sync 1, %0;" ::"r"(kRC * 32) : "memory");
