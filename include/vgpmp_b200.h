@@ -204,6 +204,16 @@ int vgpmp_rng_fill(vgpmp_handle* h, const vgpmp_dims* dims, uint64_t seed, uint6
                    int64_t sample_offset, double* omega, double* tau, double* w, double* eps_u, double* eps_j,
                    void* stream);
 
+/* Same draws, produced lazily.  eps_u / eps_j are written now; omega, tau and w are NOT: the handle remembers the key
+ * (seed, iteration, offsets) and the buffers.  The next vgpmp_elbo_fwd_bwd / vgpmp_pathwise_sample that is handed exactly
+ * these buffers either generates the values inside the sampler kernel (equispaced rank-1 inputs: they never touch memory)
+ * or writes them into the buffers right before the first kernel that has to read them.  Values are bit-identical to
+ * vgpmp_rng_fill.  The contents of omega / tau / w are unspecified for the caller afterwards.  Replaces the per-step
+ * random_fourier / exact_update draws of GPflowSampling inside tf_optimization_step (utils/miscellaneous.py:68-84). */
+int vgpmp_rng_fill_lazy(vgpmp_handle* h, const vgpmp_dims* dims, uint64_t seed, uint64_t iteration, int64_t problem_offset,
+                        int64_t sample_offset, double* omega, double* tau, double* w, double* eps_u, double* eps_j,
+                        void* stream);
+
 /* Draw prefetch on the handle's internal side stream (two buffer slots), so that generating step t+1's randomness
  * overlaps with step t's kernels.  Protocol per step t with slot = t & 1:
  *   vgpmp_rng_join(h, slot, stream)            stream waits until slot's draws are complete

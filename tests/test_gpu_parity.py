@@ -529,6 +529,32 @@ def test_errors_are_reported_not_swallowed():
         eng.gp_prepare(eng.dims(1, 31, 5, 2, 8), model._params(None))
 
 
+@pytest.mark.parametrize("scenario", ["equispaced", "irregular_inputs", "long_grid"])
+def test_lazy_draws_are_bit_identical_to_materialised_draws(scenario):
+    """train_step's default: omega / tau / w are never written to memory, the sampler's producer warps regenerate them from
+    the Philox keys (`vgpmp_rng_fill_lazy`).  Same keys, same arithmetic -> the optimisation trajectory must equal, bit for
+    bit, the one driven by materialised draws.  irregular_inputs: the device-side probe rejects the grid, the draws are
+    written right before the general sampler; long_grid: 150 points do not fit the register-resident sampler, the draws
+    are written before the shared-memory DMMA sampler."""
+    kw = dict(num_problems=3, S=9, N=40, M=10, B=96, seed=17)
+    if scenario == "long_grid":
+        kw.update(N=150, S=5)
+    case = H.make_case(**kw)
+    X = case["X"].copy()
+    if scenario == "irregular_inputs":
+        X = np.sort(np.random.default_rng(2).uniform(0, 1, size=(X.shape[0], 1)), axis=0) * np.ones((1, X.shape[1]))
+    runs = {}
+    for lazy in (True, False):
+        model = H.make_model(case, seed=77)
+        model.lazy_draws = lazy
+        losses = [model.train_step(X).clone() for _ in range(3)]
+        runs[lazy] = (torch.stack(losses), model._q_mu.clone(), model._q_sqrt.clone(), model._lengthscales.clone(),
+                      model._variances.clone())
+    for a_, b_ in zip(runs[True], runs[False]):
+        assert torch.equal(a_, b_)
+    assert torch.isfinite(runs[True][0]).all()
+
+
 def test_device_rng_key_layout_is_pinned():
     """The Philox key layout (seed, iteration, problem, latent, sample, basis) is part of the reproducibility contract:
     SHA-256 of the draws for a few shapes / offsets against tests/golden/rng_sha256.json (tools/rng_checksum.py)."""

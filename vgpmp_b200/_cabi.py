@@ -81,6 +81,7 @@ SYMBOLS = {
                                 C.POINTER(Aux), _P, _SZ, _P]),
     "vgpmp_adam_step": (_I, [_P, C.POINTER(Dims), C.POINTER(Adam), C.POINTER(Grads), _P]),
     "vgpmp_rng_fill": (_I, [_P, C.POINTER(Dims), _U64, _U64, _I64, _I64, _P, _P, _P, _P, _P, _P]),
+    "vgpmp_rng_fill_lazy": (_I, [_P, C.POINTER(Dims), _U64, _U64, _I64, _I64, _P, _P, _P, _P, _P, _P]),
     "vgpmp_rng_fill_async": (_I, [_P, C.POINTER(Dims), _U64, _U64, _I64, _I64, _P, _P, _P, _P, _P, _I]),
     "vgpmp_rng_join": (_I, [_P, _I, _P]),
     "vgpmp_rng_release": (_I, [_P, _I, _P]),

@@ -198,6 +198,7 @@ int vgpmp_set_option(vgpmp_handle* h, const char* name, int value) {
   if (std::strcmp(name, "dmma_sampler") == 0) { h->allow_dmma_path = value != 0; return VGPMP_OK; }
   if (std::strcmp(name, "split_tail") == 0) { h->allow_split_tail = value != 0; return VGPMP_OK; }
   if (std::strcmp(name, "rr_sampler") == 0) { h->allow_rr_path = value != 0; return VGPMP_OK; }
+  if (std::strcmp(name, "lazy_draws") == 0) { h->allow_lazy_draws = value != 0; return VGPMP_OK; }
   if (std::strcmp(name, "warp_sampler") == 0) { h->allow_warp_path = value != 0; return VGPMP_OK; }
   return fail(h, VGPMP_ERR_INVALID, std::string("set_option: unknown option ") + name);
 }
@@ -414,9 +415,33 @@ int vgpmp_rng_fill(vgpmp_handle* h, const vgpmp_dims* dims, uint64_t seed, uint6
   if (rc) return rc;
   if ((omega == nullptr) != (tau == nullptr) || (eps_u == nullptr) != (eps_j == nullptr))
     return fail(h, VGPMP_ERR_INVALID, "rng_fill: omega/tau and eps_u/eps_j come in pairs");
+  if (h->lazy.valid && (omega == h->lazy.omega || w == h->lazy.w)) h->lazy.valid = false;   // these buffers are real again
   StageSpan sp(h, ST_RNG, (cudaStream_t)stream);
   return check_cuda(h, launch_rng_fill(h, *dims, seed, iteration, problem_offset, sample_offset, omega, tau, w, eps_u,
                                        eps_j, (cudaStream_t)stream), "rng_fill");
+}
+
+int vgpmp_rng_fill_lazy(vgpmp_handle* h, const vgpmp_dims* dims, uint64_t seed, uint64_t iteration, int64_t problem_offset,
+                        int64_t sample_offset, double* omega, double* tau, double* w, double* eps_u, double* eps_j,
+                        void* stream) {
+  if (!h) return VGPMP_ERR_INVALID;
+  if (!h->allow_lazy_draws || !omega || !tau || !w)
+    return vgpmp_rng_fill(h, dims, seed, iteration, problem_offset, sample_offset, omega, tau, w, eps_u, eps_j, stream);
+  int rc = check_dims(h, dims);
+  if (rc) return rc;
+  if ((eps_u == nullptr) != (eps_j == nullptr)) return fail(h, VGPMP_ERR_INVALID, "rng_fill_lazy: eps_u/eps_j come in pairs");
+  {
+    StageSpan sp(h, ST_RNG, (cudaStream_t)stream);
+    rc = check_cuda(h, launch_rng_fill(h, *dims, seed, iteration, problem_offset, sample_offset, nullptr, nullptr, nullptr,
+                                       eps_u, eps_j, (cudaStream_t)stream), "rng_fill_lazy");
+  }
+  if (rc) return rc;
+  h->lazy.valid = true;
+  h->lazy.omega = omega; h->lazy.tau = tau; h->lazy.w = w;
+  h->lazy.seed = seed; h->lazy.iteration = iteration;
+  h->lazy.problem_offset = problem_offset; h->lazy.sample_offset = sample_offset;
+  h->lazy.num_problems = dims->num_problems; h->lazy.num_samples = dims->num_samples; h->lazy.num_bases = dims->num_bases;
+  return VGPMP_OK;
 }
 
 static int ensure_side(vgpmp_handle* h) {
@@ -432,6 +457,7 @@ static int ensure_side(vgpmp_handle* h) {
 int vgpmp_rng_fill_async(vgpmp_handle* h, const vgpmp_dims* dims, uint64_t seed, uint64_t iteration,
                          int64_t problem_offset, int64_t sample_offset, double* omega, double* tau, double* w,
                          double* eps_u, double* eps_j, int slot) {
+  if (h && h->lazy.valid && (omega == h->lazy.omega || w == h->lazy.w)) h->lazy.valid = false;
   int rc = check_dims(h, dims);
   if (rc) return rc;
   if (slot < 0 || slot > 1 || !omega || !tau || !w || !eps_u || !eps_j)
@@ -490,7 +516,10 @@ int vgpmp_train_step_host(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* s
     eps_j = c.take(Bp * D * S * Mp);
   };
   carve_set(slot);
-  if (pipelined && h->prefetched_step == (int64_t)st->step && h->prefetched_seed == seed) {
+  const bool lazy_ok = h->allow_lazy_draws;   // draws generated inside the sampler: no prefetch pipeline needed
+  if (lazy_ok) {
+    if ((rc = vgpmp_rng_fill_lazy(h, dims, seed, (uint64_t)st->step, 0, 0, omega, tau, w, eps_u, eps_j, stream))) return rc;
+  } else if (pipelined && h->prefetched_step == (int64_t)st->step && h->prefetched_seed == seed) {
     if ((rc = vgpmp_rng_join(h, slot, stream))) return rc;
   } else {
     if ((rc = vgpmp_rng_fill(h, dims, seed, (uint64_t)st->step, 0, 0, omega, tau, w, eps_u, eps_j, stream))) return rc;
@@ -499,7 +528,7 @@ int vgpmp_train_step_host(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* s
   vgpmp_draws r{omega, tau, w, eps_u, eps_j};
   if ((rc = vgpmp_elbo_fwd_bwd(h, dims, &p, &r, elbo_dev, g, nullptr, ws, ws_bytes, stream))) return rc;
   if ((rc = vgpmp_adam_step(h, dims, st, g, stream))) return rc;   // st->step is now the NEXT step
-  if (pipelined) {
+  if (pipelined && !lazy_ok) {
     if ((rc = vgpmp_rng_release(h, slot, stream))) return rc;
     carve_set(slot ^ 1);
     if ((rc = vgpmp_rng_fill_async(h, dims, seed, (uint64_t)st->step, 0, 0, omega, tau, w, eps_u, eps_j, slot ^ 1))) return rc;

@@ -54,6 +54,15 @@ struct vgpmp_handle {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_filled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   bool consumed_valid[2] = {false, false};
+  // lazy draws (vgpmp_rng_fill_lazy): omega / tau / w of the set below were not written; this is how to produce them
+  struct LazyDraws {
+    bool valid = false;
+    const double *omega = nullptr, *tau = nullptr, *w = nullptr;
+    uint64_t seed = 0, iteration = 0;
+    int64_t problem_offset = 0, sample_offset = 0;
+    int num_problems = 0, num_samples = 0, num_bases = 0;
+  } lazy;
+  bool allow_lazy_draws = true;   // vgpmp_set_option("lazy_draws"): 0 makes vgpmp_rng_fill_lazy behave like vgpmp_rng_fill
   int64_t prefetched_step = -1;   // vgpmp_train_step_host: which step's draws are in flight / ready
   uint64_t prefetched_seed = 0;
   // stage profiling (bench.py): event pairs recorded on the launching stream
@@ -115,7 +124,7 @@ cudaError_t launch_elbo_reduce(vgpmp_handle* h, const vgpmp_dims& d, const doubl
 cudaError_t launch_adam(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_adam& st, const vgpmp_grads& g, cudaStream_t s);
 cudaError_t launch_rng_fill(vgpmp_handle* h, const vgpmp_dims& d, uint64_t seed, uint64_t iteration,
                             int64_t problem_offset, int64_t sample_offset, double* omega, double* tau, double* w,
-                            double* eps_u, double* eps_j, cudaStream_t s);
+                            double* eps_u, double* eps_j, cudaStream_t s, const double* skip_if_grid = nullptr);
 
 // Matern-5/2 radial profile and its derivative wrt r (GPflow Matern52.K_r).
 __host__ __device__ inline double vg_matern52(double r) {

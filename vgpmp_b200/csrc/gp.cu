@@ -285,6 +285,9 @@ __global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, double ji
 // ---------------------------------------------------------------------------------------------
 struct PathwiseArgs {
   int D, M, Nq, S, B, XG, KS;
+  int gen_draws;       // 1: omega / tau / w are not in memory, the register-resident sampler generates them from the key below
+  uint64_t seed, iteration;
+  int64_t problem_offset, sample_offset;
   int split_tail;      // 1: the sampler stops at f0/h0; gp_prepare_update_kernel finishes the sample paths
   int nchunk, chunk;   // the S samples are split into nchunk CTAs per (problem, latent), `chunk` samples each (multiple of kST)
   double jitter;
@@ -887,6 +890,42 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Counter-based draws (Philox4x32-10).  Shared by rng_fill_kernel and by the register-resident sampler, whose producer
+// warps can generate omega / tau / w in place ("lazy" draws: same keys, same arithmetic, bit-identical values).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    c[1] = (uint32_t)p1; c[3] = (uint32_t)p0; c[0] = n0; c[2] = n2;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {  // (0,1), 53 bits
+  const uint64_t x = ((uint64_t)hi << 32 | lo) >> 11;
+  return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
+}
+// Four independent N(0,1) from one Philox block.  The draws are random inputs, not arithmetic of the reference: the
+// Box-Muller transform runs in float32 on the SFU (32-bit uniforms, |z| < 6.7) and is widened to float64.  Parity
+// tests feed the *materialised* draws to the oracle, so this choice cannot leak into a parity result.
+__device__ __forceinline__ void normal4(uint64_t seed, uint64_t iter, uint32_t stream, uint64_t idx, double z[4]) {
+  uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)iter, stream ^ ((uint32_t)(iter >> 32) << 8)};
+  philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float u1 = ((float)c[2 * k] + 0.5f) * 2.3283064365386963e-10f;       // (0,1]
+    const float u2 = ((float)c[2 * k + 1] + 0.5f) * 2.3283064365386963e-10f;
+    const float r = sqrtf(-2.0f * __logf(fminf(u1, 0.99999994f)));
+    float sn, cs;
+    __sincosf(6.283185307179586f * u2, &sn, &cs);
+    z[2 * k] = (double)(r * cs);
+    z[2 * k + 1] = (double)(r * sn);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
 // Equispaced sampler, register-resident features (N + 2 and M each padded to tiles of 8 rows, <= 12 tiles in total).
 // The DMMA A fragment of thread (g = lane/4, t = lane%4) is the feature of row g at basis t of a 4-basis step - exactly
 // the state of one rotation chain.  So a consumer warp keeps the chain of (row g, basis t) in registers, walks it from
@@ -895,15 +934,16 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
 // traffic, and one warp alone keeps its sub-partition's FP64 pipe busy (32 pipe cycles of DMMA hide the 2-level
 // rotation dependency).  d f0 / d lengthscale uses the separable form  h0[s,x] = t_x sum_b sin(theta_xb) (w_sb c_b / l):
 // same chain registers, weights scaled once per step, rows scaled by their coordinate at the end.
-//   warps 0-5  consumers: 4-basis steps round-robin; accumulators C[12 tiles][cos|sin][2] for the whole basis loop;
-//   warps 6-7  producers: lane = basis of a 32-basis slot; 6 branch-free sincos (start, step of both grids, the two
+//   warps 0-3  consumers: 4-basis steps round-robin; accumulators C[12 tiles][cos|sin][2] for the whole basis loop;
+//   warps 4-7  producers: lane = basis of a 32-basis slot; 6 branch-free sincos (start, step of both grids, the two
 //              conditioned endpoints), then the 8 row starts S E^g and E^8 by complex products; 42 doubles per basis
 //              into a 4-slot ring handed over with mbarriers (one arrival per warp).
 // ---------------------------------------------------------------------------------------------
 constexpr int kRB = 32;        // bases per table slot
 constexpr int kRE = 50;        // doubles per basis in a slot: Sx[8] | E8x | Sz[8] | E8z | e0 | e1 | c/l | pad | w[8 samples]
 constexpr int kRS = 4;         // ring slots
-constexpr int kRC = 6;         // consumer warps
+// consumer / producer warp split: template parameter RC (6 + 2 when the draws are read from memory, 4 + 4 when the
+// producers also generate them)
 constexpr int kRT = 12;        // point tiles (rows / 8) a consumer carries
 
 // shared-memory mbarrier helpers (producer/consumer hand-over without coupling the consumers to each other)
@@ -959,8 +999,11 @@ __device__ __forceinline__ void sincos_bf6(const double (&x)[6], double (&sn)[6]
   }
 }
 
-template <int JX>   // JX = tiles of 8 rows holding the query grid and the two conditioned endpoints; inducing rows follow
+// JX = tiles of 8 rows holding the query grid and the two conditioned endpoints (inducing rows follow); GEN = lazy draws
+template <int JX, bool GEN>
 __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, const double* __restrict__ meta) {
+  constexpr int kRC = GEN ? 4 : 6;     // consumer warps
+  constexpr int kRP = 8 - kRC;         // producer warps
   extern __shared__ __align__(16) double sm[];
   const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, B = a.B, A = Nq + Mp;
   const int pl = blockIdx.x / a.nchunk;
@@ -991,7 +1034,7 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
     const int ns = min(kST, s_end - s0);
     __syncthreads();   // barriers initialised / previous sample tile's fold is done with the shared memory
     if (warp >= kRC) {
-      // ---------------- producer: slots n = pw, pw + 2, ... ----------------
+      // ---------------- producer: slots n = pw, pw + kRP, ... ----------------
       const int pw = warp - kRC;
       // operands of slot n are loaded one slot ahead of their use; `ld.volatile`-style asm pins the loads where they
       // are written (the compiler otherwise sinks them next to their first use and the warp eats the DRAM latency)
@@ -1014,18 +1057,56 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
           if (ok && i < ns) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(wv[i]) : "l"(wp + (size_t)(s0 + i) * B + b));
         }
       };
-      fetch(pw);
-      for (int n = pw; n < T; n += 2) {
+      // lazy draws: the same Philox keys and arithmetic as rng_fill_kernel, evaluated here instead of read from memory
+      constexpr bool gen = GEN;
+      const uint64_t pairkey = ((uint64_t)(pl / D) + (uint64_t)a.problem_offset) * (uint64_t)D + (uint64_t)(pl % D);
+      const uint32_t B4 = ((uint32_t)B + 3) / 4;
+      if (!gen) fetch(pw);
+      for (int n = pw; n < T; n += kRP) {
         const int N = it * T + n, slot = N % kRS, use = N / kRS;
         const bool live = n * kRB + lane < B;
-        double c = 0.0;
+        double c = 0.0, taub = 0.0;
+        double wcur[kST];       // load mode: w[sample][this basis]; lazy mode: [0..3] | [4..7] = two Philox blocks (see below)
+        if (gen) {
+          if (live) {
+            const uint64_t key = pairkey * (uint64_t)B + (uint64_t)(n * kRB + lane);
+            double z[16];
+            const int ncall = (5 + D + 3) / 4;
 #pragma unroll
-        for (int d = 0; d < VGPMP_MAX_DOF; ++d) c += ov[d];
-        const double cb = c * inv_ell, taub = tau;
-        double wcur[kST];
+            for (int k = 0; k < 4; ++k)
+              if (k < ncall) normal4(a.seed, a.iteration, 1u, key * 4 + k, z + 4 * k);
+            const double gam = (z[0] * z[0] + z[1] * z[1] + z[2] * z[2] + z[3] * z[3] + z[4] * z[4]) / 5.0;
+            const double rs = rsqrt(gam);
 #pragma unroll
-        for (int i = 0; i < kST; ++i) wcur[i] = wv[i];
-        fetch(n + 2);
+            for (int d = 0; d < VGPMP_MAX_DOF; ++d)
+              if (d < D) c = __dadd_rn(c, __dmul_rn(z[5 + d], rs));   // as stored then summed by the load path: no FMA
+            uint32_t cc[4] = {(uint32_t)key, (uint32_t)(key >> 32), (uint32_t)a.iteration, 3u};
+            philox4x32(cc, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+            taub = 6.283185307179586476925 * u01(cc[0], cc[1]);
+          }
+          // weights: lane (quad, r) draws the two blocks (quad of 4 bases, samples r and r + 4) and later stores each
+          // component into the row of the basis it belongs to - no shuffles, 64 blocks per slot in total
+          const uint32_t b4 = (uint32_t)n * (kRB / 4) + (uint32_t)(lane >> 2);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int i = (lane & 3) + 4 * hh;
+            double z4[4] = {0.0, 0.0, 0.0, 0.0};
+            if (i < ns && 4 * b4 < (uint32_t)B) {
+              const uint64_t sg = (uint64_t)(s0 + i) + (uint64_t)a.sample_offset;
+              normal4(a.seed, a.iteration, 4u, (pairkey * (uint64_t)(1u << 24) + sg) * B4 + b4, z4);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) wcur[4 * hh + k] = z4[k];
+          }
+        } else {
+#pragma unroll
+          for (int d = 0; d < VGPMP_MAX_DOF; ++d) c += ov[d];
+          taub = tau;
+#pragma unroll
+          for (int i = 0; i < kST; ++i) wcur[i] = wv[i];
+          fetch(n + kRP);
+        }
+        const double cb = c * inv_ell;
         const double ab = live ? amp : 0.0;
         const double ax0 = t0 * cb + taub, ax1 = dt * cb, az0 = z0 * cb + taub, az1 = dz * cb, ae1 = cb + taub;
         const double arg[6] = {ax0, ax1, az0, az1, taub, ae1};
@@ -1061,8 +1142,19 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
         *reinterpret_cast<double2*>(e + 36) = make_double2(ab * ce0, ab * se0);
         *reinterpret_cast<double2*>(e + 38) = make_double2(ab * ce1, ab * se1);
         *reinterpret_cast<double2*>(e + 40) = make_double2(cb * inv_ell, 0.0);
+        if (gen) {
+          double* eq = tab + ((size_t)slot * kRB + (lane & ~3)) * kRE + 42 + (lane & 3);   // row of basis 4*quad, column of sample r
 #pragma unroll
-        for (int i = 0; i < kST; i += 2) *reinterpret_cast<double2*>(e + 42 + i) = make_double2(wcur[i], wcur[i + 1]);
+          for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const bool okb = n * kRB + (lane & ~3) + k < B;
+              eq[(size_t)k * kRE + 4 * hh] = okb ? wcur[4 * hh + k] : 0.0;
+            }
+        } else {
+#pragma unroll
+          for (int i = 0; i < kST; i += 2) *reinterpret_cast<double2*>(e + 42 + i) = make_double2(wcur[i], wcur[i + 1]);
+        }
         __syncwarp();                                      // all 32 bases written ...
         if (lane == 0) mbar_arrive(full + slot);           // ... one release for the warp (32 lanes arriving on one
                                                            // mbarrier serialise: that was most of the kernel's time)
@@ -1781,37 +1873,6 @@ __global__ void adam_kernel(int D, int M, int Bp, vgpmp_adam st, vgpmp_grads g, 
 // Philox4x32-10 draw generator: element-wise counters, so any launch shape / any GPU produces the same draw for the
 // same (seed, iteration, stream, problem, latent, row, column).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
-    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
-    c[1] = (uint32_t)p1; c[3] = (uint32_t)p0; c[0] = n0; c[2] = n2;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-}
-__device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {  // (0,1), 53 bits
-  const uint64_t x = ((uint64_t)hi << 32 | lo) >> 11;
-  return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
-}
-// Four independent N(0,1) from one Philox block.  The draws are random inputs, not arithmetic of the reference: the
-// Box-Muller transform runs in float32 on the SFU (32-bit uniforms, |z| < 6.7) and is widened to float64.  Parity
-// tests feed the *materialised* draws to the oracle, so this choice cannot leak into a parity result.
-__device__ __forceinline__ void normal4(uint64_t seed, uint64_t iter, uint32_t stream, uint64_t idx, double z[4]) {
-  uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)iter, stream ^ ((uint32_t)(iter >> 32) << 8)};
-  philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const float u1 = ((float)c[2 * k] + 0.5f) * 2.3283064365386963e-10f;       // (0,1]
-    const float u2 = ((float)c[2 * k + 1] + 0.5f) * 2.3283064365386963e-10f;
-    const float r = sqrtf(-2.0f * __logf(fminf(u1, 0.99999994f)));
-    float sn, cs;
-    __sincosf(6.283185307179586f * u2, &sn, &cs);
-    z[2 * k] = (double)(r * cs);
-    z[2 * k + 1] = (double)(r * sn);
-  }
-}
-
 struct RngArgs {
   int D, B, S, Mp, Bp;
   int64_t problem_offset, sample_offset;
@@ -1822,14 +1883,16 @@ struct RngArgs {
 // Blocks are grouped per (problem, latent) pair: `bpp` blocks of 256 threads walk the pair's B basis rows, then its
 // S*ceil(B/4) weight quads, then its S*ceil(Mp/2) eps pairs.  All index arithmetic is 32-bit (the flat 64-bit div/mod
 // of the first version was half of the kernel's instructions); the Philox keys are unchanged.
-__global__ void __launch_bounds__(256) rng_fill_kernel(RngArgs a, uint32_t bpp) {
+__global__ void __launch_bounds__(256) rng_fill_kernel(RngArgs a, uint32_t bpp, const double* __restrict__ skip_if_grid) {
+  // lazy draws: this launch only matters when the equispaced sampler did NOT run (it generated its own omega / tau / w)
+  if (skip_if_grid != nullptr && skip_if_grid[0] != 0.0) return;
   const uint32_t B = a.B, S = a.S, D = a.D, Mp = a.Mp, B4 = (B + 3) / 4, M2 = (Mp + 1) / 2;
+  const uint32_t nA = a.omega != nullptr ? B : 0, nW = a.w != nullptr ? S * B4 : 0, nE = a.eps_u != nullptr ? S * M2 : 0;
   const uint32_t pair = blockIdx.x / bpp;                       // local (problem, latent)
   uint32_t t = (blockIdx.x - pair * bpp) * 256u + threadIdx.x;   // index inside the pair
   const uint32_t pl_ = pair / D, l = pair - pl_ * D;
   const uint64_t p = (uint64_t)pl_ + (uint64_t)a.problem_offset;
-  if (t < B) {
-    if (a.omega == nullptr) return;
+  if (t < nA) {
     const uint32_t b = t;
     const uint64_t key = (p * D + l) * B + b;
     const size_t gid = (size_t)pair * B + b;
@@ -1849,9 +1912,8 @@ __global__ void __launch_bounds__(256) rng_fill_kernel(RngArgs a, uint32_t bpp) 
     a.tau[gid] = 6.283185307179586476925 * u01(c[0], c[1]);
     return;
   }
-  t -= B;
-  if (t < S * B4) {
-    if (a.w == nullptr) return;
+  t -= nA;
+  if (t < nW) {
     const uint32_t sl = t / B4, b4 = t - sl * B4;
     const uint64_t s = (uint64_t)sl + (uint64_t)a.sample_offset;
     const uint64_t key = ((p * D + l) * (uint64_t)(1u << 24) + s) * B4 + b4;  // sample index < 2^24
@@ -1867,9 +1929,8 @@ __global__ void __launch_bounds__(256) rng_fill_kernel(RngArgs a, uint32_t bpp) 
     }
     return;
   }
-  t -= S * B4;
-  if (t < S * M2) {
-    if (a.eps_u == nullptr) return;
+  t -= nW;
+  if (t < nE) {
     const uint32_t sl = t / M2, m2 = t - sl * M2;
     const uint64_t s = (uint64_t)sl + (uint64_t)a.sample_offset;
     const uint64_t key = ((p * D + l) * (uint64_t)(1u << 24) + s) * 16 + m2;
@@ -1965,6 +2026,24 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
   // preparation and the pathwise update then share one small-CTA kernel (gp_prepare_update_kernel).
   const bool split = grid_ok && !warp_path && h->allow_dmma_path && h->allow_split_tail && A <= 192 && f0 != nullptr;
   a.split_tail = split ? 1 : 0;
+  // lazy draws (vgpmp_rng_fill_lazy): omega / tau / w of this set were never written.  The register-resident sampler
+  // generates them in its producer warps; anything else needs them in memory first.
+  const bool rr_path = split && h->allow_rr_path && (Nq + 2 + 7) / 8 + (a.M + 7) / 8 <= kRT;
+  const bool lazy = h->lazy.valid && h->lazy.omega == r.omega && h->lazy.tau == r.tau && h->lazy.w == r.w &&
+                    h->lazy.num_problems == d.num_problems && h->lazy.num_samples == d.num_samples &&
+                    h->lazy.num_bases == d.num_bases;
+  a.gen_draws = 0; a.seed = 0; a.iteration = 0; a.problem_offset = 0; a.sample_offset = 0;
+  if (lazy && rr_path) {
+    a.gen_draws = 1;
+    a.seed = h->lazy.seed; a.iteration = h->lazy.iteration;
+    a.problem_offset = h->lazy.problem_offset; a.sample_offset = h->lazy.sample_offset;
+  } else if (lazy) {
+    if ((e = launch_rng_fill(h, d, h->lazy.seed, h->lazy.iteration, h->lazy.problem_offset, h->lazy.sample_offset,
+                             const_cast<double*>(r.omega), const_cast<double*>(r.tau), const_cast<double*>(r.w), nullptr,
+                             nullptr, s, nullptr)) != cudaSuccess)
+      return e;
+    h->lazy.valid = false;   // materialised
+  }
   if (!split && (e = launch_gp_prepare(h, d, p, Lc, Sfull, kl_l, kvec, Linv, s)) != cudaSuccess) return e;
   if (grid_ok) {
     analyze_grid_kernel<<<1, 256, 0, s>>>(a.D, a.M, Nq, Xq, p.Z, meta);
@@ -1984,27 +2063,32 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
         return e;
       pathwise_tail_kernel<<<d.num_problems * a.D, 128, smem_t, s>>>(a, meta);
       h->launches += 2;
-    } else if (h->allow_dmma_path && h->allow_rr_path && split && (Nq + 2 + 7) / 8 + (a.M + 7) / 8 <= kRT) {
-      const size_t ring = (size_t)kRS * kRB * kRE, fold = (size_t)kRC * 2 * kST * kRT * 8;
+    } else if (rr_path) {
+      const size_t ring = (size_t)kRS * kRB * kRE, fold = (size_t)6 * 2 * kST * kRT * 8;
       const size_t smem_r = sizeof(double) * (std::max(ring, fold) + 2 * kRS);
       void (*kern)(PathwiseArgs, const double*) = nullptr;
       switch ((Nq + 2 + 7) / 8) {
-        case 1: kern = pathwise_rr_kernel<1>; break;
-        case 2: kern = pathwise_rr_kernel<2>; break;
-        case 3: kern = pathwise_rr_kernel<3>; break;
-        case 4: kern = pathwise_rr_kernel<4>; break;
-        case 5: kern = pathwise_rr_kernel<5>; break;
-        case 6: kern = pathwise_rr_kernel<6>; break;
-        case 7: kern = pathwise_rr_kernel<7>; break;
-        case 8: kern = pathwise_rr_kernel<8>; break;
-        case 9: kern = pathwise_rr_kernel<9>; break;
-        case 10: kern = pathwise_rr_kernel<10>; break;
-        default: kern = pathwise_rr_kernel<11>; break;
+        case 1: kern = a.gen_draws ? pathwise_rr_kernel<1, true> : pathwise_rr_kernel<1, false>; break;
+        case 2: kern = a.gen_draws ? pathwise_rr_kernel<2, true> : pathwise_rr_kernel<2, false>; break;
+        case 3: kern = a.gen_draws ? pathwise_rr_kernel<3, true> : pathwise_rr_kernel<3, false>; break;
+        case 4: kern = a.gen_draws ? pathwise_rr_kernel<4, true> : pathwise_rr_kernel<4, false>; break;
+        case 5: kern = a.gen_draws ? pathwise_rr_kernel<5, true> : pathwise_rr_kernel<5, false>; break;
+        case 6: kern = a.gen_draws ? pathwise_rr_kernel<6, true> : pathwise_rr_kernel<6, false>; break;
+        case 7: kern = a.gen_draws ? pathwise_rr_kernel<7, true> : pathwise_rr_kernel<7, false>; break;
+        case 8: kern = a.gen_draws ? pathwise_rr_kernel<8, true> : pathwise_rr_kernel<8, false>; break;
+        case 9: kern = a.gen_draws ? pathwise_rr_kernel<9, true> : pathwise_rr_kernel<9, false>; break;
+        case 10: kern = a.gen_draws ? pathwise_rr_kernel<10, true> : pathwise_rr_kernel<10, false>; break;
+        default: kern = a.gen_draws ? pathwise_rr_kernel<11, true> : pathwise_rr_kernel<11, false>; break;
       }
       if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)) != cudaSuccess) return e;
       kern<<<d.num_problems * a.D * a.nchunk, 256, smem_r, s>>>(a, meta);
       gp_prepare_update_kernel<<<d.num_problems * a.D * a.nchunk, 128, 0, s>>>(a, p, Lc, Sfull, kl_l, kvec, Linv, meta);
       h->launches += 2;
+      if (a.gen_draws) {   // inputs turned out not to be an equispaced grid: the general sampler below reads memory
+        if ((e = launch_rng_fill(h, d, a.seed, a.iteration, a.problem_offset, a.sample_offset, const_cast<double*>(r.omega),
+                                 const_cast<double*>(r.tau), const_cast<double*>(r.w), nullptr, nullptr, s, meta)) != cudaSuccess)
+          return e;
+      }
     } else if (h->allow_dmma_path && A <= 192) {
       const int PT = A <= 96 ? 3 : 6, ROWS = 32 * PT;
       const size_t main_view = (size_t)2 * ROWS * kDBP + 3 * kDB * kWS + 3 * 4 * kDB + 3 * kDB + 8 * kDB * 2 + 2 * (2 * kDB * 2);
@@ -2120,15 +2204,17 @@ cudaError_t launch_adam(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_adam& 
 
 cudaError_t launch_rng_fill(vgpmp_handle* h, const vgpmp_dims& d, uint64_t seed, uint64_t iteration,
                             int64_t problem_offset, int64_t sample_offset, double* omega, double* tau, double* w,
-                            double* eps_u, double* eps_j, cudaStream_t s) {
+                            double* eps_u, double* eps_j, cudaStream_t s, const double* skip_if_grid) {
   RngArgs a;
   a.D = h->robot.dof; a.B = d.num_bases; a.S = d.num_samples; a.Mp = d.num_inducing + 2; a.Bp = d.num_problems;
   a.problem_offset = problem_offset; a.sample_offset = sample_offset; a.seed = seed; a.iteration = iteration;
   a.omega = omega; a.tau = tau; a.w = w; a.eps_u = eps_u; a.eps_j = eps_j;
-  const size_t per_pair = (size_t)a.B + (size_t)a.S * ((a.B + 3) / 4) + (size_t)a.S * ((a.Mp + 1) / 2);
+  const size_t per_pair = (omega ? (size_t)a.B : 0) + (w ? (size_t)a.S * ((a.B + 3) / 4) : 0) +
+                          (eps_u ? (size_t)a.S * ((a.Mp + 1) / 2) : 0);
+  if (per_pair == 0) return cudaSuccess;
   const size_t bpp = (per_pair + 255) / 256, blocks = bpp * (size_t)a.Bp * a.D;
   if (per_pair >= (1ull << 32) || blocks >= (1ull << 31)) return cudaErrorInvalidValue;
-  rng_fill_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, (uint32_t)bpp);
+  rng_fill_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, (uint32_t)bpp, skip_if_grid);
   h->launches++;
   return cudaGetLastError();
 }

@@ -225,6 +225,17 @@ class Engine:
                                           self._stream()), "rng_fill")
         return d
 
+    def rng_fill_lazy(self, dims: _cabi.Dims, seed: int, iteration: int, draws: dict, problem_offset: int = 0,
+                      sample_offset: int = 0) -> dict:
+        """`vgpmp_rng_fill_lazy`: eps_u / eps_j are written, omega / tau / w are produced by whoever consumes `draws` next
+        (inside the sampler kernel for equispaced inputs).  Their tensors hold unspecified values afterwards."""
+        d = draws
+        self._chk(self.lib.vgpmp_rng_fill_lazy(self.h, C.byref(dims), int(seed), int(iteration), int(problem_offset),
+                                               int(sample_offset), d["omega"].data_ptr(), d["tau"].data_ptr(),
+                                               d["w"].data_ptr(), d["eps_u"].data_ptr(), d["eps_j"].data_ptr(),
+                                               self._stream()), "rng_fill_lazy")
+        return d
+
     def rng_fill_async(self, dims: _cabi.Dims, seed: int, iteration: int, draws: dict, slot: int, problem_offset: int = 0,
                        sample_offset: int = 0):
         """Generate `draws` on the handle's side stream (overlaps with work queued on the current stream)."""

@@ -52,6 +52,7 @@ class VGPMP:
         self.kernel, self.likelihood, self.inducing_variable = kernel, likelihood, inducing_variable
         self.num_latent_gps = D = int(num_latent_gps)
         self.num_samples, self.num_bases, self.num_inducing = int(num_samples), int(num_bases), int(num_inducing)
+        self.lazy_draws = True      # train_step: draws generated inside the sampler kernel (vgpmp_rng_fill_lazy)
         self.num_data, self.prior, self.seed = num_data, prior, int(seed)
         self.optimizer = AdamConfig(learning_rate)
         self.alpha = float(alpha)
@@ -276,11 +277,16 @@ class VGPMP:
                 self._pipe = dict(key=key, sets=[eng.alloc_draws(dims), eng.alloc_draws(dims)], ready=None)
             slot = self._step & 1
             soff = self._shard["offset"] if self._shard is not None else 0
-            if self._pipe["ready"] == self._step:
-                eng.rng_join(slot)
+            if self.lazy_draws:
+                # omega / tau / w are generated inside the sampler kernel from the same Philox keys: nothing to prefetch
+                eng.rng_fill_lazy(dims, self.seed, self._step, self._pipe["sets"][0], sample_offset=soff)
+                use, slot = self._pipe["sets"][0], None
             else:
-                eng.rng_fill(dims, self.seed, self._step, self._pipe["sets"][slot], sample_offset=soff)
-            use = self._pipe["sets"][slot]
+                if self._pipe["ready"] == self._step:
+                    eng.rng_join(slot)
+                else:
+                    eng.rng_fill(dims, self.seed, self._step, self._pipe["sets"][slot], sample_offset=soff)
+                use = self._pipe["sets"][slot]
         else:
             use = self._make_draws(dims, draws)
         if self._shard is not None:
