@@ -942,8 +942,6 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint64_t iter, uint32_t s
 constexpr int kRB = 32;        // bases per table slot
 constexpr int kRE = 50;        // doubles per basis in a slot: Sx[8] | E8x | Sz[8] | E8z | e0 | e1 | c/l | pad | w[8 samples]
 constexpr int kRS = 4;         // ring slots
-// consumer / producer warp split: template parameter RC (6 + 2 when the draws are read from memory, 4 + 4 when the
-// producers also generate them)
 constexpr int kRT = 12;        // point tiles (rows / 8) a consumer carries
 
 // shared-memory mbarrier helpers (producer/consumer hand-over without coupling the consumers to each other)
@@ -1002,7 +1000,7 @@ __device__ __forceinline__ void sincos_bf6(const double (&x)[6], double (&sn)[6]
 // JX = tiles of 8 rows holding the query grid and the two conditioned endpoints (inducing rows follow); GEN = lazy draws
 template <int JX, bool GEN>
 __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, const double* __restrict__ meta) {
-  constexpr int kRC = GEN ? 4 : 6;     // consumer warps
+  constexpr int kRC = 4;               // consumer warps (4 + 4 in both modes: the fold order, hence every bit, is shared)
   constexpr int kRP = 8 - kRC;         // producer warps
   extern __shared__ __align__(16) double sm[];
   const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, B = a.B, A = Nq + Mp;
@@ -2064,7 +2062,7 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
       pathwise_tail_kernel<<<d.num_problems * a.D, 128, smem_t, s>>>(a, meta);
       h->launches += 2;
     } else if (rr_path) {
-      const size_t ring = (size_t)kRS * kRB * kRE, fold = (size_t)6 * 2 * kST * kRT * 8;
+      const size_t ring = (size_t)kRS * kRB * kRE, fold = (size_t)4 * 2 * kST * kRT * 8;
       const size_t smem_r = sizeof(double) * (std::max(ring, fold) + 2 * kRS);
       void (*kern)(PathwiseArgs, const double*) = nullptr;
       switch ((Nq + 2 + 7) / 8) {
