@@ -289,6 +289,7 @@ struct PathwiseArgs {
   uint64_t seed, iteration;
   int64_t problem_offset, sample_offset;
   int split_tail;      // 1: the sampler stops at f0/h0; gp_prepare_update_kernel finishes the sample paths
+  int items;           // work items of the general sampler (pairs x nchunk)
   int nchunk, chunk;   // the S samples are split into nchunk CTAs per (problem, latent), `chunk` samples each (multiple of kST)
   double jitter;
   const double *Z, *Xq, *ls, *var, *q_mu, *query_latent;
@@ -300,9 +301,13 @@ struct PathwiseArgs {
 __global__ void __launch_bounds__(768) pathwise_kernel(PathwiseArgs a, const double* __restrict__ meta) {
   if (meta != nullptr && meta[0] != 0.0) return;  // equispaced rank-1 inputs: pathwise_grid_kernel does the work
   extern __shared__ double sm[];
+  // work items = (problem, latent, sample chunk); the grid may be smaller than their number (the launcher sends only a
+  // couple of CTAs per SM when the equispaced path is expected to take the work: an empty launch of 1925 x 768 threads
+  // cost 6 us per step)
+  for (int item = blockIdx.x; item < a.items; item += gridDim.x) {
   const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, B = a.B, A = Nq + Mp;
-  const int pl = blockIdx.x / a.nchunk, p = pl / D, l = pl % D;
-  const int s_begin = (blockIdx.x % a.nchunk) * a.chunk, s_end = min(a.S, s_begin + a.chunk);
+  const int pl = item / a.nchunk, p = pl / D, l = pl % D;
+  const int s_begin = (item % a.nchunk) * a.chunk, s_end = min(a.S, s_begin + a.chunk);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
   const int XP = a.XG * 32;
   // shared-memory carve-up
@@ -416,6 +421,8 @@ __global__ void __launch_bounds__(768) pathwise_kernel(PathwiseArgs a, const dou
       a.f[(((size_t)p * S + s0 + i) * Nq + n) * D + l] = fv;
     }
     __syncthreads();
+  }
+  __syncthreads();
   }
 }
 
@@ -1881,13 +1888,15 @@ struct RngArgs {
 // Blocks are grouped per (problem, latent) pair: `bpp` blocks of 256 threads walk the pair's B basis rows, then its
 // S*ceil(B/4) weight quads, then its S*ceil(Mp/2) eps pairs.  All index arithmetic is 32-bit (the flat 64-bit div/mod
 // of the first version was half of the kernel's instructions); the Philox keys are unchanged.
-__global__ void __launch_bounds__(256) rng_fill_kernel(RngArgs a, uint32_t bpp, const double* __restrict__ skip_if_grid) {
+__global__ void __launch_bounds__(256) rng_fill_kernel(RngArgs a, uint32_t bpp, uint32_t nblocks,
+                                                       const double* __restrict__ skip_if_grid) {
   // lazy draws: this launch only matters when the equispaced sampler did NOT run (it generated its own omega / tau / w)
   if (skip_if_grid != nullptr && skip_if_grid[0] != 0.0) return;
   const uint32_t B = a.B, S = a.S, D = a.D, Mp = a.Mp, B4 = (B + 3) / 4, M2 = (Mp + 1) / 2;
   const uint32_t nA = a.omega != nullptr ? B : 0, nW = a.w != nullptr ? S * B4 : 0, nE = a.eps_u != nullptr ? S * M2 : 0;
-  const uint32_t pair = blockIdx.x / bpp;                       // local (problem, latent)
-  uint32_t t = (blockIdx.x - pair * bpp) * 256u + threadIdx.x;   // index inside the pair
+  for (uint32_t vb = blockIdx.x; vb < nblocks; vb += gridDim.x) {   // (the gated launch uses a small grid: it usually exits above)
+  const uint32_t pair = vb / bpp;                                // local (problem, latent)
+  uint32_t t = (vb - pair * bpp) * 256u + threadIdx.x;            // index inside the pair
   const uint32_t pl_ = pair / D, l = pair - pl_ * D;
   const uint64_t p = (uint64_t)pl_ + (uint64_t)a.problem_offset;
   if (t < nA) {
@@ -1908,7 +1917,7 @@ __global__ void __launch_bounds__(256) rng_fill_kernel(RngArgs a, uint32_t bpp, 
     uint32_t c[4] = {(uint32_t)key, (uint32_t)(key >> 32), (uint32_t)a.iteration, 3u};
     philox4x32(c, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
     a.tau[gid] = 6.283185307179586476925 * u01(c[0], c[1]);
-    return;
+    continue;
   }
   t -= nA;
   if (t < nW) {
@@ -1925,7 +1934,7 @@ __global__ void __launch_bounds__(256) rng_fill_kernel(RngArgs a, uint32_t bpp, 
       for (uint32_t k = 0; k < 4; ++k)
         if (b4 * 4 + k < B) dst[k] = z[k];
     }
-    return;
+    continue;
   }
   t -= nW;
   if (t < nE) {
@@ -1938,6 +1947,7 @@ __global__ void __launch_bounds__(256) rng_fill_kernel(RngArgs a, uint32_t bpp, 
     a.eps_u[o] = z[0];
     a.eps_j[o] = z[2];
     if (m2 * 2 + 1 < Mp) { a.eps_u[o + 1] = z[1]; a.eps_j[o + 1] = z[3]; }
+  }
   }
 }
 
@@ -2118,7 +2128,9 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   e = cudaFuncSetAttribute(pathwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  pathwise_kernel<<<d.num_problems * a.D * a.nchunk, threads_gen, smem, s>>>(a, grid_ok ? meta : nullptr);
+  a.items = d.num_problems * a.D * a.nchunk;
+  const int grid_gen = grid_ok ? std::min(a.items, 2 * h->num_sms) : a.items;
+  pathwise_kernel<<<grid_gen, threads_gen, smem, s>>>(a, grid_ok ? meta : nullptr);
   h->launches++;
   return cudaGetLastError();
 }
@@ -2212,7 +2224,8 @@ cudaError_t launch_rng_fill(vgpmp_handle* h, const vgpmp_dims& d, uint64_t seed,
   if (per_pair == 0) return cudaSuccess;
   const size_t bpp = (per_pair + 255) / 256, blocks = bpp * (size_t)a.Bp * a.D;
   if (per_pair >= (1ull << 32) || blocks >= (1ull << 31)) return cudaErrorInvalidValue;
-  rng_fill_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, (uint32_t)bpp, skip_if_grid);
+  const size_t grid = skip_if_grid != nullptr ? std::min(blocks, (size_t)8 * h->num_sms) : blocks;
+  rng_fill_kernel<<<(unsigned)grid, 256, 0, s>>>(a, (uint32_t)bpp, (uint32_t)blocks, skip_if_grid);
   h->launches++;
   return cudaGetLastError();
 }
