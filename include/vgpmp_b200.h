@@ -255,9 +255,16 @@ double vgpmp_probe_fp64_tflops(int device);
  * With profiling enabled every stage launch of vgpmp_elbo_fwd_bwd / vgpmp_adam_step / vgpmp_rng_fill is bracketed by
  * CUDA events on the launching stream; vgpmp_profile_collect synchronises, returns the summed milliseconds and launch
  * counts per stage (arrays of VGPMP_NUM_STAGES) and clears the record. */
-/* Tuning switches (all default on).  "grid_fast_path": when X and Z are rank-1 equispaced grids (always true for the
- * reference's init_trainset / initialize_Z) the Fourier features are generated by rotation recurrences; 0 forces the
- * general per-point sincos kernel. */
+/* Tuning switches (default on unless noted; every combination is covered by the parity tests).
+ *   "grid_fast_path"  X and Z rank-1 equispaced grids (always true for the reference's init_trainset / initialize_Z): the
+ *                     Fourier features come from rotation recurrences; 0 forces the general per-point sincos kernel.
+ *   "dmma_sampler"    contraction of the equispaced sampler on the FP64 tensor path (DMMA m8n8k4); 0 = FMA contraction.
+ *   "rr_sampler"      register-resident warp-specialised DMMA sampler (points must fit 12 tiles of 8 rows, e.g. N=70, M=24);
+ *                     0 = the variant that passes the features through shared memory.
+ *   "split_tail"      the sampler stops at the prior draw; GP preparation + pathwise update run in their own kernel.
+ *   "lazy_draws"      vgpmp_rng_fill_lazy / vgpmp_train_step_host leave omega, tau, w to be generated inside the sampler;
+ *                     0 = always materialise them (vgpmp_train_step_host then prefetches the next step's set instead).
+ *   "warp_sampler"    experimental warp-synchronous sampler (default off). */
 int vgpmp_set_option(vgpmp_handle* h, const char* name, int value);
 #define VGPMP_NUM_STAGES 7
 int vgpmp_profile_enable(vgpmp_handle* h, int on);
