@@ -235,3 +235,59 @@ def test_product_never_imports_oracle():
     for path in (H.ROOT / "vgpmp_b200").rglob("*.py"):
         src = path.read_text()
         assert "import oracle" not in src and "from oracle" not in src, path
+
+
+def test_oracle_matern52_matches_scikit_learn():
+    """GPflow's Matern52 is not installable here; scikit-learn's Matern(nu=2.5) is an independent implementation of the
+    same kernel.  Pins `matern52`, `k_conditioned` and `kuu` (lengthscale scaling, variance, jitter)."""
+    from sklearn.gaussian_process.kernels import Matern
+    rng = np.random.default_rng(0)
+    Zy = np.sort(rng.uniform(0, 1, size=(9, 1)), axis=0) * np.ones((1, 3))      # rank-1 inputs, 3 latents
+    X = rng.uniform(-0.2, 1.2, size=(11, 1)) * np.ones((1, 3))
+    ls, var = np.array([0.3, 1.7, 4.0]), np.array([0.5, 0.25, 2.0])
+    K = O.k_conditioned(O._t(Zy), O._t(X), O._t(ls), O._t(var)).numpy()          # [D, 9, 11]
+    Kuu = O.kuu(O._t(Zy), O._t(ls), O._t(var), 1e-6).numpy()
+    for l in range(3):
+        sk = Matern(length_scale=ls[l], nu=2.5)
+        assert np.allclose(K[l], var[l] * sk(Zy[:, l:l + 1], X[:, l:l + 1]), rtol=1e-12, atol=1e-14)
+        assert np.allclose(Kuu[l], var[l] * sk(Zy[:, l:l + 1]) + 1e-6 * np.eye(9), rtol=1e-12, atol=1e-14)
+
+
+def test_oracle_whitened_kl_matches_torch_distributions():
+    """gauss_kl(white=True) = KL(N(m, S S^T) || N(0, I)) per latent; torch.distributions is an independent implementation.
+    The conditioned-prior mean shift of prior_kl.py is removed by placing q_mu on the prior mean plus a known whitened
+    offset, so the closed form applies exactly."""
+    import torch.distributions as td
+    case = H.make_case(num_problems=1, S=2, N=5, M=6, B=8, perturb=True, seed=3)
+    p = case["oracle"][0]
+    D, M = p.robot.dof, 6
+    ls, var = O._t(case["ls"][0]), O._t(case["var"][0])
+    K = O.kuu(O._t(p.Zy), ls, var, O.JITTER)
+    L = torch.linalg.cholesky(K)
+    qs = O._t(p.joint_sigmoid_inv(p.query_states))
+    prior_mean = (K[:, :, :2] @ torch.cholesky_solve(qs.T[..., None], L[:, :2, :2]))[:, :, 0]          # [D, Mp]
+    rng = np.random.default_rng(4)
+    white = O._t(rng.standard_normal((D, M)))                                                          # whitened offset a
+    full = prior_mean + (L @ torch.cat([torch.zeros(D, 2, dtype=torch.float64), white], 1)[..., None])[:, :, 0]
+    q_mu = full[:, 2:].T                                                                                # [M, D]
+    q_sqrt = O._t(case["q_sqrt"][0])
+    got = float(p.prior_kl(q_mu, q_sqrt, ls, var))
+    want = sum(float(td.kl_divergence(td.MultivariateNormal(white[l], scale_tril=torch.tril(q_sqrt[l])),
+                                      td.MultivariateNormal(torch.zeros(M, dtype=torch.float64),
+                                                            torch.eye(M, dtype=torch.float64)))) for l in range(D))
+    assert abs(got - want) <= 1e-9 * abs(want)
+
+
+def test_oracle_fourier_features_reproduce_the_matern52_kernel():
+    """The random-Fourier prior of GPflowSampling must have the Matern-5/2 covariance: with omega = N(0,I)/sqrt(Gamma(5/2,
+    rate 5/2)), E[phi(x)^T phi(x')] = k(x, x').  Monte-Carlo over 200 000 bases, 1-D inputs (tolerance 4 sigma)."""
+    rng = np.random.default_rng(7)
+    d = O.make_draws(rng, D=1, S=1, B=200_000, Mp=3, Din=1)
+    omega, tau = d["omega"][0, :, 0], d["tau"][0]
+    x = np.array([0.0, 0.13, 0.4, 1.0, 2.5])
+    ell, var = 0.8, 1.3
+    phi = np.sqrt(2.0 * var / omega.size) * np.cos(np.outer(x, omega) / ell + tau[None, :])            # [5, B]
+    est = phi @ phi.T
+    r = np.abs(x[:, None] - x[None, :]) / ell
+    want = var * O.matern52(O._t(r)).numpy()
+    assert np.abs(est - want).max() < 4 * var * np.sqrt(0.5 / omega.size) * 2
