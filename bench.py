@@ -296,6 +296,9 @@ def run_b200(args):
             if t:
                 roofline["traffic"] = t["dram_bytes_per_launch"]
                 roofline["traffic_source"] = t["source"]
+                if "gather_probe" in t:     # measured ceiling of random 32-byte gathers (context for `frac`, not the peak)
+                    roofline["gather_probe"] = t["gather_probe"]
+                    roofline["frac_of_gather_probe"] = achieved / t["gather_probe"]["l2_resident_grid_GBps"]
         # dominant stage by time = the sampler: FP64-pipe bound (B200 runs DMMA on the FP64 pipe at the DFMA rate, see
         # profiles/r1_v9_dmma_probe.txt).  Algorithmic flops = the two contractions (f0 and d f0/d lengthscale: S*A*B FMAs
         # each, 2 flops per FMA) plus 6 FP64 operations per generated feature pair; peak = FP64 FMA rate measured now
