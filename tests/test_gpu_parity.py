@@ -529,16 +529,19 @@ def test_errors_are_reported_not_swallowed():
         eng.gp_prepare(eng.dims(1, 31, 5, 2, 8), model._params(None))
 
 
-@pytest.mark.parametrize("scenario", ["equispaced", "irregular_inputs", "long_grid"])
+@pytest.mark.parametrize("scenario", ["equispaced", "irregular_inputs", "long_grid", "sample_shard"])
 def test_lazy_draws_are_bit_identical_to_materialised_draws(scenario):
     """train_step's default: omega / tau / w are never written to memory, the sampler's producer warps regenerate them from
     the Philox keys (`vgpmp_rng_fill_lazy`).  Same keys, same arithmetic -> the optimisation trajectory must equal, bit for
     bit, the one driven by materialised draws.  irregular_inputs: the device-side probe rejects the grid, the draws are
     written right before the general sampler; long_grid: 150 points do not fit the register-resident sampler, the draws
-    are written before the shared-memory DMMA sampler."""
+    are written before the shared-memory DMMA sampler; sample_shard: rank 1 of 2 in the single-problem large-sample mode
+    (non-zero sample offset in the Philox keys, several sample tiles per CTA)."""
     kw = dict(num_problems=3, S=9, N=40, M=10, B=96, seed=17)
     if scenario == "long_grid":
         kw.update(N=150, S=5)
+    if scenario == "sample_shard":
+        kw.update(num_problems=1, S=38)
     case = H.make_case(**kw)
     X = case["X"].copy()
     if scenario == "irregular_inputs":
@@ -546,6 +549,8 @@ def test_lazy_draws_are_bit_identical_to_materialised_draws(scenario):
     runs = {}
     for lazy in (True, False):
         model = H.make_model(case, seed=77)
+        if scenario == "sample_shard":
+            model.enable_sample_sharding(1, 2)
         model.lazy_draws = lazy
         losses = [model.train_step(X).clone() for _ in range(3)]
         runs[lazy] = (torch.stack(losses), model._q_mu.clone(), model._q_sqrt.clone(), model._lengthscales.clone(),
