@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--option", action="append", default=[], metavar="NAME=INT",
                     help="experiments only: vgpmp_set_option(NAME, INT) before timing (e.g. mma_sampler=0)")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="sub-batches of the problem batch, each on its own CUDA stream (StreamedVGPMP); 1 = one VGPMP model")
     ap.add_argument("--bases", type=int, default=0, help="experiments only: number of random Fourier bases (default 1024)")
     ap.add_argument("--problems", type=int, default=0, help="experiments only: truncate / cycle the batch to this many problems")
     return ap.parse_args()
@@ -176,7 +178,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from vgpmp_b200 import _cabi
-    from vgpmp_b200.models import VGPMP
+    from vgpmp_b200.models import StreamedVGPMP, VGPMP
     from vgpmp_b200.utils.miscellaneous import default_trainable_params, disable_param_opt, init_trainset
     from vgpmp_b200.utils.robot import Robot
     from vgpmp_b200.utils.sampler import Sampler
@@ -203,13 +205,29 @@ def run_b200(args):
     q = np.stack([np.stack(pair) for pair in queries])
     X, _, _ = init_trainset(pp["time_spacing_X"], pp["time_spacing_Xnew"], robot.dof, robot.dof, q[0, 0], q[0, 1], scale=1)
     extra = {"num_bases": args.bases} if args.bases else {}
-    model = VGPMP.initialize(sdf=sdf, robot=robot, sampler=sampler, query_states=q, scene_offset=ps["scene_offset"],
-                             seed=1234 + 2 + 1000 * rank, **pp, **extra)
-    disable_param_opt(model, default_trainable_params())
+    init_kw = dict(sdf=sdf, robot=robot, sampler=sampler, scene_offset=ps["scene_offset"], seed=1234 + 2 + 1000 * rank, **pp,
+                   **extra)
+
+    def configure(m):
+        disable_param_opt(m, default_trainable_params())
+        for kv in args.option:
+            k, v = kv.split("=")
+            m._eng.set_option(k, int(v))
+        return m
+
+    # `model`: the whole batch in one VGPMP (used for the per-kernel stage profile: every launch covers all problems).
+    # `runner`: what is timed - the same batch as `--streams` sub-batches on their own CUDA streams (StreamedVGPMP), whose
+    # latency-bound kernels fill the gaps of each other's FP64-bound sampler; identical results (global Philox keys).
+    model = configure(VGPMP.initialize(query_states=q, **init_kw))
     eng = model._eng
-    for kv in args.option:
-        k, v = kv.split("=")
-        eng.set_option(k, int(v))
+    if args.streams > 1:
+        runner = StreamedVGPMP.initialize(query_states=q, num_streams=args.streams, **init_kw)
+        for m in runner.models:
+            configure(m)
+        count_launches = lambda: runner.launch_count
+    else:
+        runner = model
+        count_launches = lambda: eng.launch_count
     Bp, S, N, M, B, D, P = model.num_problems, model.num_samples, X.shape[0], model.num_inducing, model.num_bases, robot.dof, robot.num_spheres
     Xd = eng.dev(X)
 
@@ -218,45 +236,53 @@ def run_b200(args):
             dist.barrier()
 
     for _ in range(max(args.warmup, 3)):
-        model.train_step(Xd)
+        runner.train_step(Xd)
     torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ timed region (inputs resident in HBM)
-    stage_ms = (C.c_double * _cabi.NUM_STAGES)()
-    stage_n = (C.c_int64 * _cabi.NUM_STAGES)()
-    eng.lib.vgpmp_profile_collect(eng.h, stage_ms, stage_n)
-    eng.lib.vgpmp_profile_enable(eng.h, 1)
     clocks = ClockSampler(local)
     clocks.start()
     time.sleep(0.15)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = eng.launch_count
+    launches0 = count_launches()
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        model.train_step(Xd)
+        runner.train_step(Xd)
     e1.record()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = eng.launch_count - launches0
+    launches = count_launches() - launches0
+
+    # ------------------------------------------------------------------ stage profile: untimed extra pass, one launch per
+    # kernel over the whole batch, CUDA events recorded by the library around every stage (they cost ~5 %: not in `value`)
+    stage_ms = (C.c_double * _cabi.NUM_STAGES)()
+    stage_n = (C.c_int64 * _cabi.NUM_STAGES)()
+    for _ in range(3):
+        model.train_step(Xd)
+    torch.cuda.synchronize()
+    eng.lib.vgpmp_profile_collect(eng.h, stage_ms, stage_n)
+    eng.lib.vgpmp_profile_enable(eng.h, 1)
+    for _ in range(min(args.steps, 50)):
+        model.train_step(Xd)
     eng.lib.vgpmp_profile_collect(eng.h, stage_ms, stage_n)
     eng.lib.vgpmp_profile_enable(eng.h, 0)
 
     # ------------------------------------------------------------------ e2e: host buffers through the public step
     Xh = torch.from_numpy(X.copy()).pin_memory()
     for _ in range(3):
-        model.train_step_host(Xh)
+        runner.train_step_host(Xh)
     barrier()
     torch.cuda.synchronize()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     last = None
     for _ in range(args.steps):
-        last = model.train_step_host(Xh)       # H2D X, device RNG, fwd+bwd+Adam, D2H loss, stream sync
+        last = runner.train_step_host(Xh)      # H2D X, device RNG, fwd+bwd+Adam, D2H loss, stream sync(s)
     f1.record()
     torch.cuda.synchronize()
     t2 = time.perf_counter()
@@ -323,12 +349,13 @@ def run_b200(args):
                        "S": S, "N": N, "M": M, "B": B, "dof": D, "spheres": P,
                        "sdf": f"{sdf_desc}; grid {sdf.data.shape} float64, {sdf.data.nbytes * 4 / 2**20:.0f} MiB of "
                               "{value,gradient} records in HBM (the reference's own .sdf grids are missing blobs)",
-                       "rng": "device Philox4x32-10, fresh draws every step",
+                       "rng": "device Philox4x32-10, fresh draws every step (lazy: generated inside the sampler kernel)",
+                       "streams": args.streams,
                        "l2": "inputs larger than L2 (draws + SDF grid > 126 MB per step); no explicit flush"},
             "sdf_evals_per_s": world * evals_per_step * args.steps / (ms / 1000.0),
             "e2e": {"value": world * Bp * args.steps / (ms_e2e / 1000.0), "unit": UNIT,
-                    "h2d_bytes_per_step": int(X.nbytes), "d2h_bytes_per_step": int(Bp * 8),
-                    "ms_per_step": ms_e2e / args.steps, "api": "VGPMP.train_step_host -> vgpmp_train_step_host"},
+                    "h2d_bytes_per_step": int(X.nbytes) * max(args.streams, 1), "d2h_bytes_per_step": int(Bp * 8),
+                    "ms_per_step": ms_e2e / args.steps, "api": ("StreamedVGPMP.train_step_host -> vgpmp_train_step_host_begin/_end per sub-batch" if args.streams > 1 else "VGPMP.train_step_host -> vgpmp_train_step_host")},
             "gpu_launches": int(launches), "stages": stages, "roofline": roofline, "roofline_dominant_stage": out_dom,
             "clocks": clk,
         }

@@ -235,6 +235,17 @@ int vgpmp_train_step_host(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* s
                           const double* Z, const double* X_host, double* X_dev, uint64_t seed, double* draws_ws,
                           size_t draws_bytes, const vgpmp_grads* g, double* elbo_dev, double* loss_host, void* ws,
                           size_t ws_bytes, void* stream);
+
+/* The same step in two halves, for callers that drive several handles (sub-batches of independent problems on their own
+ * streams) and want their steps to overlap: _begin enqueues everything up to the asynchronous copy of the loss and
+ * returns without waiting; _end synchronises `stream` and turns the copied ELBO into loss = -ELBO.  problem_offset =
+ * global index of this handle's first problem (the Philox keys use global problem indices, so a split batch reproduces
+ * the unsplit one bit for bit). */
+int vgpmp_train_step_host_begin(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* st, const double* query_latent,
+                                const double* Z, const double* X_host, double* X_dev, uint64_t seed, int64_t problem_offset,
+                                double* draws_ws, size_t draws_bytes, const vgpmp_grads* g, double* elbo_dev,
+                                double* loss_host, void* ws, size_t ws_bytes, void* stream);
+int vgpmp_train_step_host_end(vgpmp_handle* h, const vgpmp_dims* dims, double* loss_host, void* stream);
 size_t vgpmp_draws_bytes(const vgpmp_dims* dims, int dof);
 
 /* ---- SDF producer (replaces the external SDFGen binary driven by gpflow_vgpmp/utils/gen_sdf.py:16-43) ---------------

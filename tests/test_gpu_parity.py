@@ -560,6 +560,36 @@ def test_lazy_draws_are_bit_identical_to_materialised_draws(scenario):
     assert torch.isfinite(runs[True][0]).all()
 
 
+def test_streamed_sub_batches_reproduce_the_unsplit_batch_bit_for_bit():
+    """StreamedVGPMP: the batch as sub-batches on their own CUDA streams (device step and the host-buffer begin/end step).
+    Draws are keyed by the global problem index, problems are independent -> losses and state equal the single-model
+    batch exactly."""
+    from vgpmp_b200.models import StreamedVGPMP, VGPMP
+    from vgpmp_b200.utils.robot import Robot
+    from vgpmp_b200.utils.sampler import Sampler
+    case = H.make_case(num_problems=5, S=7, N=30, M=8, B=64, seed=23, perturb=False)
+    pp = dict(case["pp"])
+    pp.update(num_samples=case["S"], num_inducing=case["M"])
+    robot = Robot.from_tables(case["name"], case["env"])
+    q = np.stack([np.stack(qq) for qq in case["queries"]])
+    kw = dict(sdf=case["sdf"], robot=robot, sampler=Sampler(None, robot), scene_offset=case["ps"]["scene_offset"],
+              num_bases=case["B"], seed=5, **pp)
+    Xh = torch.from_numpy(case["X"].copy()).pin_memory()
+    for mode in ("device", "host"):
+        one = VGPMP.initialize(query_states=q, **kw)
+        many = StreamedVGPMP.initialize(query_states=q, num_streams=3, **kw)
+        assert [m.problem_offset for m in many.models] == [0, 2, 4] and many.num_problems == 5
+        for _ in range(3):
+            if mode == "device":
+                a_, b_ = one.train_step(case["X"]), many.train_step(case["X"])
+            else:
+                a_, b_ = one.train_step_host(Xh).clone(), many.train_step_host(Xh)
+            assert torch.equal(a_.cpu().reshape(-1), b_.cpu().reshape(-1)), mode
+        torch.cuda.synchronize()
+        assert torch.equal(one._q_mu, many.q_mu) and torch.equal(one._q_sqrt, many.q_sqrt)
+        assert torch.equal(one._lengthscales, many.lengthscales) and torch.equal(one._variances, many.variances)
+
+
 def test_device_rng_key_layout_is_pinned():
     """The Philox key layout (seed, iteration, problem, latent, sample, basis) is part of the reproducibility contract:
     SHA-256 of the draws for a few shapes / offsets against tests/golden/rng_sha256.json (tools/rng_checksum.py)."""

@@ -87,6 +87,9 @@ SYMBOLS = {
     "vgpmp_rng_release": (_I, [_P, _I, _P]),
     "vgpmp_train_step_host": (_I, [_P, C.POINTER(Dims), C.POINTER(Adam), _P, _P, _P, _P, _U64, _P, _SZ,
                                    C.POINTER(Grads), _P, _P, _P, _SZ, _P]),
+    "vgpmp_train_step_host_begin": (_I, [_P, C.POINTER(Dims), C.POINTER(Adam), _P, _P, _P, _P, _U64, _I64, _P, _SZ,
+                                         C.POINTER(Grads), _P, _P, _P, _SZ, _P]),
+    "vgpmp_train_step_host_end": (_I, [_P, C.POINTER(Dims), _P, _P]),
     "vgpmp_draws_bytes": (_SZ, [C.POINTER(Dims), _I]),
     "vgpmp_mesh_to_sdf": (_I, [_I, c_double_p, c_double_p, c_int32_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.c_int32, c_double_p, _D, c_double_p]),

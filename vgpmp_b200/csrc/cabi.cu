@@ -488,10 +488,10 @@ int vgpmp_rng_release(vgpmp_handle* h, int slot, void* stream) {
   return check_cuda(h, cudaEventRecord(h->ev_consumed[slot], (cudaStream_t)stream), "rng_release");
 }
 
-int vgpmp_train_step_host(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* st, const double* query_latent,
-                          const double* Z, const double* X_host, double* X_dev, uint64_t seed, double* draws_ws,
-                          size_t draws_bytes, const vgpmp_grads* g, double* elbo_dev, double* loss_host, void* ws,
-                          size_t ws_bytes, void* stream) {
+int vgpmp_train_step_host_begin(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* st, const double* query_latent,
+                                const double* Z, const double* X_host, double* X_dev, uint64_t seed, int64_t problem_offset,
+                                double* draws_ws, size_t draws_bytes, const vgpmp_grads* g, double* elbo_dev,
+                                double* loss_host, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_dims(h, dims);
   if (rc) return rc;
   if (!st || !query_latent || !Z || !X_host || !X_dev || !draws_ws || !g || !elbo_dev || !loss_host || !ws)
@@ -518,11 +518,11 @@ int vgpmp_train_step_host(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* s
   carve_set(slot);
   const bool lazy_ok = h->allow_lazy_draws;   // draws generated inside the sampler: no prefetch pipeline needed
   if (lazy_ok) {
-    if ((rc = vgpmp_rng_fill_lazy(h, dims, seed, (uint64_t)st->step, 0, 0, omega, tau, w, eps_u, eps_j, stream))) return rc;
+    if ((rc = vgpmp_rng_fill_lazy(h, dims, seed, (uint64_t)st->step, problem_offset, 0, omega, tau, w, eps_u, eps_j, stream))) return rc;
   } else if (pipelined && h->prefetched_step == (int64_t)st->step && h->prefetched_seed == seed) {
     if ((rc = vgpmp_rng_join(h, slot, stream))) return rc;
   } else {
-    if ((rc = vgpmp_rng_fill(h, dims, seed, (uint64_t)st->step, 0, 0, omega, tau, w, eps_u, eps_j, stream))) return rc;
+    if ((rc = vgpmp_rng_fill(h, dims, seed, (uint64_t)st->step, problem_offset, 0, omega, tau, w, eps_u, eps_j, stream))) return rc;
   }
   vgpmp_params p{st->q_mu, st->q_sqrt, st->lengthscales, st->variances, query_latent, Z, X_dev};
   vgpmp_draws r{omega, tau, w, eps_u, eps_j};
@@ -531,15 +531,32 @@ int vgpmp_train_step_host(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* s
   if (pipelined && !lazy_ok) {
     if ((rc = vgpmp_rng_release(h, slot, stream))) return rc;
     carve_set(slot ^ 1);
-    if ((rc = vgpmp_rng_fill_async(h, dims, seed, (uint64_t)st->step, 0, 0, omega, tau, w, eps_u, eps_j, slot ^ 1))) return rc;
+    if ((rc = vgpmp_rng_fill_async(h, dims, seed, (uint64_t)st->step, problem_offset, 0, omega, tau, w, eps_u, eps_j, slot ^ 1))) return rc;
     h->prefetched_step = st->step;
     h->prefetched_seed = seed;
   }
   if ((rc = check_cuda(h, cudaMemcpyAsync(loss_host, elbo_dev, sizeof(double) * Bp, cudaMemcpyDeviceToHost, s), "D2H loss")))
     return rc;
-  if ((rc = check_cuda(h, cudaStreamSynchronize(s), "sync"))) return rc;
-  for (size_t i = 0; i < Bp; ++i) loss_host[i] = -loss_host[i];  // training_loss = -ELBO
+  return VGPMP_OK;   // the loss copy is in flight: vgpmp_train_step_host_end waits for it
+}
+
+int vgpmp_train_step_host_end(vgpmp_handle* h, const vgpmp_dims* dims, double* loss_host, void* stream) {
+  int rc = check_dims(h, dims);
+  if (rc) return rc;
+  if (!loss_host) return fail(h, VGPMP_ERR_INVALID, "train_step_host_end: bad argument");
+  if ((rc = check_cuda(h, cudaStreamSynchronize((cudaStream_t)stream), "sync"))) return rc;
+  for (int i = 0; i < dims->num_problems; ++i) loss_host[i] = -loss_host[i];  // training_loss = -ELBO
   return VGPMP_OK;
+}
+
+int vgpmp_train_step_host(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* st, const double* query_latent,
+                          const double* Z, const double* X_host, double* X_dev, uint64_t seed, double* draws_ws,
+                          size_t draws_bytes, const vgpmp_grads* g, double* elbo_dev, double* loss_host, void* ws,
+                          size_t ws_bytes, void* stream) {
+  int rc = vgpmp_train_step_host_begin(h, dims, st, query_latent, Z, X_host, X_dev, seed, 0, draws_ws, draws_bytes, g,
+                                       elbo_dev, loss_host, ws, ws_bytes, stream);
+  if (rc) return rc;
+  return vgpmp_train_step_host_end(h, dims, loss_host, stream);
 }
 
 }  // extern "C"

@@ -53,6 +53,7 @@ class VGPMP:
         self.num_latent_gps = D = int(num_latent_gps)
         self.num_samples, self.num_bases, self.num_inducing = int(num_samples), int(num_bases), int(num_inducing)
         self.lazy_draws = True      # train_step: draws generated inside the sampler kernel (vgpmp_rng_fill_lazy)
+        self.problem_offset = 0     # global index of this model's first problem (Philox keys use global problem indices)
         self.num_data, self.prior, self.seed = num_data, prior, int(seed)
         self.optimizer = AdamConfig(learning_rate)
         self.alpha = float(alpha)
@@ -226,7 +227,7 @@ class VGPMP:
         if self._draw_buf is None or self._draw_buf[0] != key:
             self._draw_buf = (key, eng.alloc_draws(dims))
         off = self._shard["offset"] if (self._shard is not None and dims.total_samples > 0) else 0
-        return eng.rng_fill(dims, self.seed, self._step, self._draw_buf[1], sample_offset=off)
+        return eng.rng_fill(dims, self.seed, self._step, self._draw_buf[1], problem_offset=self.problem_offset, sample_offset=off)
 
     # ---- reference API ---------------------------------------------------------------------------
     def elbo(self, data, draws=None):
@@ -279,13 +280,15 @@ class VGPMP:
             soff = self._shard["offset"] if self._shard is not None else 0
             if self.lazy_draws:
                 # omega / tau / w are generated inside the sampler kernel from the same Philox keys: nothing to prefetch
-                eng.rng_fill_lazy(dims, self.seed, self._step, self._pipe["sets"][0], sample_offset=soff)
+                eng.rng_fill_lazy(dims, self.seed, self._step, self._pipe["sets"][0], problem_offset=self.problem_offset,
+                                  sample_offset=soff)
                 use, slot = self._pipe["sets"][0], None
             else:
                 if self._pipe["ready"] == self._step:
                     eng.rng_join(slot)
                 else:
-                    eng.rng_fill(dims, self.seed, self._step, self._pipe["sets"][slot], sample_offset=soff)
+                    eng.rng_fill(dims, self.seed, self._step, self._pipe["sets"][slot], problem_offset=self.problem_offset,
+                                 sample_offset=soff)
                 use = self._pipe["sets"][slot]
         else:
             use = self._make_draws(dims, draws)
@@ -299,6 +302,7 @@ class VGPMP:
         if slot is not None:
             eng.rng_release(slot)
             eng.rng_fill_async(dims, self.seed, self._step + 1, self._pipe["sets"][slot ^ 1], slot ^ 1,
+                               problem_offset=self.problem_offset,
                                sample_offset=self._shard["offset"] if self._shard is not None else 0)
             self._pipe["ready"] = self._step + 1
         gs = _cabi.Grads(out["d_q_mu"].data_ptr(), out["d_q_sqrt"].data_ptr(), out["d_lengthscales"].data_ptr(),
@@ -309,7 +313,7 @@ class VGPMP:
         self._grads = out
         return self._squeeze(-out["elbo"])
 
-    def train_step_host(self, X_host: torch.Tensor):
+    def train_step_host(self, X_host: torch.Tensor, wait: bool = True):
         """The same optimisation step driven from HOST buffers through `vgpmp_train_step_host`: X [N,D] is read from
         (pinned) host memory, copied to the device, the step's randomness is drawn on the device, and loss = -ELBO [Bp]
         is copied back to pinned host memory before the call returns (like `loss = tf_optimization_step(...)` feeding
@@ -334,12 +338,23 @@ class VGPMP:
                          g["d_variances"].data_ptr())
         st = self._adam_struct()
         ws = eng.workspace(dims)
-        eng._chk(eng.lib.vgpmp_train_step_host(eng.h, C.byref(dims), C.byref(st), self._query_states.data_ptr(),
-                                               self._Z.data_ptr(), X_host.data_ptr(), hs["X_dev"].data_ptr(),
-                                               self.seed, hs["draws"].data_ptr(), hs["draws"].numel(), C.byref(gs),
-                                               hs["elbo"].data_ptr(), hs["loss"].data_ptr(), ws.data_ptr(), ws.numel(),
-                                               eng._stream()), "train_step_host")
+        eng._chk(eng.lib.vgpmp_train_step_host_begin(eng.h, C.byref(dims), C.byref(st), self._query_states.data_ptr(),
+                                                     self._Z.data_ptr(), X_host.data_ptr(), hs["X_dev"].data_ptr(),
+                                                     self.seed, int(self.problem_offset), hs["draws"].data_ptr(),
+                                                     hs["draws"].numel(), C.byref(gs), hs["elbo"].data_ptr(),
+                                                     hs["loss"].data_ptr(), ws.data_ptr(), ws.numel(), eng._stream()),
+                 "train_step_host_begin")
         self._step = st.step
+        hs["dims"], hs["stream"] = dims, eng._stream()
+        if not wait:
+            return None
+        return self.train_step_host_wait()
+
+    def train_step_host_wait(self):
+        """Second half of `train_step_host(..., wait=False)`: blocks until the loss of the step in flight is in host memory."""
+        eng, hs = self._eng, self._host_state
+        eng._chk(eng.lib.vgpmp_train_step_host_end(eng.h, C.byref(hs["dims"]), hs["loss"].data_ptr(), hs["stream"]),
+                 "train_step_host_end")
         return hs["loss"]
 
     def predict_f_samples(self, X, num_samples=None, draws=None):
