@@ -275,7 +275,10 @@ class VGPMP:
             # device draws, double-buffered: this step's set was generated on the side stream during the previous step
             key = (dims.num_problems, dims.num_samples, dims.num_bases, dims.total_samples)
             if self._pipe is None or self._pipe["key"] != key:
-                self._pipe = dict(key=key, sets=[eng.alloc_draws(dims), eng.alloc_draws(dims)], ready=None)
+                # lazy draws need one set (of which only eps_u / eps_j are ever written); the prefetch pipeline needs two
+                self._pipe = dict(key=key, sets=[eng.alloc_draws(dims)], ready=None)
+            if not self.lazy_draws and len(self._pipe["sets"]) < 2:
+                self._pipe["sets"].append(eng.alloc_draws(dims))
             slot = self._step & 1
             soff = self._shard["offset"] if self._shard is not None else 0
             if self.lazy_draws:
