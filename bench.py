@@ -351,7 +351,7 @@ def run_b200(args):
                               "{value,gradient} records in HBM (the reference's own .sdf grids are missing blobs)",
                        "rng": "device Philox4x32-10, fresh draws every step (lazy: generated inside the sampler kernel)",
                        "streams": args.streams,
-                       "l2": "inputs larger than L2 (draws + SDF grid > 126 MB per step); no explicit flush"},
+                       "l2": "no explicit flush: every step streams its whole working set, which exceeds the 126 MB L2 (86 MiB of SDF records + ~110 MB of GP factors, prior draws, samples, gradients and Adam state; omega/tau/w are generated in-kernel and never stored)"},
             "sdf_evals_per_s": world * evals_per_step * args.steps / (ms / 1000.0),
             "e2e": {"value": world * Bp * args.steps / (ms_e2e / 1000.0), "unit": UNIT,
                     "h2d_bytes_per_step": int(X.nbytes) * max(args.streams, 1), "d2h_bytes_per_step": int(Bp * 8),
