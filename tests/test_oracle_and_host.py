@@ -220,6 +220,13 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert b"sm_100a" in _cabi.load().vgpmp_version()
+    # and the ctypes table agrees with the header on every prototype's arity (catches ABI drift on the Python side)
+    protos = re.findall(r"\b(vgpmp_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", re.sub(r"/\*.*?\*/", "", header, flags=re.S))
+    assert {n for n, _ in protos} == declared
+    for name, args in protos:
+        args = " ".join(args.split())
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        assert n == len(_cabi.SYMBOLS[name][1]), (name, n, len(_cabi.SYMBOLS[name][1]))
 
 
 def test_product_fails_loudly_without_gpu():
