@@ -148,6 +148,14 @@ typedef struct {
 /* ---- lifetime ------------------------------------------------------------------------------- */
 int vgpmp_create(vgpmp_handle** out, int device, const vgpmp_robot_desc* robot, const vgpmp_sdf_desc* sdf,
                  const vgpmp_lik_desc* lik);
+/* A second handle on the SAME device-resident SDF records as `src` (ref-counted: the 4x-grid-size record array exists once
+ * per device and is released with the last handle that uses it).  `robot` and `lik` (each NULL = src's) let the new handle
+ * carry its own robot / likelihood constants.  For callers that drive sub-batches of problems on their own streams
+ * (the reference builds ONE SignedDistanceField per environment: utils/simulation_manager.py:45-58). */
+int vgpmp_create_shared(vgpmp_handle** out, const vgpmp_handle* src, const vgpmp_robot_desc* robot,
+                        const vgpmp_lik_desc* lik);
+/* identity of the record array a handle reads (equal for handles that share it; tests / diagnostics) */
+uint64_t vgpmp_sdf_records_id(const vgpmp_handle* h);
 int vgpmp_destroy(vgpmp_handle* h);
 const char* vgpmp_last_error(const vgpmp_handle* h); /* NULL handle -> last create() error */
 const char* vgpmp_version(void);
@@ -208,7 +216,12 @@ int vgpmp_rng_fill(vgpmp_handle* h, const vgpmp_dims* dims, uint64_t seed, uint6
  * (seed, iteration, offsets) and the buffers.  The next vgpmp_elbo_fwd_bwd / vgpmp_pathwise_sample that is handed exactly
  * these buffers either generates the values inside the sampler kernel (equispaced rank-1 inputs: they never touch memory)
  * or writes them into the buffers right before the first kernel that has to read them.  Values are bit-identical to
- * vgpmp_rng_fill.  The contents of omega / tau / w are unspecified for the caller afterwards.  Replaces the per-step
+ * vgpmp_rng_fill.  The contents of omega / tau / w are unspecified for the caller afterwards.  The remembered key is
+ * one-shot: the next vgpmp_elbo_fwd_bwd / vgpmp_pathwise_sample consumes it whatever buffers it is given.
+ * omega = tau = w = NULL is allowed ("never materialise", nothing of size Bp*D*S*B is ever allocated): the consumer must
+ * then be handed NULL for the three as well, and X / Z must be the equispaced rank-1 grids of the reference with
+ * N + M + 2 within the in-kernel generating samplers' range (96 points, or 112 with >= 64 samples); if the device-side
+ * probe finds otherwise the sample paths, the ELBO and all gradients come out NaN.  Replaces the per-step
  * random_fourier / exact_update draws of GPflowSampling inside tf_optimization_step (utils/miscellaneous.py:68-84). */
 int vgpmp_rng_fill_lazy(vgpmp_handle* h, const vgpmp_dims* dims, uint64_t seed, uint64_t iteration, int64_t problem_offset,
                         int64_t sample_offset, double* omega, double* tau, double* w, double* eps_u, double* eps_j,
@@ -247,6 +260,11 @@ int vgpmp_train_step_host_begin(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_a
                                 double* loss_host, void* ws, size_t ws_bytes, void* stream);
 int vgpmp_train_step_host_end(vgpmp_handle* h, const vgpmp_dims* dims, double* loss_host, void* stream);
 size_t vgpmp_draws_bytes(const vgpmp_dims* dims, int dof);
+/* 1 when, for equispaced rank-1 inputs of this shape (num_timesteps = number of query points), the sampler generates omega /
+ * tau / w inside the kernel, i.e. vgpmp_rng_fill_lazy may be given NULL for them */
+int vgpmp_sampler_generates_draws(const vgpmp_handle* h, const vgpmp_dims* dims);
+/* eps_u / eps_j only: a draws_ws of this size makes vgpmp_train_step_host[_begin] use lazy draws that are never materialised */
+size_t vgpmp_draws_bytes_lazy(const vgpmp_dims* dims, int dof);
 
 /* ---- SDF producer (replaces the external SDFGen binary driven by gpflow_vgpmp/utils/gen_sdf.py:16-43) ---------------
  * Exact distance from every grid node origin + (i,j,k)*delta to a triangle soup made of CONVEX pieces, negative inside
@@ -269,13 +287,14 @@ double vgpmp_probe_fp64_tflops(int device);
 /* Tuning switches (default on unless noted; every combination is covered by the parity tests).
  *   "grid_fast_path"  X and Z rank-1 equispaced grids (always true for the reference's init_trainset / initialize_Z): the
  *                     Fourier features come from rotation recurrences; 0 forces the general per-point sincos kernel.
- *   "dmma_sampler"    contraction of the equispaced sampler on the FP64 tensor path (DMMA m8n8k4); 0 = FMA contraction.
+ *   "tc_sampler"      num_samples >= 64 and N + M + 2 <= 112: the Fourier contraction runs on the 5th-generation tensor cores
+ *                     (tcgen05.mma kind::tf32 as a 3-pass hi/lo split, FP32 partial sums in TMEM folded every 64 bases);
+ *                     float32-class accuracy, gated by the tolerance tests (ELBO 1e-4, gradients 1e-3).  0 = float64 DMMA.
  *   "rr_sampler"      register-resident warp-specialised DMMA sampler (points must fit 12 tiles of 8 rows, e.g. N=70, M=24);
  *                     0 = the variant that passes the features through shared memory.
- *   "split_tail"      the sampler stops at the prior draw; GP preparation + pathwise update run in their own kernel.
+ *   "dmma_sampler"    shared-memory DMMA sampler for up to 192 points; 0 = the general kernel takes those shapes.
  *   "lazy_draws"      vgpmp_rng_fill_lazy / vgpmp_train_step_host leave omega, tau, w to be generated inside the sampler;
- *                     0 = always materialise them (vgpmp_train_step_host then prefetches the next step's set instead).
- *   "warp_sampler"    experimental warp-synchronous sampler (default off). */
+ *                     0 = always materialise them (vgpmp_train_step_host then prefetches the next step's set instead). */
 int vgpmp_set_option(vgpmp_handle* h, const char* name, int value);
 #define VGPMP_NUM_STAGES 7
 int vgpmp_profile_enable(vgpmp_handle* h, int on);

@@ -153,21 +153,26 @@ def test_gp_prepare_chol_qsqrt_kl_vs_oracle(M):
     assert abs(got - klo) <= 1e-7 * abs(klo)
 
 
-@pytest.mark.parametrize("grid", [5, 3, 4, 2, 0])
+def _select_sampler(eng, grid):
+    """grid=5: register-resident warp-specialised DMMA sampler (the float64 default when the points fit 12 row tiles);
+    grid=3: shared-memory DMMA sampler (up to 192 points, else the general kernel); grid=0: general per-point sincos
+    kernel.  All three are float64 and stop at the prior draw; preparation + pathwise update run in their own kernel.
+    The tensor-core (3xTF32) sampler is switched off here: it has its own tolerance-gated tests."""
+    eng.set_option("tc_sampler", 0)
+    eng.set_option("grid_fast_path", int(grid > 0))
+    eng.set_option("dmma_sampler", int(grid >= 3))
+    eng.set_option("rr_sampler", int(grid == 5))
+
+
+@pytest.mark.parametrize("grid", [5, 3, 0])
 @pytest.mark.parametrize("S,N,M,B", [(7, 70, 24, 64), (3, 5, 1, 3), (20, 50, 7, 40), (9, 150, 12, 33), (8, 2, 2, 32),
                                      (17, 300, 30, 70), (203, 12, 5, 16), (7, 70, 24, 1024), (5, 150, 30, 100)])
 def test_pathwise_sample_vs_oracle(S, N, M, B, grid):
-    """grid=5: equispaced fast path, register-resident warp-specialised DMMA sampler (default when the points fit 12 row
-    tiles, else grid=3); grid=3: shared-memory DMMA sampler, preparation + pathwise update in their own kernel
-    (N+M+2 <= 192, else the FMA kernel); grid=4: same sampler with the update fused into its tail;
-    grid=2: equispaced fast path, FMA contraction; grid=0: general per-point sincos kernel.
-    (203, 12, 5, 16): samples split over several CTAs."""
+    """(203, 12, 5, 16): samples split over several CTAs; (17, 300, 30, 70): too many points for either equispaced
+    sampler, the general kernel takes it."""
     case = H.make_case(num_problems=2, S=S, N=N, M=M, B=B, seed=S + N)
     model = H.make_model(case)
-    model._eng.set_option("grid_fast_path", int(grid > 0))
-    model._eng.set_option("dmma_sampler", int(grid >= 3))
-    model._eng.set_option("split_tail", int(grid in (3, 5)))
-    model._eng.set_option("rr_sampler", int(grid == 5))
+    _select_sampler(model._eng, grid)
     f = _np(model.predict_f_samples(case["X"], draws=case["draws_stacked"]))
     for b, p in enumerate(case["oracle"]):
         want = p.sample_paths(p.X, O._t(case["q_mu"][b]), O._t(case["q_sqrt"][b]), O._t(case["ls"][b]),
@@ -207,19 +212,13 @@ def test_pathwise_sample_irregular_inputs_fall_back_to_general_kernel():
     ("kuka", "industrial", dict(B=96)),                           # config 3 shapes: S=20, N=50, M=7
     ("ur10", "bookshelves", dict(B=64, S=33)),                    # config 4 robot (D=6), more samples than one tile
 ])
-@pytest.mark.parametrize("grid", [5, 3, 4, 1, 2, 0])
+@pytest.mark.parametrize("grid", [5, 3, 0])
 def test_elbo_and_gradients_vs_oracle(name, env, kw, grid):
-    """grid: 5 = register-resident warp-specialised DMMA sampler (default), 3 = shared-memory DMMA sampler + split
-    preparation/update kernel, 4 = DMMA sampler
-    with the fused tail, 1 = warp-synchronous equispaced sampler, 2 = equispaced sampler with the FMA contraction,
-    0 = general sincos sampler."""
+    """grid: 5 = register-resident warp-specialised DMMA sampler (default), 3 = shared-memory DMMA sampler,
+    0 = general sincos sampler (see _select_sampler)."""
     case = H.make_case(name, env, num_problems=2, seed=4, **kw)
     model = H.make_model(case)
-    model._eng.set_option("grid_fast_path", int(grid > 0))
-    model._eng.set_option("warp_sampler", int(grid == 1))
-    model._eng.set_option("dmma_sampler", int(grid >= 3))
-    model._eng.set_option("split_tail", int(grid in (3, 5)))
-    model._eng.set_option("rr_sampler", int(grid == 5))
+    _select_sampler(model._eng, grid)
     out = model.elbo_and_grads(case["X"], draws=case["draws_stacked"], want_aux=True)
     for b, p in enumerate(case["oracle"]):
         ref = O.elbo_and_grads(p, case["q_mu"][b], case["q_sqrt"][b], case["ls"][b], case["var"][b], case["draws"][b])
@@ -471,15 +470,136 @@ def test_single_problem_many_samples_split_reverse_pass_vs_oracle():
 
 
 def test_config5_shapes_vs_oracle():
-    """BASELINE config 5 shapes (S=256 samples, N=64 timesteps, B=1024 bases) on two problems: 32 sample tiles per latent."""
+    """BASELINE config 5 shapes (S=256 samples, N=64 timesteps, B=1024 bases) on two problems, float64 samplers (the
+    tensor-core sampler that takes this shape by default has its own tolerance-gated tests below)."""
     case = H.make_case("franka", "bookshelves", num_problems=2, S=256, N=64, B=1024, seed=55)
     model = H.make_model(case)
+    model._eng.set_option("tc_sampler", 0)
     out = model.elbo_and_grads(case["X"], draws=case["draws_stacked"])
     for b, p in enumerate(case["oracle"]):
         ref = O.elbo_and_grads(p, case["q_mu"][b], case["q_sqrt"][b], case["ls"][b], case["var"][b], case["draws"][b])
         assert abs(float(out["elbo"][b]) - ref["elbo"]) <= 1e-8 * abs(ref["elbo"])
         for key in ("q_mu", "q_sqrt", "lengthscales", "variances"):
             assert H.rel_err(_np(out["d_" + key][b]), ref["d_" + key]) < 1e-5, key
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core sampler
+# tcgen05 / TMEM 3xTF32 sampler (csrc/sampler_tc.cu): float32-class arithmetic, so these tests gate it on BASELINE.json's
+# tolerances (ELBO 1e-4, gradients 1e-3 relative) instead of the 1e-8 the float64 samplers reach, and report how many
+# (sample, timestep) cells moved to another voxel.
+@pytest.mark.parametrize("name,S,N,M,B", [("franka", 128, 64, 24, 1024), ("franka", 256, 64, 24, 1024),
+                                          ("ur10", 150, 70, 12, 256), ("kuka", 64, 50, 7, 96), ("franka", 200, 12, 5, 64)])
+def test_tc_sampler_paths_vs_oracle(name, S, N, M, B):
+    """Latent sample paths from explicit draws: ragged sample blocks (150, 200), a partial last basis stage (B=96),
+    points that need padding to a multiple of 16."""
+    case = H.make_case(name, "bookshelves", num_problems=2, S=S, N=N, M=M, B=B, seed=S + N)
+    model = H.make_model(case)
+    f = _np(model.predict_f_samples(case["X"], draws=case["draws_stacked"]))
+    model._eng.set_option("tc_sampler", 0)
+    f64 = _np(model.predict_f_samples(case["X"], draws=case["draws_stacked"]))
+    assert not np.array_equal(f, f64), "the tensor-core sampler did not run"
+    for b, p in enumerate(case["oracle"]):
+        want = p.sample_paths(p.X, O._t(case["q_mu"][b]), O._t(case["q_sqrt"][b]), O._t(case["ls"][b]),
+                              O._t(case["var"][b]), case["draws"][b]).numpy()
+        assert H.rel_err(f64[b], want) < 1e-7
+        err = np.abs(f[b] - want).max()
+        print(f"tc sampler {name} S={S} N={N} M={M} B={B}: max|df| = {err:.2e} (scale {np.abs(want).max():.2f})")
+        assert err < 2e-5, err             # joint-angle error of a sample path, radians
+
+
+@pytest.mark.parametrize("name,env,S,N,B", [("franka", "bookshelves", 256, 64, 1024), ("ur10", "bookshelves", 192, 70, 512)])
+def test_tc_sampler_elbo_and_gradients_within_north_star_tolerances(name, env, S, N, B):
+    """The fused iteration with the tensor-core sampler (config-5 and config-4 shapes) against the float64 oracle."""
+    case = H.make_case(name, env, num_problems=2, S=S, N=N, B=B, seed=55)
+    model = H.make_model(case)
+    out = model.elbo_and_grads(case["X"], draws=case["draws_stacked"], want_aux=True)
+    for b, p in enumerate(case["oracle"]):
+        ref = O.elbo_and_grads(p, case["q_mu"][b], case["q_sqrt"][b], case["ls"][b], case["var"][b], case["draws"][b])
+        moved = np.abs(_np(out["logp"][b]) - ref["logp"]) > 1e-3 * np.abs(ref["logp"]).max()
+        rel_elbo = abs(float(out["elbo"][b]) - ref["elbo"]) / abs(ref["elbo"])
+        errs = {k: H.rel_err(_np(out["d_" + k][b]), ref["d_" + k]) for k in ("q_mu", "q_sqrt", "lengthscales", "variances")}
+        print(f"tc sampler {name} S={S}: max|df| {np.abs(_np(out['f'][b]) - ref['f']).max():.2e}, ELBO rel {rel_elbo:.2e}, "
+              f"grads {errs}, cells with a changed voxel {int(moved.sum())} of {moved.size}")
+        assert rel_elbo <= 1e-4
+        for k, e in errs.items():
+            assert e < 1e-3, (k, e)
+        assert moved.mean() < 2e-3
+
+
+def test_tc_sampler_lazy_draws_follow_the_materialised_keys():
+    """In-kernel draws of the tensor-core sampler use the keys of `vgpmp_rng_fill`: a lazy step (no omega / tau / w buffers
+    at all) must agree, to float32 class, with the float64 samplers run on the materialised draws of the same (seed, step)."""
+    case = H.make_case("franka", "bookshelves", num_problems=3, S=128, N=64, B=256, seed=9)
+    a = H.make_model(case, seed=77)
+    b = H.make_model(case, seed=77)
+    b._eng.set_option("tc_sampler", 0)
+    b.lazy_draws = False
+    la, lb = a.train_step(case["X"]), b.train_step(case["X"])
+    assert a._pipe["sets"][0]["w"] is None, "lazy draws must not allocate omega / tau / w"
+    assert H.rel_err(_np(la), _np(lb)) < 1e-4
+    for k in ("d_q_mu", "d_q_sqrt", "d_lengthscales", "d_variances"):
+        assert H.rel_err(_np(a._grads[k]), _np(b._grads[k])) < 1e-3, k
+
+
+def test_null_draw_buffers_with_irregular_inputs_fail_loudly():
+    """Lazy draws without buffers can only be consumed by an in-kernel generating sampler; if the device-side probe finds the
+    inputs not to be the reference's equispaced grids, the result must be NaN, not garbage."""
+    case = H.make_case(num_problems=2, S=7, N=30, M=8, B=64, seed=3)
+    model = H.make_model(case, seed=1)
+    eng = model._eng
+    X = eng.dev(np.sort(np.random.default_rng(0).uniform(0, 1, size=(30, 1)), axis=0) * np.ones((1, 7)))
+    dims = model._dims(30)
+    draws = eng.rng_fill_lazy(dims, 1, 0, eng.alloc_draws(dims, lazy_only=True))
+    out = eng.elbo_fwd_bwd(dims, model._params(X), draws, need_grad=True)
+    assert torch.isnan(out["elbo"]).all()
+    # the model-level step notices the irregular inputs on the host and allocates the buffers instead
+    loss = model.train_step(X)
+    assert torch.isfinite(loss).all()
+
+
+def test_chunked_training_step_is_bit_identical_to_the_unchunked_one():
+    """Batches larger than `max_workspace_bytes` run as consecutive problem chunks (BASELINE config 5 on one GPU)."""
+    case = H.make_case(num_problems=7, S=7, N=30, M=8, B=64, seed=4)
+    one, many = H.make_model(case, seed=5), H.make_model(case, seed=5)
+    whole, _ = one._plan(one._eng.dev(case["X"]), False)
+    assert whole == [(0, 7)]
+    many.max_workspace_bytes = 1                          # -> one problem per launch
+    chunks, _ = many._plan(many._eng.dev(case["X"]), False)
+    assert chunks == [(i, i + 1) for i in range(7)]
+    for _ in range(3):
+        la, lb = one.train_step(case["X"]), many.train_step(case["X"])
+        assert torch.equal(la, lb)
+    for k in ("_q_mu", "_q_sqrt", "_lengthscales", "_variances"):
+        assert torch.equal(getattr(one, k), getattr(many, k)), k
+
+
+def test_sdf_records_exist_once_per_device():
+    """StreamedVGPMP sub-models, a model with another alpha and the SignedDistanceField object all read ONE record array."""
+    from vgpmp_b200.models import StreamedVGPMP, VGPMP
+    from vgpmp_b200.utils.robot import Robot
+    from vgpmp_b200.utils.sampler import Sampler
+    from vgpmp_b200.utils.sdf_utils import synthetic_shelf_sdf
+    sdf = synthetic_shelf_sdf(shape=(160, 160, 160), delta=0.016, origin=(-1.28, -1.28, -1.28), seed=1)   # 125 MiB of records
+    case = H.make_case(num_problems=4, S=7, N=30, M=8, B=64, seed=23, perturb=False, sdf=sdf)
+    pp = dict(case["pp"])
+    pp.update(num_samples=case["S"], num_inducing=case["M"])
+    robot = Robot.from_tables(case["name"], case["env"])
+    q = np.stack([np.stack(qq) for qq in case["queries"]])
+    kw = dict(sdf=sdf, robot=robot, sampler=Sampler(None, robot), scene_offset=case["ps"]["scene_offset"],
+              num_bases=case["B"], seed=5, **pp)
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    many = StreamedVGPMP.initialize(query_states=q, num_streams=4, **kw)
+    other = VGPMP.initialize(query_states=q, share_engine=many.models[0]._eng, **dict(kw, alpha=3.0))
+    torch.cuda.synchronize()
+    used = free0 - torch.cuda.mem_get_info()[0]
+    rec_bytes = sdf.data.nbytes * 4
+    ids = {m._eng.sdf_records_id for m in many.models} | {other._eng.sdf_records_id, sdf._eng().sdf_records_id}
+    assert len(ids) == 1
+    assert used < 2.0 * rec_bytes, (used, rec_bytes)       # one copy (+ raw-grid staging and model state), not six
+    assert other._eng.alpha == 3.0 and many.models[0]._eng.alpha == case["pp"]["alpha"]
+    many.train_step(case["X"])
+    del many, other
 
 
 def test_full_size_batch_properties():

@@ -62,6 +62,8 @@ class Adam(C.Structure):
 _P, _I, _I64, _U64, _D, _SZ = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double, C.c_size_t
 SYMBOLS = {
     "vgpmp_create": (_I, [C.POINTER(_P), _I, C.POINTER(RobotDesc), C.POINTER(SdfDesc), C.POINTER(LikDesc)]),
+    "vgpmp_create_shared": (_I, [C.POINTER(_P), _P, C.POINTER(RobotDesc), C.POINTER(LikDesc)]),
+    "vgpmp_sdf_records_id": (_U64, [_P]),
     "vgpmp_destroy": (_I, [_P]),
     "vgpmp_last_error": (C.c_char_p, [_P]),
     "vgpmp_version": (C.c_char_p, []),
@@ -91,6 +93,8 @@ SYMBOLS = {
                                          C.POINTER(Grads), _P, _P, _P, _SZ, _P]),
     "vgpmp_train_step_host_end": (_I, [_P, C.POINTER(Dims), _P, _P]),
     "vgpmp_draws_bytes": (_SZ, [C.POINTER(Dims), _I]),
+    "vgpmp_draws_bytes_lazy": (_SZ, [C.POINTER(Dims), _I]),
+    "vgpmp_sampler_generates_draws": (_I, [_P, C.POINTER(Dims)]),
     "vgpmp_mesh_to_sdf": (_I, [_I, c_double_p, c_double_p, c_int32_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.c_int32, c_double_p, _D, c_double_p]),
     "vgpmp_probe_fp64_tflops": (_D, [_I]),

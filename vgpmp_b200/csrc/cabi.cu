@@ -79,10 +79,43 @@ GpScratch carve(void* ws, int D, const vgpmp_dims& d, size_t* total, int num_sms
   g.df = c.take(Bp * S * N * D);
   g.logp = c.take(Bp * S * N);
   g.meta = c.take(8);
+  g.loss = c.take(Bp);
   const size_t np = backward_partial_doubles(num_sms, (int)(Bp * D), (int)S);
   g.partial = np ? c.take(np) : nullptr;
   *total = c.off;
   return g;
+}
+
+// Sampler.__init__ constants -> the by-value kernel parameter block; returns an error text or nullptr
+const char* fill_robot(RobotDev& r, const vgpmp_robot_desc* robot) {
+  if (robot->dof < 1 || robot->dof > VGPMP_MAX_DOF) return "dof must be in 1..8";
+  if (robot->num_spheres < 1 || robot->num_spheres > VGPMP_MAX_SPHERES) return "num_spheres must be in 1..64";
+  std::memset(&r, 0, sizeof(r));
+  r.dof = robot->dof; r.craig = robot->craig ? 1 : 0; r.num_spheres = robot->num_spheres;
+  for (int j = 0; j < r.dof; ++j) {
+    for (int k = 0; k < 3; ++k) r.dh[j][k] = robot->dh[3 * j + k];
+    r.cos_alpha[j] = std::cos(r.dh[j][2]);
+    r.sin_alpha[j] = std::sin(r.dh[j][2]);
+    r.twist[j] = robot->twist[j];
+    r.lo[j] = robot->limits_lo[j];
+    r.hi[j] = robot->limits_hi[j];
+  }
+  for (int i = 0; i < 12; ++i) r.base[i] = robot->base_pose[i];
+  int prev = 0;
+  for (int p = 0; p < r.num_spheres; ++p) {
+    const int fr = robot->sphere_frame[p];
+    if (fr < prev || fr > r.dof) return "sphere_frame must be non-decreasing and within 0..dof";
+    prev = fr;
+    r.sphere_frame[p] = fr;
+    for (int k = 0; k < 3; ++k) r.sphere_off[p][k] = robot->sphere_offsets[3 * p + k];
+    r.sphere_rad[p] = robot->sphere_radii[p];
+  }
+  for (int k = 0; k <= r.dof; ++k) {
+    int end = 0;
+    while (end < r.num_spheres && r.sphere_frame[end] <= k) ++end;
+    r.frame_end[k] = end;
+  }
+  return nullptr;
 }
 
 int check_dims(vgpmp_handle* h, const vgpmp_dims* d) {
@@ -136,34 +169,9 @@ int vgpmp_create(vgpmp_handle** out, int device, const vgpmp_robot_desc* robot, 
   if (!h) return fail(nullptr, VGPMP_ERR_INVALID, "out of host memory");
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
-  RobotDev& r = h->robot;
-  std::memset(&r, 0, sizeof(r));
-  r.dof = robot->dof; r.craig = robot->craig ? 1 : 0; r.num_spheres = robot->num_spheres;
-  for (int j = 0; j < r.dof; ++j) {
-    for (int k = 0; k < 3; ++k) r.dh[j][k] = robot->dh[3 * j + k];
-    r.cos_alpha[j] = std::cos(r.dh[j][2]);
-    r.sin_alpha[j] = std::sin(r.dh[j][2]);
-    r.twist[j] = robot->twist[j];
-    r.lo[j] = robot->limits_lo[j];
-    r.hi[j] = robot->limits_hi[j];
-  }
-  for (int i = 0; i < 12; ++i) r.base[i] = robot->base_pose[i];
-  int prev = 0;
-  for (int p = 0; p < r.num_spheres; ++p) {
-    const int fr = robot->sphere_frame[p];
-    if (fr < prev || fr > r.dof) {
-      delete h;
-      return fail(nullptr, VGPMP_ERR_INVALID, "sphere_frame must be non-decreasing and within 0..dof");
-    }
-    prev = fr;
-    r.sphere_frame[p] = fr;
-    for (int k = 0; k < 3; ++k) r.sphere_off[p][k] = robot->sphere_offsets[3 * p + k];
-    r.sphere_rad[p] = robot->sphere_radii[p];
-  }
-  for (int k = 0; k <= r.dof; ++k) {
-    int end = 0;
-    while (end < r.num_spheres && r.sphere_frame[end] <= k) ++end;
-    r.frame_end[k] = end;
+  if (const char* msg = fill_robot(h->robot, robot)) {
+    delete h;
+    return fail(nullptr, VGPMP_ERR_INVALID, msg);
   }
   h->lik.sigma_obs = lik->sigma_obs; h->lik.epsilon = lik->epsilon; h->lik.alpha = lik->alpha;
   h->lik.jitter = lik->jitter;
@@ -187,19 +195,57 @@ int vgpmp_create(vgpmp_handle** out, int device, const vgpmp_robot_desc* robot, 
     return fail(nullptr, VGPMP_ERR_CUDA, msg);
   }
   cudaFree(raw);
+  const int dev_of_records = device;
+  h->rec_owner = std::shared_ptr<double4>(h->rec_dev, [dev_of_records](double4* q) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(dev_of_records);
+    cudaFree(q);
+    cudaSetDevice(cur);
+  });
   h->sdf.rec = h->rec_dev;
   *out = h;
   return VGPMP_OK;
 }
 
+int vgpmp_create_shared(vgpmp_handle** out, const vgpmp_handle* src, const vgpmp_robot_desc* robot,
+                        const vgpmp_lik_desc* lik) {
+  if (!out || !src) return fail(nullptr, VGPMP_ERR_INVALID, "create_shared: null argument");
+  *out = nullptr;
+  if (lik && !(lik->sigma_obs > 0.0)) return fail(nullptr, VGPMP_ERR_INVALID, "sigma_obs must be > 0");
+  vgpmp_handle* h = new (std::nothrow) vgpmp_handle();
+  if (!h) return fail(nullptr, VGPMP_ERR_INVALID, "out of host memory");
+  h->device = src->device;
+  h->num_sms = src->num_sms;
+  h->robot = src->robot;
+  if (robot) {
+    if (const char* msg = fill_robot(h->robot, robot)) {
+      delete h;
+      return fail(nullptr, VGPMP_ERR_INVALID, msg);
+    }
+  }
+  h->sdf = src->sdf;
+  h->lik = src->lik;
+  h->rec_owner = src->rec_owner;     // one copy of the records per device, released with the last handle
+  h->rec_dev = src->rec_dev;
+  if (lik) {
+    h->lik.sigma_obs = lik->sigma_obs; h->lik.epsilon = lik->epsilon; h->lik.alpha = lik->alpha;
+    h->lik.jitter = lik->jitter;
+    for (int k = 0; k < 3; ++k) h->lik.offset[k] = lik->scene_offset[k];
+  }
+  *out = h;
+  return VGPMP_OK;
+}
+
+uint64_t vgpmp_sdf_records_id(const vgpmp_handle* h) { return h ? (uint64_t)(uintptr_t)h->rec_dev : 0; }
+
 int vgpmp_set_option(vgpmp_handle* h, const char* name, int value) {
   if (!h || !name) return fail(h, VGPMP_ERR_INVALID, "set_option: bad argument");
   if (std::strcmp(name, "grid_fast_path") == 0) { h->allow_grid_path = value != 0; return VGPMP_OK; }
   if (std::strcmp(name, "dmma_sampler") == 0) { h->allow_dmma_path = value != 0; return VGPMP_OK; }
-  if (std::strcmp(name, "split_tail") == 0) { h->allow_split_tail = value != 0; return VGPMP_OK; }
   if (std::strcmp(name, "rr_sampler") == 0) { h->allow_rr_path = value != 0; return VGPMP_OK; }
   if (std::strcmp(name, "lazy_draws") == 0) { h->allow_lazy_draws = value != 0; return VGPMP_OK; }
-  if (std::strcmp(name, "warp_sampler") == 0) { h->allow_warp_path = value != 0; return VGPMP_OK; }
+  if (std::strcmp(name, "tc_sampler") == 0) { h->allow_tc_path = value != 0; return VGPMP_OK; }
   return fail(h, VGPMP_ERR_INVALID, std::string("set_option: unknown option ") + name);
 }
 
@@ -242,7 +288,7 @@ int vgpmp_destroy(vgpmp_handle* h) {
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
   }
   if (h->side) cudaStreamDestroy(h->side);
-  if (h->rec_dev) cudaFree(h->rec_dev);
+  h->rec_owner.reset();
   delete h;
   return VGPMP_OK;
 }
@@ -252,6 +298,17 @@ size_t vgpmp_workspace_bytes(const vgpmp_handle* h, const vgpmp_dims* dims) {
   size_t total = 0;
   carve(nullptr, h->robot.dof, *dims, &total, h->num_sms);
   return total;
+}
+
+int vgpmp_sampler_generates_draws(const vgpmp_handle* h, const vgpmp_dims* dims) {
+  if (!h || !dims) return 0;
+  return sampler_generates_draws(h, *dims);
+}
+
+size_t vgpmp_draws_bytes_lazy(const vgpmp_dims* d, int dof) {
+  if (!d) return 0;
+  const size_t Bp = d->num_problems, D = dof, S = d->num_samples, Mp = d->num_inducing + 2;
+  return 2 * align_up(Bp * D * S * Mp * 8);
 }
 
 size_t vgpmp_draws_bytes(const vgpmp_dims* d, int dof) {
@@ -333,7 +390,7 @@ int vgpmp_gp_prepare(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_params
   // kl[p] = sum_l kl_l: reuse the ELBO reducer with an empty likelihood term
   vgpmp_dims d0 = *dims;
   d0.num_timesteps = 0;
-  return check_cuda(h, launch_elbo_reduce(h, d0, g.logp, g.kl_l, g.f0 /*scratch for -kl*/, kl, s), "kl_reduce");
+  return check_cuda(h, launch_elbo_reduce(h, d0, g.logp, g.kl_l, g.f0 /*scratch for -kl*/, kl, nullptr, s), "kl_reduce");
 }
 
 int vgpmp_pathwise_sample(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_params* p, const vgpmp_draws* r,
@@ -348,7 +405,7 @@ int vgpmp_pathwise_sample(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_p
   GpScratch g = carve(ws, h->robot.dof, dq, &need, h->num_sms);
   if (ws_bytes < need) return fail(h, VGPMP_ERR_WORKSPACE, "pathwise_sample: workspace too small (size it with num_timesteps = num_query)");
   cudaStream_t s = (cudaStream_t)stream;
-  return check_cuda(h, launch_pathwise(h, dq, *p, *r, Xq, num_query, g.Lc, g.Sfull, g.Linv, g.kl_l, g.kvec, f, nullptr, nullptr, nullptr, g.meta, s),
+  return check_cuda(h, launch_pathwise(h, dq, *p, *r, Xq, num_query, g.Lc, g.Sfull, g.Linv, g.kl_l, g.kvec, f, nullptr, g.f0, nullptr, g.meta, s),
                     "pathwise_sample");
 }
 
@@ -371,7 +428,7 @@ int vgpmp_elbo_fwd_bwd(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_para
     // GP preparation kernel + pathwise sampling kernels (one stage for the profile)
     StageSpan sp(h, ST_PATHWISE, s);
     if ((rc = check_cuda(h, launch_pathwise(h, *dims, *p, *r, p->X, dims->num_timesteps, g.Lc, g.Sfull, g.Linv, g.kl_l,
-                                            g.kvec, f, bwd ? g.v : nullptr, bwd ? g.f0 : nullptr, bwd ? g.h0 : nullptr,
+                                            g.kvec, f, bwd ? g.v : nullptr, g.f0, bwd ? g.h0 : nullptr,
                                             g.meta, s), "pathwise")))
       return rc;
   }
@@ -383,7 +440,7 @@ int vgpmp_elbo_fwd_bwd(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_para
   }
   {
     StageSpan sp(h, ST_REDUCE, s);
-    if ((rc = check_cuda(h, launch_elbo_reduce(h, *dims, logp, g.kl_l, elbo, aux ? aux->kl : nullptr, s), "elbo_reduce")))
+    if ((rc = check_cuda(h, launch_elbo_reduce(h, *dims, logp, g.kl_l, elbo, aux ? aux->kl : nullptr, g.loss, s), "elbo_reduce")))
       return rc;
   }
   if (bwd) {
@@ -425,7 +482,8 @@ int vgpmp_rng_fill_lazy(vgpmp_handle* h, const vgpmp_dims* dims, uint64_t seed, 
                         int64_t sample_offset, double* omega, double* tau, double* w, double* eps_u, double* eps_j,
                         void* stream) {
   if (!h) return VGPMP_ERR_INVALID;
-  if (!h->allow_lazy_draws || !omega || !tau || !w)
+  const bool no_buffers = !omega && !tau && !w;     // never materialised: only an in-kernel generating sampler can consume this set
+  if (!no_buffers && (!h->allow_lazy_draws || !omega || !tau || !w))
     return vgpmp_rng_fill(h, dims, seed, iteration, problem_offset, sample_offset, omega, tau, w, eps_u, eps_j, stream);
   int rc = check_dims(h, dims);
   if (rc) return rc;
@@ -496,8 +554,14 @@ int vgpmp_train_step_host_begin(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_a
   if (rc) return rc;
   if (!st || !query_latent || !Z || !X_host || !X_dev || !draws_ws || !g || !elbo_dev || !loss_host || !ws)
     return fail(h, VGPMP_ERR_INVALID, "train_step_host: bad argument");
+  if (dims->total_samples > 0 || dims->kl_shards > 1)
+    return fail(h, VGPMP_ERR_INVALID, "train_step_host: a sample-sharded step needs the all-reduce between the reverse pass and Adam; "
+                                      "drive it with vgpmp_elbo_fwd_bwd + vgpmp_adam_step");
   const int D = h->robot.dof;
-  if (draws_bytes < vgpmp_draws_bytes(dims, D)) return fail(h, VGPMP_ERR_WORKSPACE, "train_step_host: draws buffer too small");
+  // a buffer that only holds eps_u / eps_j (vgpmp_draws_bytes_lazy) selects lazy draws that are never materialised
+  const bool compact = draws_bytes < vgpmp_draws_bytes(dims, D);
+  if (compact && (draws_bytes < vgpmp_draws_bytes_lazy(dims, D) || !h->allow_lazy_draws))
+    return fail(h, VGPMP_ERR_WORKSPACE, "train_step_host: draws buffer too small");
   cudaStream_t s = (cudaStream_t)stream;
   const size_t Bp = dims->num_problems, B = dims->num_bases, S = dims->num_samples, Mp = dims->num_inducing + 2;
   if ((rc = check_cuda(h, cudaMemcpyAsync(X_dev, X_host, sizeof(double) * dims->num_timesteps * D, cudaMemcpyHostToDevice, s),
@@ -509,9 +573,9 @@ int vgpmp_train_step_host_begin(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_a
   double *omega, *tau, *w, *eps_u, *eps_j;
   auto carve_set = [&](int which) {
     Carver c(static_cast<char*>(static_cast<void*>(draws_ws)) + (size_t)which * one_set);
-    omega = c.take(Bp * D * B * D);
-    tau = c.take(Bp * D * B);
-    w = c.take(Bp * D * S * B);
+    omega = compact ? nullptr : c.take(Bp * D * B * D);
+    tau = compact ? nullptr : c.take(Bp * D * B);
+    w = compact ? nullptr : c.take(Bp * D * S * B);
     eps_u = c.take(Bp * D * S * Mp);
     eps_j = c.take(Bp * D * S * Mp);
   };
@@ -535,8 +599,12 @@ int vgpmp_train_step_host_begin(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_a
     h->prefetched_step = st->step;
     h->prefetched_seed = seed;
   }
-  if ((rc = check_cuda(h, cudaMemcpyAsync(loss_host, elbo_dev, sizeof(double) * Bp, cudaMemcpyDeviceToHost, s), "D2H loss")))
-    return rc;
+  {
+    size_t need = 0;
+    GpScratch gsc = carve(ws, D, *dims, &need, h->num_sms);   // loss = -ELBO was written by the ELBO reduction
+    if ((rc = check_cuda(h, cudaMemcpyAsync(loss_host, gsc.loss, sizeof(double) * Bp, cudaMemcpyDeviceToHost, s), "D2H loss")))
+      return rc;
+  }
   return VGPMP_OK;   // the loss copy is in flight: vgpmp_train_step_host_end waits for it
 }
 
@@ -544,9 +612,7 @@ int vgpmp_train_step_host_end(vgpmp_handle* h, const vgpmp_dims* dims, double* l
   int rc = check_dims(h, dims);
   if (rc) return rc;
   if (!loss_host) return fail(h, VGPMP_ERR_INVALID, "train_step_host_end: bad argument");
-  if ((rc = check_cuda(h, cudaStreamSynchronize((cudaStream_t)stream), "sync"))) return rc;
-  for (int i = 0; i < dims->num_problems; ++i) loss_host[i] = -loss_host[i];  // training_loss = -ELBO
-  return VGPMP_OK;
+  return check_cuda(h, cudaStreamSynchronize((cudaStream_t)stream), "sync");   // idempotent: the loss was negated on the device
 }
 
 int vgpmp_train_step_host(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* st, const double* query_latent,

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -47,6 +48,7 @@ struct vgpmp_handle {
   RobotDev robot{};
   SdfDev sdf{};
   LikDev lik{};
+  std::shared_ptr<double4> rec_owner;   // the SDF records in HBM; shared (ref-counted) by handles made with vgpmp_create_shared
   double4* rec_dev = nullptr;
   uint64_t launches = 0;
   std::string err;
@@ -66,9 +68,8 @@ struct vgpmp_handle {
   int64_t prefetched_step = -1;   // vgpmp_train_step_host: which step's draws are in flight / ready
   uint64_t prefetched_seed = 0;
   // stage profiling (bench.py): event pairs recorded on the launching stream
-  bool allow_warp_path = false; // experimental warp-synchronous sampler (N + Mp <= 96); slower than the CTA kernel so far
-  bool allow_dmma_path = true;  // DMMA contraction in the equispaced sampler (N + M + 2 <= 192), else the FMA kernel
-  bool allow_split_tail = true; // DMMA sampler stops at f0/h0; preparation + pathwise update share gp_prepare_update_kernel
+  bool allow_tc_path = true;    // tcgen05 / TMEM 3xTF32 sampler for large sample counts (sampler_tc.cu)
+  bool allow_dmma_path = true;  // shared-memory DMMA sampler (N + M + 2 <= 192), else the general kernel
   bool allow_rr_path = true;    // register-resident warp-specialised DMMA sampler (<= 12 point tiles), else the shared-memory one
   bool allow_grid_path = true;  // equispaced rank-1 fast path of the pathwise sampler (vgpmp_set_option)
   bool profiling = false;
@@ -102,6 +103,7 @@ struct GpScratch {  // carved from the caller's workspace by cabi.cu
   double* df;      // [Bp,S,N,D]
   double* logp;    // [Bp,S,N]
   double* meta;    // [8] input-structure probe {grid flag, t0, dt, z0, dz}
+  double* loss;    // [Bp] -ELBO, what vgpmp_train_step_host copies back
   double* partial; // reverse-pass partial sums when the sample loop is split over CTAs (else nullptr)
 };
 size_t backward_partial_doubles(int num_sms, int pairs, int S);
@@ -115,12 +117,13 @@ cudaError_t launch_gp_prepare(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_
 cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
                             const double* Xq, int Nq, double* Lc, double* Sfull, double* Linv, double* kl_l, double* kvec,
                             double* f, double* v, double* f0, double* h0, double* meta, cudaStream_t s);
+int sampler_generates_draws(const vgpmp_handle* h, const vgpmp_dims& d);
 cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
                                const GpScratch& ws, const vgpmp_grads& g, cudaStream_t s);
 cudaError_t launch_predict_mean(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const double* Xq, int Nq,
                                 const double* Lc, double* mean, cudaStream_t s);
 cudaError_t launch_elbo_reduce(vgpmp_handle* h, const vgpmp_dims& d, const double* logp, const double* kl_l,
-                               double* elbo, double* kl_out, cudaStream_t s);
+                               double* elbo, double* kl_out, double* loss_out, cudaStream_t s);
 cudaError_t launch_adam(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_adam& st, const vgpmp_grads& g, cudaStream_t s);
 cudaError_t launch_rng_fill(vgpmp_handle* h, const vgpmp_dims& d, uint64_t seed, uint64_t iteration,
                             int64_t problem_offset, int64_t sample_offset, double* omega, double* tau, double* w,

@@ -19,6 +19,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "device_utils.cuh"
 
 namespace {
 
@@ -283,23 +284,8 @@ __global__ void __launch_bounds__(128) gp_prepare_kernel(int D, int M, double ji
 //            register and is consumed immediately by the kST sample accumulators (w is a warp-uniform load).
 //   phase 2: u = mu + S eps_u;  v = Khat^-1 (u - f0(Zy) - sqrt(jitter) eps_j);  f = f0(X) + Kfu v.
 // ---------------------------------------------------------------------------------------------
-struct PathwiseArgs {
-  int D, M, Nq, S, B, XG, KS;
-  int gen_draws;       // 1: omega / tau / w are not in memory, the register-resident sampler generates them from the key below
-  uint64_t seed, iteration;
-  int64_t problem_offset, sample_offset;
-  int split_tail;      // 1: the sampler stops at f0/h0; gp_prepare_update_kernel finishes the sample paths
-  int items;           // work items of the general sampler (pairs x nchunk)
-  int nchunk, chunk;   // the S samples are split into nchunk CTAs per (problem, latent), `chunk` samples each (multiple of kST)
-  double jitter;
-  const double *Z, *Xq, *ls, *var, *q_mu, *query_latent;
-  const double *omega, *tau, *w, *eps_u, *eps_j;
-  const double *Lc, *Sfull, *Linv;
-  double *f, *v, *f0, *h0;
-};
-
 __global__ void __launch_bounds__(768) pathwise_kernel(PathwiseArgs a, const double* __restrict__ meta) {
-  if (meta != nullptr && meta[0] != 0.0) return;  // equispaced rank-1 inputs: pathwise_grid_kernel does the work
+  if (meta != nullptr && meta[0] != 0.0) return;  // equispaced rank-1 inputs: the equispaced samplers do the work
   extern __shared__ double sm[];
   // work items = (problem, latent, sample chunk); the grid may be smaller than their number (the launcher sends only a
   // couple of CTAs per SM when the equispaced path is expected to take the work: an empty launch of 1925 x 768 threads
@@ -460,243 +446,17 @@ __global__ void __launch_bounds__(256) analyze_grid_kernel(int D, int M, int Nq,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pathwise sampler, equispaced rank-1 inputs.  One CTA per (problem, latent).  Per tile of kGB bases:
-//   phase 1  thread (basis, chunk of points): 2 sincos (chunk start, step) then one complex rotation per point;
-//            cos feature and lengthscale-derivative feature go to shared memory [basis][point];
-//   phase 2  thread (half of the tile's bases, cos|dl feature, 4 points) x 8 samples: 32 register accumulators,
-//            features and weights come from shared memory as 128-bit loads (weights are warp-uniform broadcasts).
-// The second half (update + Kfu v) is shared with the general kernel.
-// ---------------------------------------------------------------------------------------------
-constexpr int kGB = 32;   // bases per tile
-
-__device__ __forceinline__ void pathwise_update_tail(const PathwiseArgs& a, int pl, int p, int l, int s0, int ns,
-                                                     const double* f0s, int XP, const double* Lism, const double* Ssm,
-                                                     int lds, const double* Kfu, double* vs, const double* mu,
-                                                     double sqrtj) {
-  // f0s[i*XP + x]: prior draw of sample s0+i at point x (x < Nq: query points, then the Mp inducing points)
-  // Lism: explicit inverse Cholesky factor in shared memory; Ssm: q_sqrt_full with leading dimension lds
-  // v = Khat^-1 r = Li^T (Li r); vs doubles as the per-sample scratch row ([kST][32], one row per warp-sample)
-  const int Mp = a.M + 2, Nq = a.Nq, S = a.S, D = a.D;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
-  for (int i = warp; i < ns; i += nw) {
-    const int s = s0 + i;
-    const double* eu = a.eps_u + ((size_t)pl * S + s) * Mp;
-    double r = 0.0;
-    if (lane < Mp) {
-      double u = mu[lane];
-      for (int k = 0; k <= lane; ++k) u += Ssm[lane * lds + k] * eu[k];
-      r = u - f0s[(size_t)i * XP + Nq + lane] - sqrtj * a.eps_j[((size_t)pl * S + s) * Mp + lane];
-    }
-    double* row = vs + i * 32;
-    row[lane] = r;
-    __syncwarp();
-    const double y = warp_lower_mv(Lism, Mp, row);
-    __syncwarp();
-    row[lane] = y;
-    __syncwarp();
-    const double vv = warp_lowerT_mv(Lism, Mp, row);
-    __syncwarp();
-    row[lane] = lane < Mp ? vv : 0.0;
-    if (lane < Mp && a.v != nullptr) a.v[((size_t)pl * S + s) * Mp + lane] = vv;
-  }
-  __syncthreads();
-  for (int idx = tid; idx < ns * Nq; idx += nt) {
-    const int i = idx / Nq, n = idx % Nq;
-    double fv = f0s[(size_t)i * XP + n];
-    for (int m = 0; m < Mp; ++m) fv += Kfu[n * Mp + m] * vs[i * 32 + m];
-    a.f[(((size_t)p * S + s0 + i) * Nq + n) * D + l] = fv;
-  }
-  __syncthreads();
-}
-
-// one chunk of an equispaced run: points first..first+count-1 of the grid g0 + k*dg, written at column col0 + k
-__device__ __forceinline__ void rotate_run(double* fc, double* fd, int col0, int first, int count, double g0, double dg,
-                                           double c, double tau, double amp, double inv_ell) {
-  if (count <= 0) return;
-  double sn, cs, sd, cd;
-  const double tn = g0 + dg * first;
-  sincos(tn * c + tau, &sn, &cs);
-  sincos(dg * c, &sd, &cd);
-  cs *= amp; sn *= amp;
-  double q = tn * c * inv_ell;
-  const double dq = dg * c * inv_ell;
-  for (int k = 0; k < count; ++k) {
-    fc[col0 + first + k] = cs;
-    fd[col0 + first + k] = sn * q;      // d/d lengthscale of amp cos(t c + tau), c = sum(omega)/lengthscale
-    const double c2 = cs * cd - sn * sd;
-    sn = sn * cd + cs * sd;
-    cs = c2;
-    q += dq;
-  }
-}
-
-// ST = live sample accumulators per thread (7 when the whole sample set fits one tile of 7, else 8); all shared-memory
-// layouts keep the tile stride kST = 8.
-template <int XT, int ST>
-__global__ void __launch_bounds__(256, 2) pathwise_grid_kernel(PathwiseArgs a, const double* __restrict__ meta) {
-  extern __shared__ __align__(16) double sm[];
-  const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, B = a.B, A = Nq + Mp;
-  const int pl = blockIdx.x / a.nchunk, p = pl / D, l = pl % D;
-  const int s_begin = (blockIdx.x % a.nchunk) * a.chunk, s_end = min(a.S, s_begin + a.chunk);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
-  const int XG = (A + XT - 1) / XT, XP = XG * XT, AP = XP | 1;   // odd row stride: conflict-free column walks
-  // main-loop view of shared memory
-  double* feat = sm;                                  // [2][kGB][AP]
-  double* Wt = feat + (((size_t)2 * kGB * AP + 1) & ~(size_t)1);   // [2 buffers][kGB][kST], 16-byte aligned
-  double* osum = Wt + 2 * kGB * kST;                  // [2][4][kGB] partial sums over the input dims of omega_b
-  double* tb = osum + 2 * 4 * kGB;                    // [2][kGB] tau_b
-  // tail view (after the base loop the feature tile is dead): red | Lsm | Kfu | vs | mu | zy
-  double* red = sm;                                   // [KS][2][kST][XP]
-  double* Lsm = red + (size_t)2 * 2 * kST * XP;
-  double* Kfu = Lsm + 32 * LDM;                       // [Nq][Mp]
-  double* vs = Kfu + (size_t)Nq * Mp;                 // [kST][32]
-  double* mu = vs + kST * 32;
-  double* zy = mu + 32;
-
-  if (meta[0] == 0.0) return;  // inputs are not an equispaced rank-1 grid: the general kernel does the sampling
-  const double ell = a.ls[pl], s2 = a.var[pl];
-  const double amp = sqrt(2.0 * s2 / (double)B), sqrtj = sqrt(a.jitter), inv_ell = 1.0 / ell;
-  const double t0 = meta[1], dt = meta[2], z0 = meta[3], dz = meta[4];
-  const double* om = a.omega + (size_t)pl * B * D;
-  const double* ta = a.tau + (size_t)pl * B;
-  const double* wp = a.w + (size_t)pl * S * B;
-
-  // phase-1 roles: lane = basis within the tile; warps 0..nxc-1 walk chunks of the query grid, the last two warps
-  // walk the inducing points (conditioned endpoints + first half of Z | second half of Z)
-  const int nxc = nw - 2;
-  const int per = (Nq + nxc - 1) / nxc;
-  const int mhalf = (M + 1) / 2;
-  // phase-2 roles: thread = (base slice ks, cos|dl feature, point group xg); its XT points are xg + i*XG
-  const int KS = max(1, min(4, nt / (2 * XG)));
-  const bool worker = tid < 2 * KS * XG;
-  const int xg = tid % XG, which = (tid / XG) & 1, ks = tid / (2 * XG);
-  const int bper = (kGB + KS - 1) / KS;
-
-  for (int s0 = s_begin; s0 < s_end; s0 += kST) {
-    const int ns = min(kST, s_end - s0);
-    double acc[XT][ST];
-#pragma unroll
-    for (int i = 0; i < XT; ++i)
-#pragma unroll
-      for (int j = 0; j < ST; ++j) acc[i][j] = 0.0;
-
-    // staging registers: this thread's share of the next tile's operands, prefetched one tile ahead with no dependent
-    // arithmetic.  Warp g (< 4) loads omega[base = lane][g] and omega[base][g + 4]; the sum over input dimensions is
-    // folded through shared memory when the tile is staged.
-    double st_o[2] = {0.0, 0.0}, st_t = 0.0, st_w[2] = {0.0, 0.0};
-    auto prefetch = [&](int b0) {
-      const int nb = min(kGB, B - b0);
-      if (warp < 4) {
-        st_o[0] = (lane < nb && warp < D) ? om[(size_t)(b0 + lane) * D + warp] : 0.0;
-        st_o[1] = (lane < nb && warp + 4 < D) ? om[(size_t)(b0 + lane) * D + warp + 4] : 0.0;
-      }
-      st_t = (tid < kGB && tid < nb) ? ta[b0 + tid] : 0.0;
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int idx = tid + k * nt;       // kGB*kST = 256 elements, nt >= 128
-        const int i = idx / kGB, b = idx % kGB;
-        st_w[k] = (idx < kGB * kST && i < ns && b < nb) ? wp[(size_t)(s0 + i) * B + b0 + b] : 0.0;
-      }
-    };
-    prefetch(0);
-    int buf = 0;
-    for (int b0 = 0; b0 < B; b0 += kGB, buf ^= 1) {
-      if (warp < 4) osum[(buf * 4 + warp) * kGB + lane] = st_o[0] + st_o[1];
-      if (tid < kGB) tb[buf * kGB + tid] = st_t;
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int idx = tid + k * nt;
-        if (idx < kGB * kST) Wt[(buf * kGB + idx % kGB) * kST + idx / kGB] = st_w[k];
-      }
-      if (b0 + kGB < B) prefetch(b0 + kGB);   // lands while this tile is being processed
-      __syncthreads();  // staging visible; previous tile's contraction finished -> feature tile is free
-      {  // phase 1: features by rotation along the grid
-        const double* os = osum + (size_t)buf * 4 * kGB + lane;
-        const double c = (os[0] + os[kGB] + os[2 * kGB] + os[3 * kGB]) * inv_ell, tau = tb[buf * kGB + lane];
-        double* fc = feat + (size_t)lane * AP;
-        double* fd = feat + (size_t)(kGB + lane) * AP;
-        if (warp < nxc) {
-          const int n0 = warp * per;
-          rotate_run(fc, fd, 0, n0, min(Nq, n0 + per) - n0, t0, dt, c, tau, amp, inv_ell);
-        } else if (warp == nxc) {
-          double sn, cs;
-          sincos(tau, &sn, &cs);                       // Zy[0] = 0
-          fc[Nq] = amp * cs; fd[Nq] = 0.0;
-          sincos(c + tau, &sn, &cs);                   // Zy[1] = 1
-          fc[Nq + 1] = amp * cs; fd[Nq + 1] = amp * sn * c * inv_ell;
-          rotate_run(fc, fd, Nq + 2, 0, mhalf, z0, dz, c, tau, amp, inv_ell);
-        } else {
-          rotate_run(fc, fd, Nq + 2, mhalf, M - mhalf, z0, dz, c, tau, amp, inv_ell);
-        }
-      }
-      __syncthreads();
-      if (worker) {  // phase 2: XT x kST register tile, features as conflict-free 64-bit loads, weights broadcast
-        const double* fsrc = feat + (size_t)which * kGB * AP + xg;
-        const double* wsrc = Wt + (size_t)buf * kGB * kST;
-        const int bb0 = ks * bper, bb1 = min(kGB, bb0 + bper);
-#pragma unroll 2
-        for (int b = bb0; b < bb1; ++b) {
-          double fv[XT], wv[kST];
-#pragma unroll
-          for (int i = 0; i < XT; ++i) fv[i] = fsrc[(size_t)b * AP + i * XG];
-#pragma unroll
-          for (int j = 0; j < kST; j += 2) {
-            const double2 w2 = *reinterpret_cast<const double2*>(wsrc + b * kST + j);
-            wv[j] = w2.x; wv[j + 1] = w2.y;
-          }
-#pragma unroll
-          for (int i = 0; i < XT; ++i)
-#pragma unroll
-            for (int j = 0; j < ST; ++j) acc[i][j] += fv[i] * wv[j];
-        }
-      }
-    }
-    __syncthreads();
-    // publish red[ks][which][s][x] over the dead feature tile, load the tail operands behind it, fold the slices
-    if (worker) {
-#pragma unroll
-      for (int i = 0; i < XT; ++i)
-#pragma unroll
-        for (int j = 0; j < kST; ++j) red[((size_t)(ks * 2 + which) * kST + j) * XP + xg + i * XG] = j < ST ? acc[i][j < ST ? j : 0] : 0.0;
-    }
-    if (tid < 32) {
-      zy[tid] = tid < Mp ? zy_at(a.Z, D, l, tid) : 0.0;
-      mu[tid] = tid >= Mp ? 0.0 : (tid < 2 ? a.query_latent[((size_t)p * 2 + tid) * D + l]
-                                          : a.q_mu[((size_t)p * M + tid - 2) * D + l]);
-    }
-    __syncthreads();
-    for (int idx = tid; idx < 2 * kST * XP; idx += nt) {
-      double t = red[idx];
-      for (int k = 1; k < KS; ++k) t += red[(size_t)k * 2 * kST * XP + idx];
-      red[idx] = t;
-      const int wh = idx / (kST * XP), i = (idx / XP) % kST, xx = idx % XP;
-      if (i < ns && xx < A) {
-        double* dst = wh == 0 ? a.f0 : a.h0;
-        if (dst != nullptr) dst[((size_t)pl * S + s0 + i) * A + xx] = t;
-      }
-    }
-    __syncthreads();  // slices 1.. of red are dead from here on: Lsm / Kfu live behind slice 1
-    for (int idx = tid; idx < Mp * Mp; idx += nt)
-      Lsm[(idx / Mp) * LDM + idx % Mp] = a.Linv[(size_t)pl * Mp * Mp + idx];   // explicit inverse factor
-    for (int idx = tid; idx < Nq * Mp; idx += nt) {
-      const int n = idx / Mp, m = idx % Mp;
-      Kfu[idx] = s2 * vg_matern52(fabs(a.Xq[(size_t)n * D + l] - zy[m]) / ell);
-    }
-    __syncthreads();
-    pathwise_update_tail(a, pl, p, l, s0, ns, red, XP, Lsm, a.Sfull + (size_t)pl * Mp * Mp, Mp, Kfu, vs, mu, sqrtj);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Equispaced sampler with the contraction on the FP64 tensor path (DMMA m8n8k4).
-// Same two phases per tile of 32 bases as pathwise_grid_kernel, but phase 2 is  C[8 points x 8 samples] += A[8 x 4 bases]
-// B[4 x 8]  with A fragments read straight from the feature tile (one 64-bit shared load per 256 FMAs) and C held in
-// 2*PT registers per thread for the whole base loop.  B200 executes DMMA at the DFMA rate (profiles/r1_v9_dmma_probe.txt),
-// so the gain is not flops: the contraction shrinks from ~250 to ~60 issued instructions per warp and tile, the
-// accumulator file from 48 to 2*PT doubles, the kernel fits 3 CTAs per SM (was 2) and the latency-bound feature phase
-// gets 1.5x the warps.  The warps that are light in phase 2 also precompute, for the NEXT tile, everything phase 1 would
-// otherwise recompute per chunk (step phasors of both grids, the two conditioned endpoints): 12 sincos per basis
-// instead of 18, and exactly one on every thread's critical path.
+// Equispaced sampler with the contraction on the FP64 tensor path (DMMA m8n8k4), features through shared memory: the
+// fallback of the register-resident sampler below for point sets that need more than its 12 row tiles (N + M + 2 <= 192,
+// e.g. the 150-point prediction grid).  Per tile of 32 bases:
+//   phase 1  thread (basis, chunk of points): one complex rotation per point from tabulated start / step phasors; cos
+//            feature and lengthscale-derivative feature go to shared memory [point][basis];
+//   phase 2  C[8 points x 8 samples] += A[8 x 4 bases] B[4 x 8]  with A fragments read straight from the feature tile
+//            (one 64-bit shared load per 256 FMAs) and C held in 2*PT registers per thread for the whole base loop.
+// B200 executes DMMA at the DFMA rate (profiles/r1_v9_dmma_probe.txt), so the gain over an FMA contraction is issue
+// slots and operand traffic, not flops.  The warps that are light in phase 2 also precompute, for the NEXT tile,
+// everything phase 1 would otherwise recompute per chunk (step phasors of both grids, the two conditioned endpoints).
+// The kernel stops at the prior draw f0 / h0; gp_prepare_update_kernel finishes the sample paths.
 // ---------------------------------------------------------------------------------------------
 constexpr int kDB = 32;    // bases per tile
 constexpr int kDBP = 36;   // padded basis stride of a feature row: the 4 rows x 4 lanes of an A fragment hit 16 distinct banks
@@ -746,17 +506,12 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
   double* stt = tb + 3 * kDB;                   // [8 chunks][kDB][2]  chunk-start phasors, amplitude folded in
   double* stp = stt + 8 * kDB * 2;              // [2][kDB][2]  step phasors (cos, sin) of the query grid | inducing grid
   double* ept = stp + 2 * kDB * 2;              // [2][kDB][2]  unit phasors of the conditioned endpoints Zy = 0 | 1
-  // tail view over the dead feature tile: red | Lsm | Kfu | vs | mu | zy
+  // after the basis loop the feature tile is dead: the accumulators are transposed through it
   double* red = sm;                             // [2][kST][ROWS]
-  double* Lsm = red + (size_t)2 * kST * ROWS;
-  double* Kfu = Lsm + 32 * LDM;
-  double* vs = Kfu + (size_t)Nq * Mp;
-  double* mu = vs + kST * 32;
-  double* zy = mu + 32;
 
   if (meta[0] == 0.0) return;  // not an equispaced rank-1 grid: the general kernel does the sampling
   const double ell = a.ls[pl], s2 = a.var[pl];
-  const double amp = sqrt(2.0 * s2 / (double)B), sqrtj = sqrt(a.jitter), inv_ell = 1.0 / ell;
+  const double amp = sqrt(2.0 * s2 / (double)B), inv_ell = 1.0 / ell;
   const double t0 = meta[1], dt = meta[2], z0 = meta[3], dz = meta[4];
   const double* om = a.omega + (size_t)pl * B * D;
   const double* ta = a.tau + (size_t)pl * B;
@@ -793,7 +548,7 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
 #pragma unroll
     for (int j = 0; j < PT; ++j) acc[j][0] = acc[j][1] = 0.0;
 
-    // staging registers: this thread's share of a tile's operands (as in pathwise_grid_kernel), one tile ahead of the
+    // staging registers: this thread's share of a tile's operands (warps 0-3: omega[base = lane][warp] and [warp + 4]; tid < 32: tau; all: one weight), one tile ahead of the
     // shared-memory copy, which itself is one tile ahead of its use
     double st_o[2] = {0.0, 0.0}, st_t = 0.0, st_w = 0.0;
     auto prefetch = [&](int b0) {
@@ -864,17 +619,12 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
       }
     }
     __syncthreads();
-    // publish red[feature][sample][point] over the dead feature tile, load the tail operands behind it
+    // publish red[feature][sample][point] over the dead feature tile
 #pragma unroll
     for (int j = 0; j < PT; ++j) {
       const int u = warp * PT + j, f = u / (4 * PT), tile = u % (4 * PT);
       red[((size_t)f * kST + 2 * t4) * ROWS + tile * 8 + g] = acc[j][0];
       red[((size_t)f * kST + 2 * t4 + 1) * ROWS + tile * 8 + g] = acc[j][1];
-    }
-    if (tid < 32) {
-      zy[tid] = tid < Mp ? zy_at(a.Z, D, l, tid) : 0.0;
-      mu[tid] = tid >= Mp ? 0.0 : (tid < 2 ? a.query_latent[((size_t)p * 2 + tid) * D + l]
-                                          : a.q_mu[((size_t)p * M + tid - 2) * D + l]);
     }
     __syncthreads();
     for (int idx = tid; idx < 2 * kST * ROWS; idx += nt) {
@@ -884,53 +634,8 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
         if (dst != nullptr) dst[((size_t)pl * S + s0 + i) * A + xx] = red[idx];
       }
     }
-    if (a.split_tail) continue;   // gp_prepare_update_kernel takes it from f0
-    for (int idx = tid; idx < Mp * Mp; idx += nt)
-      Lsm[(idx / Mp) * LDM + idx % Mp] = a.Linv[(size_t)pl * Mp * Mp + idx];   // explicit inverse factor
-    for (int idx = tid; idx < Nq * Mp; idx += nt) {
-      const int n = idx / Mp, m = idx % Mp;
-      Kfu[idx] = s2 * vg_matern52(fabs(a.Xq[(size_t)n * D + l] - zy[m]) / ell);
-    }
-    __syncthreads();
-    pathwise_update_tail(a, pl, p, l, s0, ns, red, ROWS, Lsm, a.Sfull + (size_t)pl * Mp * Mp, Mp, Kfu, vs, mu, sqrtj);
   }
 }
-
-// ---------------------------------------------------------------------------------------------
-// Counter-based draws (Philox4x32-10).  Shared by rng_fill_kernel and by the register-resident sampler, whose producer
-// warps can generate omega / tau / w in place ("lazy" draws: same keys, same arithmetic, bit-identical values).
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
-    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
-    c[1] = (uint32_t)p1; c[3] = (uint32_t)p0; c[0] = n0; c[2] = n2;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-}
-__device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {  // (0,1), 53 bits
-  const uint64_t x = ((uint64_t)hi << 32 | lo) >> 11;
-  return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
-}
-// Four independent N(0,1) from one Philox block.  The draws are random inputs, not arithmetic of the reference: the
-// Box-Muller transform runs in float32 on the SFU (32-bit uniforms, |z| < 6.7) and is widened to float64.  Parity
-// tests feed the *materialised* draws to the oracle, so this choice cannot leak into a parity result.
-__device__ __forceinline__ void normal4(uint64_t seed, uint64_t iter, uint32_t stream, uint64_t idx, double z[4]) {
-  uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)iter, stream ^ ((uint32_t)(iter >> 32) << 8)};
-  philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const float u1 = ((float)c[2 * k] + 0.5f) * 2.3283064365386963e-10f;       // (0,1]
-    const float u2 = ((float)c[2 * k + 1] + 0.5f) * 2.3283064365386963e-10f;
-    const float r = sqrtf(-2.0f * __logf(fminf(u1, 0.99999994f)));
-    float sn, cs;
-    __sincosf(6.283185307179586f * u2, &sn, &cs);
-    z[2 * k] = (double)(r * cs);
-    z[2 * k + 1] = (double)(r * sn);
-  }
-}
-
 
 // ---------------------------------------------------------------------------------------------
 // Equispaced sampler, register-resident features (N + 2 and M each padded to tiles of 8 rows, <= 12 tiles in total).
@@ -950,59 +655,6 @@ constexpr int kRB = 32;        // bases per table slot
 constexpr int kRE = 50;        // doubles per basis in a slot: Sx[8] | E8x | Sz[8] | E8z | e0 | e1 | c/l | pad | w[8 samples]
 constexpr int kRS = 4;         // ring slots
 constexpr int kRT = 12;        // point tiles (rows / 8) a consumer carries
-
-// shared-memory mbarrier helpers (producer/consumer hand-over without coupling the consumers to each other)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-  asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
-  } while (!ok);
-}
-
-// Six branch-free double sincos evaluated in lock-step (|x| < 2^20, the caller checks and falls back): three-term
-// Cody-Waite reduction by pi/2, Taylor kernels on [-pi/4, pi/4] truncated below 1e-17.  Written as loops over the six
-// arguments so every Horner step issues six independent FMAs: a lone producer warp otherwise crawls through six
-// back-to-back dependency chains at one instruction per FP64 latency (measured: the producers, not the DMMAs, set the
-// kernel time before this).
-__device__ __forceinline__ void sincos_bf6(const double (&x)[6], double (&sn)[6], double (&cs)[6]) {
-  double r[6], z[6], ps[6], pc[6];
-  int q[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const double n = rint(x[k] * 0.63661977236758134308);
-    q[k] = __double2int_rn(n);
-    r[k] = fma(-n, 6.123233995736766e-17, fma(-n, 1.5707963267948966, x[k]));
-    z[k] = r[k] * r[k];
-    ps[k] = 1.0 / 1307674368000.0;
-    pc[k] = 1.0 / 20922789888000.0;
-  }
-  const double S[6] = {1.0 / 6227020800.0, 1.0 / 39916800.0, 1.0 / 362880.0, 1.0 / 5040.0, 1.0 / 120.0, 1.0 / 6.0};
-  const double C[7] = {1.0 / 87178291200.0, 1.0 / 479001600.0, 1.0 / 3628800.0, 1.0 / 40320.0, 1.0 / 720.0, 1.0 / 24.0, 0.5};
-#pragma unroll
-  for (int t = 0; t < 6; ++t)
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      ps[k] = fma(ps[k], -z[k], S[t]);
-      pc[k] = fma(pc[k], -z[k], C[t]);
-    }
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    pc[k] = fma(pc[k], -z[k], C[6]);
-    const double s = fma(-z[k] * r[k], ps[k], r[k]);
-    const double c = fma(-z[k], pc[k], 1.0);
-    const double a = (q[k] & 1) ? c : s, b = (q[k] & 1) ? s : c;
-    sn[k] = (q[k] & 2) ? -a : a;
-    cs[k] = ((q[k] + 1) & 2) ? -b : b;
-  }
-}
 
 // JX = tiles of 8 rows holding the query grid and the two conditioned endpoints (inducing rows follow); GEN = lazy draws
 template <int JX, bool GEN>
@@ -1322,165 +974,6 @@ __global__ void __launch_bounds__(128, 7) gp_prepare_update_kernel(PathwiseArgs 
       for (int i = 0; i < kST; ++i)
         if (i < ns) a.f[(((size_t)p * S + s0 + i) * Nq + n) * D + l] = acc[i];
     }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Warp-synchronous variant of the equispaced sampler (used when N + Mp <= 96): ONE WARP per (problem, latent, sample
-// tile).  No block-level barrier exists anywhere in the kernel, so the FP64 pipe is kept busy by the warp scheduler
-// interleaving ~13 independent warps per SM that sit in different phases:
-//   phase 1  lane = (basis of an 8-basis tile, chunk of points): 2-4 sincos, then one rotation per point;
-//   phase 2  lane = (cos | d/dlengthscale feature, point group): XT points x 8 samples = 8*XT register accumulators.
-// f0 / h0 go to global memory; the pathwise update runs in pathwise_tail_kernel.
-// ---------------------------------------------------------------------------------------------
-constexpr int kWB = 8;   // bases per tile of the warp kernel
-
-template <int XT>
-__global__ void __launch_bounds__(32, 12) pathwise_warp_kernel(PathwiseArgs a, const double* __restrict__ meta) {
-  if (meta[0] == 0.0) return;
-  extern __shared__ __align__(16) double sm[];
-  const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, B = a.B, A = Nq + Mp;
-  const int tiles_s = (S + kST - 1) / kST;
-  const int pl = blockIdx.x / tiles_s, l = pl % D;
-  const int s0 = (blockIdx.x % tiles_s) * kST, ns = min(kST, S - s0);
-  const int lane = threadIdx.x;
-  const int XG = (A + XT - 1) / XT, XP = XG * XT, AP = XP | 1;   // XG <= 16
-  const int plane = (kWB * AP + 15) & ~15;                        // second feature plane starts on a 128-byte boundary
-  double* feat = sm;                                  // [2][kWB][AP]
-  double* Wt = feat + 2 * plane;                      // [kWB][kST]
-  double* cb = Wt + kWB * kST;                        // [kWB]
-  double* tb = cb + kWB;                              // [kWB]
-
-  const double ell = a.ls[pl], s2 = a.var[pl];
-  const double amp = sqrt(2.0 * s2 / (double)B), inv_ell = 1.0 / ell;
-  const double t0 = meta[1], dt = meta[2], z0 = meta[3], dz = meta[4];
-  const double* om = a.omega + (size_t)pl * B * D;
-  const double* ta = a.tau + (size_t)pl * B;
-  const double* wp = a.w + (size_t)pl * S * B;
-
-  // phase-1 role
-  const int pb = lane & (kWB - 1), chunk = lane >> 3;           // 8 bases x 4 chunks
-  const int per = (Nq + 2) / 3;                                  // chunks 0..2 walk the query grid, chunk 3 the inducing points
-  // phase-2 role
-  const int which = lane >> 4, xg = lane & 15;
-  const bool worker = xg < XG;
-
-  double acc[XT][kST];
-#pragma unroll
-  for (int i = 0; i < XT; ++i)
-#pragma unroll
-    for (int j = 0; j < kST; ++j) acc[i][j] = 0.0;
-
-  // staging registers, prefetched one tile ahead with no dependent arithmetic: lane (base = lane&7, group = lane>>3)
-  // loads omega[base][group] and omega[base][group+4]; the sum over the input dimensions is folded at store time
-  double st_o[2], st_t = 0.0, st_w[2];
-  auto prefetch = [&](int b0) {
-    const int b = b0 + (lane & 7), g = lane >> 3;
-    st_o[0] = (b < B && g < D) ? om[(size_t)b * D + g] : 0.0;
-    st_o[1] = (b < B && g + 4 < D) ? om[(size_t)b * D + g + 4] : 0.0;
-    st_t = (lane < kWB && b < B) ? ta[b] : 0.0;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int idx = lane + 32 * k, i = idx >> 3, bb = idx & 7;   // kWB * kST = 64 weights per tile
-      st_w[k] = (i < ns && b0 + bb < B) ? wp[(size_t)(s0 + i) * B + b0 + bb] : 0.0;
-    }
-  };
-  prefetch(0);
-  for (int b0 = 0; b0 < B; b0 += kWB) {
-    __syncwarp();
-    {
-      double c = st_o[0] + st_o[1];
-      c += __shfl_xor_sync(kFull, c, 8);
-      c += __shfl_xor_sync(kFull, c, 16);
-      if (lane < kWB) { cb[lane] = c * inv_ell; tb[lane] = st_t; }
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int idx = lane + 32 * k;
-      Wt[(idx & 7) * kST + (idx >> 3)] = st_w[k];
-    }
-    if (b0 + kWB < B) prefetch(b0 + kWB);
-    __syncwarp();
-    {  // phase 1: every lane runs the same code on lane-dependent run parameters (no divergent paths)
-      const double c = cb[pb], tau = tb[pb];
-      double* fc = feat + (size_t)pb * AP;
-      double* fd = feat + plane + (size_t)pb * AP;
-      const bool onx = chunk < 3;
-      const int first = onx ? chunk * per : 0;
-      const int count = onx ? min(Nq, first + per) - first : M;
-      rotate_run(fc, fd, onx ? 0 : Nq + 2, first, count, onx ? t0 : z0, onx ? dt : dz, c, tau, amp, inv_ell);
-      if (chunk < 2) {  // the two conditioned timesteps Zy[0] = 0, Zy[1] = 1: one point each on chunk-0 / chunk-1 lanes
-        const double t = (double)chunk;
-        double sn, cs;
-        sincos(t * c + tau, &sn, &cs);
-        fc[Nq + chunk] = amp * cs;
-        fd[Nq + chunk] = amp * sn * (t * c * inv_ell);
-      }
-    }
-    __syncwarp();
-    if (worker) {  // phase 2
-      const double* fsrc = feat + which * plane + xg;
-#pragma unroll 2
-      for (int b = 0; b < kWB; ++b) {
-        double fv[XT], wv[kST];
-#pragma unroll
-        for (int i = 0; i < XT; ++i) fv[i] = fsrc[(size_t)b * AP + i * XG];
-#pragma unroll
-        for (int j = 0; j < kST; j += 2) {
-          const double2 w2 = *reinterpret_cast<const double2*>(Wt + b * kST + j);
-          wv[j] = w2.x; wv[j + 1] = w2.y;
-        }
-#pragma unroll
-        for (int i = 0; i < XT; ++i)
-#pragma unroll
-          for (int j = 0; j < kST; ++j) acc[i][j] += fv[i] * wv[j];
-      }
-    }
-  }
-  if (worker) {
-    double* dst = which == 0 ? a.f0 : a.h0;
-#pragma unroll
-    for (int i = 0; i < XT; ++i) {
-      const int x = xg + i * XG;
-      if (x < A)
-#pragma unroll
-        for (int j = 0; j < kST; ++j)
-          if (j < ns) dst[((size_t)pl * S + s0 + j) * A + x] = acc[i][j];
-    }
-  }
-}
-
-// Pathwise update for the warp kernel: v = Khat^-1 (u - f0(Zy) - sqrt(jitter) eps_j), f = f0(X) + Kfu v.
-// One CTA (128 threads) per (problem, latent); samples in tiles of kST.
-__global__ void __launch_bounds__(128) pathwise_tail_kernel(PathwiseArgs a, const double* __restrict__ meta) {
-  if (meta[0] == 0.0) return;
-  extern __shared__ double sm[];
-  const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, A = Nq + Mp;
-  const int pl = blockIdx.x, p = pl / D, l = pl % D;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
-  double* f0s = sm;                                   // [kST][A]
-  double* Lism = f0s + (size_t)kST * A;               // [32][LDM]
-  double* Kfu = Lism + 32 * LDM;                      // [Nq][Mp]
-  double* vs = Kfu + (size_t)Nq * Mp;                 // [kST][32]
-  double* mu = vs + kST * 32;
-  double* zy = mu + 32;
-  const double ell = a.ls[pl], s2 = a.var[pl], sqrtj = sqrt(a.jitter);
-  if (tid < 32) {
-    zy[tid] = tid < Mp ? zy_at(a.Z, D, l, tid) : 0.0;
-    mu[tid] = tid >= Mp ? 0.0 : (tid < 2 ? a.query_latent[((size_t)p * 2 + tid) * D + l]
-                                        : a.q_mu[((size_t)p * M + tid - 2) * D + l]);
-  }
-  for (int i = warp; i < Mp; i += nw)
-    if (lane < Mp) Lism[i * LDM + lane] = a.Linv[(size_t)pl * Mp * Mp + i * Mp + lane];
-  __syncthreads();
-  for (int n = warp; n < Nq; n += nw)
-    if (lane < Mp) Kfu[n * Mp + lane] = s2 * vg_matern52(fabs(a.Xq[(size_t)n * D + l] - zy[lane]) / ell);
-  for (int s0 = 0; s0 < S; s0 += kST) {
-    const int ns = min(kST, S - s0);
-    __syncthreads();
-    for (int idx = tid; idx < ns * A; idx += nt) f0s[idx] = a.f0[((size_t)pl * S + s0) * A + idx];
-    __syncthreads();
-    pathwise_update_tail(a, pl, p, l, s0, ns, f0s, A, Lism, a.Sfull + (size_t)pl * Mp * Mp, Mp, Kfu, vs, mu, sqrtj);
   }
 }
 
@@ -1817,7 +1310,7 @@ __global__ void __launch_bounds__(128) predict_mean_kernel(int D, int M, int Nq,
 __global__ void __launch_bounds__(256) elbo_reduce_kernel(int D, int SN, double scale, double klw,
                                                          const double* __restrict__ logp,
                                                          const double* __restrict__ kl_l, double* __restrict__ elbo,
-                                                         double* __restrict__ kl_out) {
+                                                         double* __restrict__ kl_out, double* __restrict__ loss_out) {
   __shared__ double red[8];
   const int p = blockIdx.x;
   double t = 0.0;
@@ -1826,8 +1319,10 @@ __global__ void __launch_bounds__(256) elbo_reduce_kernel(int D, int SN, double 
   if (threadIdx.x == 0) {
     double kl = 0.0;
     for (int l = 0; l < D; ++l) kl += kl_l[(size_t)p * D + l];
-    elbo[p] = scale * lik - klw * kl;
+    const double e = scale * lik - klw * kl;
+    elbo[p] = e;
     if (kl_out != nullptr) kl_out[p] = kl;
+    if (loss_out != nullptr) loss_out[p] = -e;      // training_loss = -ELBO (utils/miscellaneous.py:77-79)
   }
 }
 
@@ -1978,11 +1473,42 @@ cudaError_t launch_gp_prepare(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_
   return cudaGetLastError();
 }
 
+// gated on the device-side input probe: the caller handed over NO omega / tau / w buffers (lazy draws that are never
+// materialised) but X / Z turned out not to be an equispaced rank-1 grid, so no sampler could run.  Fail loudly: the
+// sample paths (hence the ELBO and every gradient) become NaN.
+__global__ void poison_paths_kernel(double* __restrict__ f, size_t n, const double* __restrict__ meta) {
+  if (meta[0] != 0.0) return;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) f[i] = nan;
+}
+
+// Which sampler takes equispaced rank-1 inputs of this shape: tensor-core (tcgen05, 3xTF32) for large sample counts,
+// register-resident DMMA when the points fit its 12 row tiles, shared-memory DMMA up to 192 points, else the general kernel.
+enum SamplerKind { SAMPLER_GENERAL = 0, SAMPLER_DMMA, SAMPLER_RR, SAMPLER_TC };
+
+static SamplerKind pick_sampler(const vgpmp_handle* h, const PathwiseArgs& a) {
+  const int A = a.Nq + a.M + 2;
+  if (!h->allow_grid_path || a.Nq < 2 || a.M < 2) return SAMPLER_GENERAL;
+  if (h->allow_tc_path && pathwise_tc_supported(a)) return SAMPLER_TC;
+  if (h->allow_rr_path && (a.Nq + 2 + 7) / 8 + (a.M + 7) / 8 <= kRT) return SAMPLER_RR;
+  if (h->allow_dmma_path && A <= 192) return SAMPLER_DMMA;
+  return SAMPLER_GENERAL;
+}
+
+int sampler_generates_draws(const vgpmp_handle* h, const vgpmp_dims& d) {
+  PathwiseArgs a{};
+  a.D = h->robot.dof; a.M = d.num_inducing; a.Nq = d.num_timesteps; a.S = d.num_samples; a.B = d.num_bases;
+  const SamplerKind k = pick_sampler(h, a);
+  return (k == SAMPLER_TC || k == SAMPLER_RR) ? 1 : 0;
+}
+
 cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
                             const double* Xq, int Nq, double* Lc, double* Sfull, double* Linv, double* kl_l, double* kvec,
                             double* f, double* v, double* f0, double* h0, double* meta, cudaStream_t s) {
-  // The GP preparation (Kuu, Cholesky, L^-1, q_sqrt_full, KL) is this launcher's job too.  (Fusing it into the sampler
-  // CTAs was tried: correct but neutral-to-slower, the extra code costs the FP64-bound main loop more than the launch saves.)
+  // Schedule: [draw materialisation if needed] -> input probe -> equispaced sampler (stops at the prior draw f0 / h0; it
+  // needs no GP factor) -> gp_prepare_update_kernel (Kuu, Cholesky, L^-1, q_sqrt_full, KL, then the pathwise update) ->
+  // general sampler, which exits at once unless the probe found X / Z not to be an equispaced rank-1 grid.
+  // (Fusing the preparation into the sampler CTAs was tried: neutral-to-slower.)
   PathwiseArgs a;
   a.D = h->robot.dof; a.M = d.num_inducing; a.Nq = Nq; a.S = d.num_samples; a.B = d.num_bases;
   const int Mp = a.M + 2, A = Nq + Mp;
@@ -2003,74 +1529,37 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
   a.omega = r.omega; a.tau = r.tau; a.w = r.w; a.eps_u = r.eps_u; a.eps_j = r.eps_j;
   a.Lc = Lc; a.Sfull = Sfull; a.Linv = Linv; a.f = f; a.v = v; a.f0 = f0; a.h0 = h0;
   cudaError_t e;
-  // fast path: equispaced rank-1 inputs (decided on the device, see analyze_grid_kernel)
-  int XT = 3, threads = 128;
-  {
-    // pick the points-per-thread / CTA size that keeps every warp busy in the contraction phase
-    double best = -1.0;
-    for (int nt : {128, 256})
-      for (int xt : {3, 4}) {
-        const int xg = (A + xt - 1) / xt;
-        if (2 * xg > nt) continue;
-        const int ks = std::max(1, std::min(4, nt / (2 * xg)));
-        const double fill = (double)(2 * ks * xg) / nt - (nt == 256 ? 0.05 : 0.0) - (xt == 3 ? 0.0 : 0.01);
-        if (fill > best) { best = fill; XT = xt; threads = nt; }
-      }
-    if (best < 0) XT = 0;
-  }
-  bool grid_ok = h->allow_grid_path && XT != 0 && Nq >= 2 && a.M >= 2;
-  size_t smem_g = 0;
-  if (grid_ok) {
-    const int XGq = (A + XT - 1) / XT, XP = XGq * XT, AP = XP | 1;
-    const size_t main_view = (((size_t)2 * kGB * AP + 1) & ~(size_t)1) + 2 * kGB * kST + 10 * kGB;
-    const size_t tail_view = (size_t)2 * 2 * kST * XP + 32 * LDM + (size_t)Nq * Mp + kST * 32 + 64;
-    const int ks = std::max(1, std::min(4, threads / (2 * XGq)));
-    const size_t red_view = (size_t)ks * 2 * kST * XP;
-    smem_g = sizeof(double) * std::max(std::max(main_view, tail_view), red_view);
-    grid_ok = smem_g <= 200 * 1024;
-  }
-  const bool warp_path = grid_ok && h->allow_warp_path && A <= 96 && f0 != nullptr && h0 != nullptr && a.M >= 2;
-  // split schedule (default): the DMMA sampler needs none of the GP factors, so it runs first and stops at f0 / h0; the
-  // preparation and the pathwise update then share one small-CTA kernel (gp_prepare_update_kernel).
-  const bool split = grid_ok && !warp_path && h->allow_dmma_path && h->allow_split_tail && A <= 192 && f0 != nullptr;
-  a.split_tail = split ? 1 : 0;
-  // lazy draws (vgpmp_rng_fill_lazy): omega / tau / w of this set were never written.  The register-resident sampler
-  // generates them in its producer warps; anything else needs them in memory first.
-  const bool rr_path = split && h->allow_rr_path && (Nq + 2 + 7) / 8 + (a.M + 7) / 8 <= kRT;
+  const int pairs = d.num_problems * a.D;
+  const SamplerKind kind = f0 != nullptr ? pick_sampler(h, a) : SAMPLER_GENERAL;
+  const bool tc_path = kind == SAMPLER_TC, rr_path = kind == SAMPLER_RR;
+  const bool fast = kind != SAMPLER_GENERAL;
+  // lazy draws (vgpmp_rng_fill_lazy): omega / tau / w of this set were never written.  The tensor-core and the
+  // register-resident samplers generate them in their producer warps; anything else needs them in memory first.
+  // The state is one-shot: whatever happens below, this call consumes it.
   const bool lazy = h->lazy.valid && h->lazy.omega == r.omega && h->lazy.tau == r.tau && h->lazy.w == r.w &&
                     h->lazy.num_problems == d.num_problems && h->lazy.num_samples == d.num_samples &&
                     h->lazy.num_bases == d.num_bases;
+  const vgpmp_handle::LazyDraws lz = h->lazy;
+  h->lazy.valid = false;
+  const bool have_buffers = r.omega != nullptr && r.tau != nullptr && r.w != nullptr;
+  if (!lazy && !have_buffers) return cudaErrorInvalidValue;   // NULL draw buffers are only legal right after vgpmp_rng_fill_lazy
   a.gen_draws = 0; a.seed = 0; a.iteration = 0; a.problem_offset = 0; a.sample_offset = 0;
-  if (lazy && rr_path) {
+  if (lazy && (tc_path || rr_path)) {
     a.gen_draws = 1;
-    a.seed = h->lazy.seed; a.iteration = h->lazy.iteration;
-    a.problem_offset = h->lazy.problem_offset; a.sample_offset = h->lazy.sample_offset;
+    a.seed = lz.seed; a.iteration = lz.iteration; a.problem_offset = lz.problem_offset; a.sample_offset = lz.sample_offset;
   } else if (lazy) {
-    if ((e = launch_rng_fill(h, d, h->lazy.seed, h->lazy.iteration, h->lazy.problem_offset, h->lazy.sample_offset,
-                             const_cast<double*>(r.omega), const_cast<double*>(r.tau), const_cast<double*>(r.w), nullptr,
-                             nullptr, s, nullptr)) != cudaSuccess)
+    if (!have_buffers) return cudaErrorInvalidValue;          // no in-kernel generator for this shape: the caller must provide buffers
+    if ((e = launch_rng_fill(h, d, lz.seed, lz.iteration, lz.problem_offset, lz.sample_offset, const_cast<double*>(r.omega),
+                             const_cast<double*>(r.tau), const_cast<double*>(r.w), nullptr, nullptr, s, nullptr)) != cudaSuccess)
       return e;
-    h->lazy.valid = false;   // materialised
   }
-  if (!split && (e = launch_gp_prepare(h, d, p, Lc, Sfull, kl_l, kvec, Linv, s)) != cudaSuccess) return e;
-  if (grid_ok) {
+  if (!fast) {
+    if ((e = launch_gp_prepare(h, d, p, Lc, Sfull, kl_l, kvec, Linv, s)) != cudaSuccess) return e;
+  } else {
     analyze_grid_kernel<<<1, 256, 0, s>>>(a.D, a.M, Nq, Xq, p.Z, meta);
     h->launches++;
-    if (warp_path) {
-      const int xt = std::max(4, (A + 15) / 16);        // <= 16 point groups per feature plane
-      const int XGq = (A + xt - 1) / xt, XP = XGq * xt, AP = XP | 1;
-      const int plane = (kWB * AP + 15) & ~15;
-      const size_t smem_w = sizeof(double) * ((size_t)2 * plane + kWB * kST + 2 * kWB);
-      const int tiles_s = (a.S + kST - 1) / kST;
-      void (*kern)(PathwiseArgs, const double*) = xt <= 4 ? pathwise_warp_kernel<4>
-                                                : (xt == 5 ? pathwise_warp_kernel<5> : pathwise_warp_kernel<6>);
-      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w)) != cudaSuccess) return e;
-      kern<<<d.num_problems * a.D * tiles_s, 32, smem_w, s>>>(a, meta);
-      const size_t smem_t = sizeof(double) * ((size_t)kST * A + 32 * LDM + (size_t)Nq * Mp + kST * 32 + 64);
-      if ((e = cudaFuncSetAttribute(pathwise_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)) != cudaSuccess)
-        return e;
-      pathwise_tail_kernel<<<d.num_problems * a.D, 128, smem_t, s>>>(a, meta);
-      h->launches += 2;
+    if (tc_path) {
+      if ((e = launch_pathwise_tc(h, a, pairs, meta, s)) != cudaSuccess) return e;
     } else if (rr_path) {
       const size_t ring = (size_t)kRS * kRB * kRE, fold = (size_t)4 * 2 * kST * kRT * 8;
       const size_t smem_r = sizeof(double) * (std::max(ring, fold) + 2 * kRS);
@@ -2089,48 +1578,44 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
         default: kern = a.gen_draws ? pathwise_rr_kernel<11, true> : pathwise_rr_kernel<11, false>; break;
       }
       if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)) != cudaSuccess) return e;
-      kern<<<d.num_problems * a.D * a.nchunk, 256, smem_r, s>>>(a, meta);
-      gp_prepare_update_kernel<<<d.num_problems * a.D * a.nchunk, 128, 0, s>>>(a, p, Lc, Sfull, kl_l, kvec, Linv, meta);
-      h->launches += 2;
-      if (a.gen_draws) {   // inputs turned out not to be an equispaced grid: the general sampler below reads memory
-        if ((e = launch_rng_fill(h, d, a.seed, a.iteration, a.problem_offset, a.sample_offset, const_cast<double*>(r.omega),
-                                 const_cast<double*>(r.tau), const_cast<double*>(r.w), nullptr, nullptr, s, meta)) != cudaSuccess)
-          return e;
-      }
-    } else if (h->allow_dmma_path && A <= 192) {
+      kern<<<pairs * a.nchunk, 256, smem_r, s>>>(a, meta);
+      h->launches++;
+    } else {
       const int PT = A <= 96 ? 3 : 6, ROWS = 32 * PT;
       const size_t main_view = (size_t)2 * ROWS * kDBP + 3 * kDB * kWS + 3 * 4 * kDB + 3 * kDB + 8 * kDB * 2 + 2 * (2 * kDB * 2);
-      const size_t tail_view = (size_t)2 * kST * ROWS + 32 * LDM + (size_t)Nq * Mp + kST * 32 + 64;
-      size_t smem_m = sizeof(double) * std::max(main_view, tail_view);
+      const size_t smem_m = sizeof(double) * std::max(main_view, (size_t)2 * kST * ROWS);
       if (smem_m > 227 * 1024) return cudaErrorInvalidValue;
       void (*kern)(PathwiseArgs, const double*) = PT == 3 ? pathwise_dmma_kernel<3> : pathwise_dmma_kernel<6>;
       if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m)) != cudaSuccess)
         return e;
-      kern<<<d.num_problems * a.D * a.nchunk, 256, smem_m, s>>>(a, meta);
-      h->launches++;
-      if (split) {
-        gp_prepare_update_kernel<<<d.num_problems * a.D * a.nchunk, 128, 0, s>>>(a, p, Lc, Sfull, kl_l, kvec, Linv, meta);
-        h->launches++;
-      }
-    } else {
-      void (*kern)(PathwiseArgs, const double*);
-      if (a.S <= 7) kern = XT == 3 ? pathwise_grid_kernel<3, 7> : pathwise_grid_kernel<4, 7>;
-      else kern = XT == 3 ? pathwise_grid_kernel<3, 8> : pathwise_grid_kernel<4, 8>;
-      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g)) != cudaSuccess)
-        return e;
-      kern<<<d.num_problems * a.D * a.nchunk, threads, smem_g, s>>>(a, meta);
+      kern<<<pairs * a.nchunk, 256, smem_m, s>>>(a, meta);
       h->launches++;
     }
+    gp_prepare_update_kernel<<<pairs * a.nchunk, 128, 0, s>>>(a, p, Lc, Sfull, kl_l, kvec, Linv, meta);
+    h->launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (a.gen_draws) {
+      // should the probe find the inputs not to be an equispaced grid, the general sampler below reads the draws from
+      // memory: write them now (gated on the probe), or - without buffers - poison the result
+      if (have_buffers) {
+        if ((e = launch_rng_fill(h, d, a.seed, a.iteration, a.problem_offset, a.sample_offset, const_cast<double*>(r.omega),
+                                 const_cast<double*>(r.tau), const_cast<double*>(r.w), nullptr, nullptr, s, meta)) != cudaSuccess)
+          return e;
+      } else {
+        poison_paths_kernel<<<2 * h->num_sms, 256, 0, s>>>(f, (size_t)d.num_problems * a.S * Nq * a.D, meta);
+        h->launches++;
+        return cudaGetLastError();
+      }
+    }
   }
   const int threads_gen = 32 * a.XG * a.KS;
   const size_t smem = sizeof(double) * ((size_t)a.KS * 2 * kST * a.XG * 32 + 2 * 32 * LDM + (size_t)Nq * Mp + kST * 32 + 64);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   e = cudaFuncSetAttribute(pathwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  a.items = d.num_problems * a.D * a.nchunk;
-  const int grid_gen = grid_ok ? std::min(a.items, 2 * h->num_sms) : a.items;
-  pathwise_kernel<<<grid_gen, threads_gen, smem, s>>>(a, grid_ok ? meta : nullptr);
+  a.items = pairs * a.nchunk;
+  const int grid_gen = fast ? std::min(a.items, 2 * h->num_sms) : a.items;
+  pathwise_kernel<<<grid_gen, threads_gen, smem, s>>>(a, fast ? meta : nullptr);
   h->launches++;
   return cudaGetLastError();
 }
@@ -2193,11 +1678,11 @@ cudaError_t launch_predict_mean(vgpmp_handle* h, const vgpmp_dims& d, const vgpm
 }
 
 cudaError_t launch_elbo_reduce(vgpmp_handle* h, const vgpmp_dims& d, const double* logp, const double* kl_l,
-                               double* elbo, double* kl_out, cudaStream_t s) {
+                               double* elbo, double* kl_out, double* loss_out, cudaStream_t s) {
   const int stot = d.total_samples > 0 ? d.total_samples : d.num_samples;
   const double klw = d.kl_shards > 1 ? 1.0 / (double)d.kl_shards : 1.0;
   elbo_reduce_kernel<<<d.num_problems, 256, 0, s>>>(h->robot.dof, d.num_samples * d.num_timesteps,
-                                                     h->lik.alpha / (double)stot, klw, logp, kl_l, elbo, kl_out);
+                                                     h->lik.alpha / (double)stot, klw, logp, kl_l, elbo, kl_out, loss_out);
   h->launches++;
   return cudaGetLastError();
 }

@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(kThreads, 3) loglik_kernel(RobotDev rb, SdfDev
       const int j = k - 1;
       const double xin = xnext;
       if (k < D) xnext = in[c * D + k];
+      lp += xin - xin;     // 0 for a finite input; NaN / Inf inputs must not vanish in the voxel clip and the hinge's fmax
       double thj = xin, dsq = 1.0;
       if (squash) {
         const double sg = stable_sigmoid(xin), span = rb.hi[j] - rb.lo[j];

@@ -51,7 +51,10 @@ class Engine:
 
     def __init__(self, robot: RobotConstants, sdf_data: np.ndarray, sdf_origin: Sequence[float], sdf_delta: float,
                  sigma_obs: float = 1.0, epsilon: float = 0.0, alpha: float = 1.0,
-                 scene_offset: Sequence[float] = (0.0, 0.0, 0.0), jitter: float = 1e-6, device: Optional[int] = None):
+                 scene_offset: Sequence[float] = (0.0, 0.0, 0.0), jitter: float = 1e-6, device: Optional[int] = None,
+                 share_from: Optional["Engine"] = None):
+        """`share_from`: another Engine on the same device whose SDF records (and robot constants) this handle re-uses
+        (`vgpmp_create_shared`): one copy of the grid per device however many handles / streams drive it."""
         self.lib = _cabi.load()
         if not torch.cuda.is_available():
             raise _cabi.VgpmpError("vgpmp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -60,23 +63,41 @@ class Engine:
         self.robot = robot
         self.D, self.P = int(robot.dof), int(len(robot.sphere_radii))
         self.sigma_obs, self.epsilon, self.alpha, self.jitter = float(sigma_obs), float(epsilon), float(alpha), float(jitter)
+        self.scene_offset = tuple(float(v) for v in scene_offset)
+        self._ws = None
         keep = dict(dh=_c64(robot.dh), twist=_c64(robot.twist), base=_c64(robot.base_pose),
                     frame=np.ascontiguousarray(robot.sphere_frame, dtype=np.int32), off=_c64(robot.sphere_offsets),
-                    rad=_c64(robot.sphere_radii), lo=_c64(robot.limits_lo), hi=_c64(robot.limits_hi),
-                    grid=_c64(sdf_data))
+                    rad=_c64(robot.sphere_radii), lo=_c64(robot.limits_lo), hi=_c64(robot.limits_hi))
         rd = _cabi.RobotDesc(self.D, int(bool(robot.craig)), self.P, _dp(keep["dh"]), _dp(keep["twist"]),
                              _dp(keep["base"]), keep["frame"].ctypes.data_as(_cabi.c_int32_p), _dp(keep["off"]),
                              _dp(keep["rad"]), _dp(keep["lo"]), _dp(keep["hi"]))
+        ld = _cabi.LikDesc(self.sigma_obs, self.epsilon, self.alpha, (C.c_double * 3)(*self.scene_offset), self.jitter)
+        h = C.c_void_p()
+        if share_from is not None:
+            if share_from.device_index != self.device_index:
+                raise _cabi.VgpmpError("share_from must live on the same device")
+            rc = self.lib.vgpmp_create_shared(C.byref(h), share_from.h, C.byref(rd), C.byref(ld))
+            if rc != 0:
+                raise _cabi.VgpmpError(f"vgpmp_create_shared failed ({rc}): {self.lib.vgpmp_last_error(None).decode()}")
+            self.h = h
+            return
+        keep["grid"] = _c64(sdf_data)
         nx, ny, nz = keep["grid"].shape
         sd = _cabi.SdfDesc(nx, ny, nz, _dp(keep["grid"]), (C.c_double * 3)(*map(float, sdf_origin)), float(sdf_delta))
-        ld = _cabi.LikDesc(self.sigma_obs, self.epsilon, self.alpha, (C.c_double * 3)(*map(float, scene_offset)),
-                           self.jitter)
-        h = C.c_void_p()
         rc = self.lib.vgpmp_create(C.byref(h), self.device_index, C.byref(rd), C.byref(sd), C.byref(ld))
         if rc != 0:
             raise _cabi.VgpmpError(f"vgpmp_create failed ({rc}): {self.lib.vgpmp_last_error(None).decode()}")
         self.h = h
-        self._ws = None
+
+    def shared(self, alpha: Optional[float] = None) -> "Engine":
+        """A second handle on the same SDF records (e.g. for a sub-batch driven on its own stream)."""
+        return Engine(self.robot, None, (0, 0, 0), 1.0, sigma_obs=self.sigma_obs, epsilon=self.epsilon,
+                      alpha=self.alpha if alpha is None else alpha, scene_offset=self.scene_offset, jitter=self.jitter,
+                      device=self.device_index, share_from=self)
+
+    @property
+    def sdf_records_id(self) -> int:
+        return int(self.lib.vgpmp_sdf_records_id(self.h))
 
     def __del__(self):
         h, self.h = getattr(self, "h", None), None
@@ -206,13 +227,21 @@ class Engine:
         return ps
 
     @staticmethod
+    def _ptr(t):
+        return None if t is None else t.data_ptr()
+
+    @staticmethod
     def draws_struct(d: dict) -> _cabi.Draws:
-        ds = _cabi.Draws(*(d[k].data_ptr() for k in ("omega", "tau", "w", "eps_u", "eps_j")))
+        ds = _cabi.Draws(*(Engine._ptr(d[k]) for k in ("omega", "tau", "w", "eps_u", "eps_j")))
         ds._keep = tuple(d[k] for k in ("omega", "tau", "w", "eps_u", "eps_j"))
         return ds
 
-    def alloc_draws(self, dims: _cabi.Dims) -> dict:
+    def alloc_draws(self, dims: _cabi.Dims, lazy_only: bool = False) -> dict:
+        """`lazy_only`: omega / tau / w stay None (a set for `rng_fill_lazy` that is never materialised: at BASELINE
+        config 5, w alone would be 8192 x 7 x 256 x 1024 doubles = 112 GiB)."""
         Bp, D, B, S, Mp = dims.num_problems, self.D, dims.num_bases, dims.num_samples, dims.num_inducing + 2
+        if lazy_only:
+            return dict(omega=None, tau=None, w=None, eps_u=self.empty(Bp, D, S, Mp), eps_j=self.empty(Bp, D, S, Mp))
         return dict(omega=self.empty(Bp, D, B, D), tau=self.empty(Bp, D, B), w=self.empty(Bp, D, S, B),
                     eps_u=self.empty(Bp, D, S, Mp), eps_j=self.empty(Bp, D, S, Mp))
 
@@ -231,8 +260,8 @@ class Engine:
         (inside the sampler kernel for equispaced inputs).  Their tensors hold unspecified values afterwards."""
         d = draws
         self._chk(self.lib.vgpmp_rng_fill_lazy(self.h, C.byref(dims), int(seed), int(iteration), int(problem_offset),
-                                               int(sample_offset), d["omega"].data_ptr(), d["tau"].data_ptr(),
-                                               d["w"].data_ptr(), d["eps_u"].data_ptr(), d["eps_j"].data_ptr(),
+                                               int(sample_offset), self._ptr(d["omega"]), self._ptr(d["tau"]),
+                                               self._ptr(d["w"]), d["eps_u"].data_ptr(), d["eps_j"].data_ptr(),
                                                self._stream()), "rng_fill_lazy")
         return d
 

@@ -63,15 +63,21 @@ class VariationalMonteCarloLikelihood:
         self.joint_sigmoid = JointSigmoid(low=self.joint_constraints[:, 1], high=self.joint_constraints[:, 0])
         self.epsilon = float(epsilon)
         self.p = robot.num_spheres
-        self._alpha = 1.0
-        self._eng = None
+        self._engines = {}          # alpha -> Engine; all of them share ONE copy of the SDF records on the device
+        self._share_from = kwargs.get("share_engine")   # an Engine of another likelihood over the same robot + SDF
 
-    def _engine(self) -> Engine:
-        if self._eng is None:
-            self._eng = Engine(self.sampler.constants(), self.sdf.data, self.sdf.origin, self.sdf.delta,
-                               sigma_obs=self.sigma_obs, epsilon=self.epsilon, alpha=self._alpha,
-                               scene_offset=self.offset.reshape(3))
-        return self._eng
+    def _engine(self, alpha: float = 1.0) -> Engine:
+        """The handle that carries this likelihood's constants and `alpha` (VGPMP.alpha is baked into the handle).  A
+        likelihood used with several alphas, or several likelihoods over one environment (`share_engine`), get handles
+        made with `vgpmp_create_shared`: the SDF is uploaded once."""
+        alpha = float(alpha)
+        if alpha not in self._engines:
+            # the SignedDistanceField object owns the device copy of its records (sdf._eng()); every handle made here shares it
+            base = next(iter(self._engines.values()), None) or self._share_from or self.sdf._eng()
+            self._engines[alpha] = Engine(self.sampler.constants(), None, (0, 0, 0), 1.0, share_from=base,
+                                          sigma_obs=self.sigma_obs, epsilon=self.epsilon, alpha=alpha,
+                                          scene_offset=self.offset.reshape(3))
+        return self._engines[alpha]
 
     # ---- reference API ---------------------------------------------------------------------------
     def log_prob(self, F):

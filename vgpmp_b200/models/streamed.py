@@ -38,6 +38,8 @@ class StreamedVGPMP:
         num_streams = max(1, min(int(num_streams), qs.shape[0]))
         models, start = [], 0
         for idx in np.array_split(np.arange(qs.shape[0]), num_streams):
+            if models and "share_engine" not in kw:
+                kw = dict(kw, share_engine=models[0]._eng)      # one copy of the SDF records, one handle per stream
             m = VGPMP.initialize(query_states=qs[idx], **kw)
             m.problem_offset = start
             start += len(idx)

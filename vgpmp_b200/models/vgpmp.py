@@ -58,8 +58,7 @@ class VGPMP:
         self.optimizer = AdamConfig(learning_rate)
         self.alpha = float(alpha)
         self.trainable = dict(q_mu=True, q_sqrt=True, lengthscales=True, kernel_variance=True)
-        likelihood._alpha = self.alpha
-        self._eng = eng = likelihood._engine()
+        self._eng = eng = likelihood._engine(alpha=self.alpha)   # the handle carries alpha: one (shared-SDF) handle per value
         if eng.D != D:
             raise AssertionError("num_latent_gps must equal the robot's degrees of freedom")
 
@@ -68,11 +67,11 @@ class VGPMP:
         self.num_problems = Bp = qs.shape[0]
         self._query_joint = qs
         self._query_states = eng.dev(likelihood.joint_sigmoid.inverse(qs))            # [Bp,2,D] latent (vgpmp.py:75-76)
-        iv = inducing_variable.inducing_variable if isinstance(inducing_variable, SharedIndependentInducingVariables) \
-            else inducing_variable
-        if len(iv) != self.num_inducing:
+        from ..covariances import unwrap_inducing
+        Zh = unwrap_inducing(inducing_variable)        # also rejects conditioned timesteps other than t = 0, 1 (the kernels hard-code Zy = [0; 1; Z])
+        if Zh.shape[0] != self.num_inducing:
             raise AssertionError("inducing variable size and num_inducing disagree")
-        self._Z = eng.dev(iv._Z)                                                      # [M,D]
+        self._Z = eng.dev(Zh)                                                         # [M,D]
         self._init_variational_parameters(self.num_inducing, q_mu, None, False)
         ls, var = kernel.hyper_arrays()
         if np.any(var <= variance_lower):
@@ -127,7 +126,8 @@ class VGPMP:
         Z = initialize_Z(num_latent_gps, num_inducing)
         _Z = ConditionedVariableInducingPoints(Z=Z, conditioned_timesteps=conditioned_timesteps)
         likelihood = VariationalMonteCarloLikelihood(sigma_obs=sigma_obs, robot=robot, sdf=sdf, sampler=sampler,
-                                                     offset=scene_offset, epsilon=epsilon)
+                                                     offset=scene_offset, epsilon=epsilon,
+                                                     share_engine=kwargs.get("share_engine"))
         batched = qs.ndim == 3
         q3 = qs.reshape(-1, 2, num_output_dims)
         if q_mu is None:
@@ -206,11 +206,12 @@ class VGPMP:
         self._draw_buf = None
         return self
 
-    def _dims(self, N, S=None):
+    def _dims(self, N, S=None, Bp=None):
+        Bp = self.num_problems if Bp is None else Bp
         if self._shard is not None and S is None:
-            return self._eng.dims(self.num_problems, self.num_inducing, N, self.num_samples, self.num_bases,
+            return self._eng.dims(Bp, self.num_inducing, N, self.num_samples, self.num_bases,
                                   total_samples=self._shard["total"], kl_shards=self._shard["world"])
-        return self._eng.dims(self.num_problems, self.num_inducing, N, self.num_samples if S is None else S, self.num_bases)
+        return self._eng.dims(Bp, self.num_inducing, N, self.num_samples if S is None else S, self.num_bases)
 
     def _params(self, X):
         return self._eng.params_struct(self._q_mu, self._q_sqrt, self._lengthscales, self._variances, self._query_states,
@@ -257,85 +258,150 @@ class VGPMP:
         closure.model, closure.data = self, X
         return closure
 
-    def _adam_struct(self) -> _cabi.Adam:
+    def _adam_struct(self, lo: int = 0, hi: Optional[int] = None) -> _cabi.Adam:
+        """Adam state of problems [lo, hi) (every buffer is problem-major, so a slice is contiguous)."""
         o, t = self.optimizer, self.trainable
-        return _cabi.Adam(self._q_mu.data_ptr(), self._q_sqrt.data_ptr(), self._raw_lengthscales.data_ptr(),
-                          self._raw_variances.data_ptr(), self._lengthscales.data_ptr(), self._variances.data_ptr(),
-                          self._adam_m.data_ptr(), self._adam_v.data_ptr(), self._variance_lower, o.learning_rate,
-                          o.beta_1, o.beta_2, o.epsilon, self._step, int(t["q_mu"]), int(t["q_sqrt"]),
-                          int(t["lengthscales"]), int(t["kernel_variance"]))
+        hi = self.num_problems if hi is None else hi
+        per = self._adam_m.numel() // self.num_problems
+        st = _cabi.Adam(self._q_mu[lo:hi].data_ptr(), self._q_sqrt[lo:hi].data_ptr(),
+                        self._raw_lengthscales[lo:hi].data_ptr(), self._raw_variances[lo:hi].data_ptr(),
+                        self._lengthscales[lo:hi].data_ptr(), self._variances[lo:hi].data_ptr(),
+                        self._adam_m[lo * per:hi * per].data_ptr(), self._adam_v[lo * per:hi * per].data_ptr(),
+                        self._variance_lower, o.learning_rate, o.beta_1, o.beta_2, o.epsilon, self._step, int(t["q_mu"]),
+                        int(t["q_sqrt"]), int(t["lengthscales"]), int(t["kernel_variance"]))
+        return st
+
+    # ---- batching plan ------------------------------------------------------------------------------
+    max_workspace_bytes = 32 << 30   # per launch: workspace + draws; larger batches run as several problem chunks
+
+    def _inputs_are_reference_grids(self, X) -> bool:
+        """X and Z equispaced and identical across columns (what init_trainset / initialize_Z always produce)?  Same
+        criterion as the device-side probe (8 ulp).  One device->host read per distinct X buffer."""
+        key = (X.data_ptr(), tuple(X.shape), self._Z.data_ptr())
+        if getattr(self, "_grid_key", None) != key:
+            def ok(T):
+                n = T.shape[0]
+                if n < 2:
+                    return False
+                t0, t1 = T[0, 0], T[-1, 0]
+                ref = t0 + (t1 - t0) / (n - 1) * torch.arange(n, dtype=T.dtype, device=T.device)
+                tol = 8.0 * 2.220446049250313e-16 * torch.clamp(torch.maximum(t0.abs(), t1.abs()), min=1e-300)
+                return bool(((T - ref[:, None]).abs() <= tol).all())
+            self._grid_key, self._grid_ok = key, ok(X) and ok(self._Z)
+        return self._grid_ok
+
+    def _plan(self, X, explicit_draws: bool):
+        """-> (chunks [(lo, hi)], lazy_only): problem chunks that keep workspace + draws under `max_workspace_bytes`, and
+        whether omega / tau / w can stay unallocated (lazy draws, inputs are the reference's grids, and the sampler the
+        library picks for this shape generates them in-kernel)."""
+        eng, N, Bp = self._eng, X.shape[0], self.num_problems
+        one = self._dims(N, Bp=1)
+        lazy_only = (not explicit_draws and self.lazy_draws and self._inputs_are_reference_grids(X)
+                     and bool(eng.lib.vgpmp_sampler_generates_draws(eng.h, C.byref(one))))
+        per = int(eng.lib.vgpmp_workspace_bytes(eng.h, C.byref(one)))
+        per += int(eng.lib.vgpmp_draws_bytes_lazy(C.byref(one), eng.D) if lazy_only
+                   else (1 if self.lazy_draws else 2) * eng.lib.vgpmp_draws_bytes(C.byref(one), eng.D))
+        nchunks = max(1, -(-Bp * per // int(self.max_workspace_bytes)))
+        size = -(-Bp // nchunks)
+        return [(lo, min(Bp, lo + size)) for lo in range(0, Bp, size)], lazy_only
 
     def train_step(self, X, draws=None):
-        """One optimization_step (utils/miscellaneous.py:68-84): ELBO forward + reverse + Adam; returns loss = -ELBO."""
+        """One optimization_step (utils/miscellaneous.py:68-84): ELBO forward + reverse + Adam; returns loss = -ELBO.
+        Batches whose workspace would exceed `max_workspace_bytes` run as consecutive problem chunks (independent
+        problems; the Philox keys use global problem indices, so chunking does not change a single bit)."""
+        eng, D, Bp, M = self._eng, self.num_latent_gps, self.num_problems, self.num_inducing
+        X = eng.dev(X).reshape(-1, D)
+        chunks, lazy_only = self._plan(X, draws is not None)
+        if self._shard is not None and len(chunks) > 1:
+            raise NotImplementedError("sample-sharded mode holds one problem per model; it does not chunk")
+        if self._grads is None or self._grads["elbo"].shape[0] != Bp:
+            self._grads = dict(elbo=eng.empty(Bp), d_q_mu=eng.empty(Bp, M, D), d_q_sqrt=eng.empty(Bp, D, M, M),
+                               d_lengthscales=eng.empty(Bp, D), d_variances=eng.empty(Bp, D))
+        for lo, hi in chunks:
+            self._train_chunk(X, lo, hi, draws, lazy_only, single=len(chunks) == 1)
+        self._step += 1
+        return self._squeeze(-self._grads["elbo"])
+
+    def _train_chunk(self, X, lo, hi, draws, lazy_only, single):
         eng = self._eng
-        X = eng.dev(X).reshape(-1, self.num_latent_gps)
-        dims = self._dims(X.shape[0])
+        dims = self._dims(X.shape[0], Bp=hi - lo)
+        poff = self.problem_offset + lo
+        soff = self._shard["offset"] if self._shard is not None else 0
         slot = None
-        if draws is None:
-            # device draws, double-buffered: this step's set was generated on the side stream during the previous step
-            key = (dims.num_problems, dims.num_samples, dims.num_bases, dims.total_samples)
+        if draws is not None:
+            use = self._make_draws(dims, {k: v[lo:hi] for k, v in draws.items()} if not single else draws)
+        else:
+            key = (dims.num_problems, dims.num_samples, dims.num_bases, dims.total_samples, lazy_only)
             if self._pipe is None or self._pipe["key"] != key:
                 # lazy draws need one set (of which only eps_u / eps_j are ever written); the prefetch pipeline needs two
-                self._pipe = dict(key=key, sets=[eng.alloc_draws(dims)], ready=None)
-            if not self.lazy_draws and len(self._pipe["sets"]) < 2:
-                self._pipe["sets"].append(eng.alloc_draws(dims))
-            slot = self._step & 1
-            soff = self._shard["offset"] if self._shard is not None else 0
+                self._pipe = dict(key=key, sets=[eng.alloc_draws(dims, lazy_only=lazy_only)], ready=None)
             if self.lazy_draws:
                 # omega / tau / w are generated inside the sampler kernel from the same Philox keys: nothing to prefetch
-                eng.rng_fill_lazy(dims, self.seed, self._step, self._pipe["sets"][0], problem_offset=self.problem_offset,
-                                  sample_offset=soff)
-                use, slot = self._pipe["sets"][0], None
+                use = eng.rng_fill_lazy(dims, self.seed, self._step, self._pipe["sets"][0], problem_offset=poff,
+                                        sample_offset=soff)
+            elif not single:
+                use = eng.rng_fill(dims, self.seed, self._step, self._pipe["sets"][0], problem_offset=poff, sample_offset=soff)
             else:
+                # materialised draws, double-buffered: this step's set was generated on the side stream during the previous step
+                if len(self._pipe["sets"]) < 2:
+                    self._pipe["sets"].append(eng.alloc_draws(dims))
+                slot = self._step & 1
                 if self._pipe["ready"] == self._step:
                     eng.rng_join(slot)
                 else:
-                    eng.rng_fill(dims, self.seed, self._step, self._pipe["sets"][slot], problem_offset=self.problem_offset,
-                                 sample_offset=soff)
+                    eng.rng_fill(dims, self.seed, self._step, self._pipe["sets"][slot], problem_offset=poff, sample_offset=soff)
                 use = self._pipe["sets"][slot]
-        else:
-            use = self._make_draws(dims, draws)
+        params = eng.params_struct(self._q_mu[lo:hi], self._q_sqrt[lo:hi], self._lengthscales[lo:hi], self._variances[lo:hi],
+                                   self._query_states[lo:hi], self._Z, X)
         if self._shard is not None:
             from ..utils.sharding import allreduce_packed, packed_views
             views = packed_views(self._shard["flat"], self.num_problems, self.num_inducing, self.num_latent_gps)
-            out = eng.elbo_fwd_bwd(dims, self._params(X), use, need_grad=True, out=views)
+            out = eng.elbo_fwd_bwd(dims, params, use, need_grad=True, out=views)
             allreduce_packed(self._shard["flat"], self._shard["group"])      # one collective: gradients || ELBO
+            self._grads = out
         else:
-            out = eng.elbo_fwd_bwd(dims, self._params(X), use, need_grad=True)
+            out = eng.elbo_fwd_bwd(dims, params, use, need_grad=True, out={k: v[lo:hi] for k, v in self._grads.items()})
         if slot is not None:
             eng.rng_release(slot)
             eng.rng_fill_async(dims, self.seed, self._step + 1, self._pipe["sets"][slot ^ 1], slot ^ 1,
-                               problem_offset=self.problem_offset,
-                               sample_offset=self._shard["offset"] if self._shard is not None else 0)
+                               problem_offset=poff, sample_offset=soff)
             self._pipe["ready"] = self._step + 1
         gs = _cabi.Grads(out["d_q_mu"].data_ptr(), out["d_q_sqrt"].data_ptr(), out["d_lengthscales"].data_ptr(),
                          out["d_variances"].data_ptr())
-        st = self._adam_struct()
+        st = self._adam_struct(lo, hi)
         eng._chk(eng.lib.vgpmp_adam_step(eng.h, C.byref(dims), C.byref(st), C.byref(gs), eng._stream()), "adam_step")
-        self._step = st.step
-        self._grads = out
-        return self._squeeze(-out["elbo"])
 
     def train_step_host(self, X_host: torch.Tensor, wait: bool = True):
         """The same optimisation step driven from HOST buffers through `vgpmp_train_step_host`: X [N,D] is read from
         (pinned) host memory, copied to the device, the step's randomness is drawn on the device, and loss = -ELBO [Bp]
         is copied back to pinned host memory before the call returns (like `loss = tf_optimization_step(...)` feeding
-        the tqdm readout, utils/miscellaneous.py:101-103).  Returns a CPU tensor view of the pinned loss buffer."""
+        the tqdm readout, utils/miscellaneous.py:101-103).  Returns a CPU tensor (a copy of the pinned loss buffer)."""
         eng, D = self._eng, self.num_latent_gps
+        if self._shard is not None:
+            raise NotImplementedError("train_step_host does not all-reduce: a sample-sharded model steps with train_step")
         if X_host.device.type != "cpu" or X_host.dtype != torch.float64 or not X_host.is_contiguous():
             raise TypeError("train_step_host expects a contiguous float64 CPU tensor (pinned for async copies)")
         N = X_host.numel() // D
         dims = self._dims(N)
         hs = getattr(self, "_host_state", None)
         if hs is None or hs["N"] != N:
-            nbytes = 2 * int(eng.lib.vgpmp_draws_bytes(C.byref(dims), D))   # two draw sets: next step drawn on the side stream
+            Xc = X_host.reshape(N, D)
+            probe = eng.dev(Xc)
+            compact = (self.lazy_draws and self._inputs_are_reference_grids(probe)
+                       and bool(eng.lib.vgpmp_sampler_generates_draws(eng.h, C.byref(dims))))
+            # compact: eps_u / eps_j only (lazy draws never materialised); else two full sets (next step drawn on the side stream)
+            nbytes = int(eng.lib.vgpmp_draws_bytes_lazy(C.byref(dims), D)) if compact \
+                else 2 * int(eng.lib.vgpmp_draws_bytes(C.byref(dims), D))
             hs = dict(N=N, X_dev=eng.empty(N, D), draws=torch.empty(nbytes, dtype=torch.uint8, device=eng.device),
                       elbo=eng.empty(self.num_problems),
-                      loss=torch.empty(self.num_problems, dtype=torch.float64).pin_memory(),
+                      loss=torch.empty(self.num_problems, dtype=torch.float64).pin_memory(), pending=False,
                       g=dict(d_q_mu=eng.empty(self.num_problems, self.num_inducing, D),
                              d_q_sqrt=eng.empty(self.num_problems, D, self.num_inducing, self.num_inducing),
                              d_lengthscales=eng.empty(self.num_problems, D), d_variances=eng.empty(self.num_problems, D)))
             self._host_state = hs
+        if hs["pending"]:
+            raise RuntimeError("train_step_host(wait=False) was called twice without train_step_host_wait(): the pinned "
+                               "loss buffer of the step in flight would be overwritten")
         g = hs["g"]
         gs = _cabi.Grads(g["d_q_mu"].data_ptr(), g["d_q_sqrt"].data_ptr(), g["d_lengthscales"].data_ptr(),
                          g["d_variances"].data_ptr())
@@ -348,17 +414,19 @@ class VGPMP:
                                                      hs["loss"].data_ptr(), ws.data_ptr(), ws.numel(), eng._stream()),
                  "train_step_host_begin")
         self._step = st.step
-        hs["dims"], hs["stream"] = dims, eng._stream()
+        hs["dims"], hs["stream"], hs["pending"] = dims, eng._stream(), True
         if not wait:
             return None
         return self.train_step_host_wait()
 
     def train_step_host_wait(self):
-        """Second half of `train_step_host(..., wait=False)`: blocks until the loss of the step in flight is in host memory."""
+        """Second half of `train_step_host(..., wait=False)`: blocks until the loss of the step in flight is in host
+        memory and returns a copy of it (the pinned buffer is re-used by the next step)."""
         eng, hs = self._eng, self._host_state
         eng._chk(eng.lib.vgpmp_train_step_host_end(eng.h, C.byref(hs["dims"]), hs["loss"].data_ptr(), hs["stream"]),
                  "train_step_host_end")
-        return hs["loss"]
+        hs["pending"] = False
+        return hs["loss"].clone()
 
     def predict_f_samples(self, X, num_samples=None, draws=None):
         """temporary_paths + predict_f_samples (models/vgpmp.py:281-282): [S,N,D] latent samples."""
