@@ -61,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if failed:
         (PKG / "lib" / "build.log").write_text(log_text)
         raise RuntimeError("nvcc failed:\n" + "\n".join(r.stderr[-4000:] for r in failed))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *[str(o) for o, _ in results]]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB), *[str(o) for o, _ in results]]
     res = subprocess.run(cmd, capture_output=True, text=True)
     (PKG / "lib" / "build.log").write_text(log_text + "==== link\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if res.returncode != 0:

@@ -80,6 +80,7 @@ GpScratch carve(void* ws, int D, const vgpmp_dims& d, size_t* total, int num_sms
   g.logp = c.take(Bp * S * N);
   g.meta = c.take(8);
   g.loss = c.take(Bp);
+  g.lik_part = c.take(Bp * (size_t)elbo_reduce_segments(num_sms, (int)Bp, (int)(S * N)));
   const size_t np = backward_partial_doubles(num_sms, (int)(Bp * D), (int)S);
   g.partial = np ? c.take(np) : nullptr;
   *total = c.off;
@@ -390,7 +391,7 @@ int vgpmp_gp_prepare(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_params
   // kl[p] = sum_l kl_l: reuse the ELBO reducer with an empty likelihood term
   vgpmp_dims d0 = *dims;
   d0.num_timesteps = 0;
-  return check_cuda(h, launch_elbo_reduce(h, d0, g.logp, g.kl_l, g.f0 /*scratch for -kl*/, kl, nullptr, s), "kl_reduce");
+  return check_cuda(h, launch_elbo_reduce(h, d0, g.logp, g.kl_l, g.f0 /*scratch for -kl*/, kl, nullptr, nullptr, s), "kl_reduce");
 }
 
 int vgpmp_pathwise_sample(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_params* p, const vgpmp_draws* r,
@@ -440,7 +441,7 @@ int vgpmp_elbo_fwd_bwd(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_para
   }
   {
     StageSpan sp(h, ST_REDUCE, s);
-    if ((rc = check_cuda(h, launch_elbo_reduce(h, *dims, logp, g.kl_l, elbo, aux ? aux->kl : nullptr, g.loss, s), "elbo_reduce")))
+    if ((rc = check_cuda(h, launch_elbo_reduce(h, *dims, logp, g.kl_l, elbo, aux ? aux->kl : nullptr, g.loss, g.lik_part, s), "elbo_reduce")))
       return rc;
   }
   if (bwd) {

@@ -104,6 +104,7 @@ struct GpScratch {  // carved from the caller's workspace by cabi.cu
   double* logp;    // [Bp,S,N]
   double* meta;    // [8] input-structure probe {grid flag, t0, dt, z0, dz}
   double* loss;    // [Bp] -ELBO, what vgpmp_train_step_host copies back
+  double* lik_part; // [Bp * segments] partial sums of the ELBO reduction (few problems, many samples)
   double* partial; // reverse-pass partial sums when the sample loop is split over CTAs (else nullptr)
 };
 size_t backward_partial_doubles(int num_sms, int pairs, int S);
@@ -122,8 +123,9 @@ cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp
                                const GpScratch& ws, const vgpmp_grads& g, cudaStream_t s);
 cudaError_t launch_predict_mean(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const double* Xq, int Nq,
                                 const double* Lc, double* mean, cudaStream_t s);
+int elbo_reduce_segments(int num_sms, int Bp, int SN);
 cudaError_t launch_elbo_reduce(vgpmp_handle* h, const vgpmp_dims& d, const double* logp, const double* kl_l,
-                               double* elbo, double* kl_out, double* loss_out, cudaStream_t s);
+                               double* elbo, double* kl_out, double* loss_out, double* partial, cudaStream_t s);
 cudaError_t launch_adam(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_adam& st, const vgpmp_grads& g, cudaStream_t s);
 cudaError_t launch_rng_fill(vgpmp_handle* h, const vgpmp_dims& d, uint64_t seed, uint64_t iteration,
                             int64_t problem_offset, int64_t sample_offset, double* omega, double* tau, double* w,

@@ -16,16 +16,18 @@
 // TMEM accumulator only ever holds the partial sum of 64 bases: two TMEM regions alternate, and the worker warps fold
 // every finished partial into FP32 registers with round-to-nearest adds (16 folds per output) while the next 64 bases run.
 //
-// Warp roles (320 threads, 1 CTA per SM, persistent over work items):
-//   warps 0-7  workers.  Per stage of 32 bases: features by complex rotation along the two grids in float64 (warp =
+// Warp roles (576 threads, 1 CTA per SM, persistent over work items):
+//   warps 0-15 workers.  Per stage of 32 bases: features by complex rotation along the two grids in float64 (warp =
 //              segment of rows, lane = basis; start / step phasors come from the table warp), split into hi / lo and
 //              stored in the UMMA canonical K-major no-swizzle layout [basis / 4][row][4]; the stage's 128 x 32 weights
 //              from Philox4x32-10 (same keys as rng_fill_kernel: the trajectory is the one materialised draws give) or
-//              from memory; every second stage the fold described above (warp = TMEM lane quarter x column half).
-//   warp 8     table producer: lane = basis; omega / tau draws, 6 lock-step sincos, segment start phasors by powers.
-//   warp 9     lane 0 issues the MMAs (12 per stage) and commits them to the mbarriers that free the stage / publish the
+//              from memory; every second stage the fold described above (warp = TMEM lane quarter x column quarter).
+//              The producer side is issue / latency bound (Philox and Box-Muller are serial chains), hence 16 warps.
+//   warp 16    table producer: lane = basis; omega / tau draws, 6 lock-step sincos, segment start phasors by powers.
+//   warp 17    lane 0 issues the MMAs (12 per stage) and commits them to the mbarriers that free the stage / publish the
 //              group; the warp also owns the TMEM allocation.
 #include <algorithm>
+#include <cstdlib>
 
 #include "device_utils.cuh"
 
@@ -34,17 +36,23 @@ namespace {
 constexpr int kTM = 128;          // samples per CTA = MMA M
 constexpr int kTB = 32;           // bases per stage
 constexpr int kGroup = 2;         // stages per TMEM partial sum (64 bases)
-constexpr int kWorkers = 8;       // worker warps
-constexpr int kThreads = (kWorkers + 2) * 32;
-constexpr int kTE = 26;           // doubles per basis in a table slot: slot starts [8][2] | Ex | Ez | e0 | e1 | cl | pad
+#ifndef VGPMP_TC_WORKERS
+#define VGPMP_TC_WORKERS 16
+#endif
+constexpr int kWorkers = VGPMP_TC_WORKERS;   // worker warps (8 or 16)
+constexpr int kTabWarps = 4;      // table producer warps, one table slot each (stage t is produced by warp t mod 4)
+constexpr int kThreads = (kWorkers + kTabWarps + 1) * 32;
+constexpr int kTE = 2 * kWorkers + 10;   // doubles per basis in a table slot: segment starts [16][2] | Ex | Ez | e0 | e1 | cl | pad
+constexpr int kEx = 2 * kWorkers, kEz = kEx + 2, kE0 = kEx + 4, kE1 = kEx + 6, kCl = kEx + 8;
 constexpr int kWChunk = kTM * 4;  // floats per 4-basis chunk of the weight operand (LBO = 2048 B)
 
 struct TcShape {
   int AP;          // points padded to a multiple of 16
-  int nx;          // worker warps walking the query grid (the other 8 - nx walk the inducing grid)
+  int nx;          // worker warps walking the query grid (the other 16 - nx walk the inducing grid)
   int perx, perz;  // rows per segment
   int blocks;      // sample blocks per pair
   int items;       // pairs * blocks
+  int ablate;      // experiments only (VGPMP_TC_ABLATE): 1 no MMAs, 2 no weight draws, 4 no features, 8 no table math, 16 no fold
 };
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes) {
@@ -74,6 +82,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+}
+
 // value -> (hi, lo): hi keeps 11 significant bits (round to nearest), lo is the exact float32 remainder
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
@@ -97,15 +114,15 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
   constexpr int kWOp = (kTB / 4) * kWChunk, kFOp = (kTB / 4) * FChunk;   // floats per operand copy
   constexpr int kStage = 2 * kWOp + 2 * kFOp;                            // W hi | W lo | F hi | F lo
   float* stage0 = reinterpret_cast<float*>(smem_raw);
-  double* tab = reinterpret_cast<double*>(stage0 + 2 * kStage);          // [2][kTE][32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tab + 2 * kTE * 32);
-  uint64_t* full = bars;            // [2] stage written (8 worker warps)
+  double* tab = reinterpret_cast<double*>(stage0 + 2 * kStage);          // [kTabWarps][kTE][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tab + kTabWarps * kTE * 32);
+  uint64_t* full = bars;            // [2] stage written (16 worker warps)
   uint64_t* empty = bars + 2;       // [2] stage consumed (MMA commit)
-  uint64_t* tab_full = bars + 4;    // [2] table written (table warp)
-  uint64_t* tab_empty = bars + 6;   // [2] table read (8 worker warps)
-  uint64_t* grp_full = bars + 8;    // [2] TMEM partial complete (MMA commit)
-  uint64_t* grp_empty = bars + 10;  // [2] TMEM partial folded (8 worker warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* grp_full = bars + 4;    // [2] TMEM partial complete (MMA commit)
+  uint64_t* grp_empty = bars + 6;   // [2] TMEM partial folded (worker warps)
+  uint64_t* tab_full = bars + 8;    // [kTabWarps] table written (its table warp)
+  uint64_t* tab_empty = bars + 12;  // [kTabWarps] table read (worker warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   if (meta[0] == 0.0) return;       // not an equispaced rank-1 grid: the general kernel does the sampling
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -117,12 +134,12 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(full + i, kWorkers); mbar_init(empty + i, 1);
-      mbar_init(tab_full + i, 1); mbar_init(tab_empty + i, kWorkers);
       mbar_init(grp_full + i, 1); mbar_init(grp_empty + i, kWorkers);
     }
+    for (int i = 0; i < kTabWarps; ++i) { mbar_init(tab_full + i, 1); mbar_init(tab_empty + i, kWorkers); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kWorkers + 1) {
+  if (warp == kWorkers + kTabWarps) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -139,39 +156,49 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
 
   if (warp < kWorkers) {
     // =========================================== workers ===========================================
-    const int q = warp & 3, hf = warp >> 2;      // fold role: TMEM lane quarter, column half (0 = cos -> f0, 1 = sin -> h0)
+    constexpr int kParts = kWorkers / 4;         // column parts of the fold (2: cos | sin; 4: two each)
+    constexpr int CW = NROW / kParts;            // columns of the fold per thread
+    constexpr int NCH = CW / 8;                  // 8-column TMEM loads per fold
+    const int q = warp & 3, cp = warp >> 2;      // fold role: TMEM lane quarter, column part
     // feature role: segment `warp` of the rows, basis = lane
     int rowbase, cnt;
     if (warp < sh.nx) { const int r0 = warp * sh.perx; rowbase = r0; cnt = min(Nq, r0 + sh.perx) - r0; }
     else { const int r0 = (warp - sh.nx) * sh.perz; rowbase = Nq + 2 + r0; cnt = min(M, r0 + sh.perz) - r0; }
     const bool onx = warp < sh.nx;
+    const int endpoint = kWorkers - 1 - warp;    // the last two warps (short inducing segments) also place Zy = 0 and Zy = 1
     const int fcol = (lane >> 2) * FChunk + (lane & 3);                  // this basis' column inside a feature operand
+    constexpr int kQStep = kWorkers / 4;                                  // quads advance by the number of 128-thread groups
+    constexpr int kQPer = 8 / kQStep;                                     // quads (Philox blocks) per thread and stage
+    const int sl = tid & (kTM - 1), qb = tid >> 7;                        // weight role: sample row, first quad
     for (int item = blockIdx.x; item < sh.items; item += gridDim.x) {
       const int pl = item / sh.blocks, s0 = (item % sh.blocks) * kTM;
       const uint64_t pairkey = ((uint64_t)(pl / D) + (uint64_t)a.problem_offset) * (uint64_t)D + (uint64_t)(pl % D);
       const uint32_t B4 = ((uint32_t)B + 3) / 4;
       const double* wp = GEN ? nullptr : a.w + (size_t)pl * S * B;
-      float acc[NC16 * 16];
+      const int srow = s0 + sl;
+      const uint64_t wkey = (pairkey * (uint64_t)(1u << 24) + (uint64_t)srow + (uint64_t)a.sample_offset) * B4;
+      float acc[CW];
 #pragma unroll
-      for (int i = 0; i < NC16 * 16; ++i) acc[i] = 0.f;
+      for (int i = 0; i < CW; ++i) acc[i] = 0.f;
 
       int folded = 0;                             // groups of this item folded so far
       auto fold_next = [&]() {
         const int gi = gg + folded;               // global group counter of the group to fold
         mbar_wait(grp_full + (gi & 1), (gi >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((gi & 1) * 256 + hf * AP);
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((gi & 1) * 256 + cp * CW);
 #pragma unroll
-        for (int c = 0; c < NC16; c += 2) {
-          float v0[16], v1[16];
-          tmem_ld16(taddr + 16 * c, v0);
-          if (c + 1 < NC16) tmem_ld16(taddr + 16 * (c + 1), v1);
+        for (int c = 0; c < NCH; c += 2) {
+          if (sh.ablate & 16) break;
+          float v0[8], v1[8];
+          tmem_ld8(taddr + 8 * c, v0);
+          if (c + 1 < NCH) tmem_ld8(taddr + 8 * (c + 1), v1);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[16 * c + j] += v0[j];
-          if (c + 1 < NC16) {
+          for (int k = 0; k < 8; ++k) acc[8 * c + k] += v0[k];
+          if (c + 1 < NCH) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[16 * (c + 1) + j] += v1[j];
+            for (int k = 0; k < 8; ++k) acc[8 * (c + 1) + k] += v1[k];
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -186,16 +213,51 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
         float* Wlo = Whi + kWOp;
         float* Fhi = Wlo + kWOp;
         float* Flo = Fhi + kFOp;
-        mbar_wait(tab_full + slot, use & 1);                 // this stage's table is there
-        mbar_wait(empty + slot, (use & 1) ^ 1);              // the MMAs that read this slot two stages ago are done
+        // probe the two barriers this stage needs now, consume the answers after the weight draws: the try_wait round
+        // trips (~hundreds of cycles each) then overlap with the Philox / Box-Muller chains instead of preceding them
+        const int tslot = tg & (kTabWarps - 1), tuse = tg / kTabWarps;
+        const uint32_t ok_empty = mbar_test(empty + slot, (use & 1) ^ 1);
+        const uint32_t ok_tab = mbar_test(tab_full + tslot, tuse & 1);
+        // ---- weights first (they need nothing but the key): 128 samples x 8 quads of 4 bases ----
+        float4 whi[kQPer], wlo[kQPer];
+#pragma unroll
+        for (int j = 0; j < kQPer; ++j) {
+          const int b4 = qb + kQStep * j;                     // quad inside the stage
+          const uint32_t b4g = (uint32_t)t * (kTB / 4) + (uint32_t)b4;
+          float z[4] = {0.f, 0.f, 0.f, 0.f};
+          if (srow < S && 4 * b4g < (uint32_t)B && !(sh.ablate & 2)) {
+            if (GEN) {
+              normal4f(a.seed, a.iteration, 4u, wkey + b4g, z);
+            } else {
+              const double* src = wp + (size_t)srow * B + 4 * b4g;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) z[k] = (float)__ldg(src + min(k, B - 1 - (int)(4 * b4g)));
+            }
+            if (4 * b4g + 4 > (uint32_t)B) {                  // ragged last quad (B not a multiple of 4)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (4 * b4g + k >= (uint32_t)B) z[k] = 0.f;
+            }
+          }
+          split_tf32(z[0], whi[j].x, wlo[j].x); split_tf32(z[1], whi[j].y, wlo[j].y);
+          split_tf32(z[2], whi[j].z, wlo[j].z); split_tf32(z[3], whi[j].w, wlo[j].w);
+        }
+        if (!ok_empty) mbar_wait(empty + slot, (use & 1) ^ 1);   // the MMAs that read this slot two stages ago are done
+#pragma unroll
+        for (int j = 0; j < kQPer; ++j) {
+          const int b4 = qb + kQStep * j;
+          *reinterpret_cast<float4*>(Whi + b4 * kWChunk + sl * 4) = whi[j];
+          *reinterpret_cast<float4*>(Wlo + b4 * kWChunk + sl * 4) = wlo[j];
+        }
+        if (!ok_tab) mbar_wait(tab_full + tslot, tuse & 1);  // this stage's table is there
         {  // ---- features: rotation chain along this warp's rows ----
-          const double* e = tab + (size_t)slot * kTE * 32 + lane;
+          const double* e = tab + (size_t)tslot * kTE * 32 + lane;
           double cs = e[(2 * warp) * 32], sn = e[(2 * warp + 1) * 32];
-          const double cd = e[(onx ? 16 : 18) * 32], sd = e[(onx ? 17 : 19) * 32];
-          const double cl = e[24 * 32];
+          const double cd = e[(onx ? kEx : kEz) * 32], sd = e[(onx ? kEx + 1 : kEz + 1) * 32];
+          const double cl = e[kCl * 32];
           float* ph = Fhi + fcol + rowbase * 4;
           float* pl_ = Flo + fcol + rowbase * 4;
-          for (int i = 0; i < cnt; ++i) {
+          for (int i = 0; i < ((sh.ablate & 4) ? 0 : cnt); ++i) {
             float hi, lo;
             split_tf32((float)cs, hi, lo);
             ph[i * 4] = hi; pl_[i * 4] = lo;
@@ -203,49 +265,18 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
             ph[(AP + i) * 4] = hi; pl_[(AP + i) * 4] = lo;
             cmul(cs, sn, cd, sd);
           }
-          if (warp < 2) {                                     // the two conditioned timesteps: rows Nq, Nq + 1
-            const double ec = e[(20 + 2 * warp) * 32], es = e[(21 + 2 * warp) * 32];
+          if (endpoint < 2) {                                 // the two conditioned timesteps: rows Nq, Nq + 1
+            const double ec = e[(kE0 + 2 * endpoint) * 32], es = e[(kE0 + 1 + 2 * endpoint) * 32];
             float hi, lo;
             split_tf32((float)ec, hi, lo);
-            Fhi[fcol + (Nq + warp) * 4] = hi; Flo[fcol + (Nq + warp) * 4] = lo;
+            Fhi[fcol + (Nq + endpoint) * 4] = hi; Flo[fcol + (Nq + endpoint) * 4] = lo;
             split_tf32((float)(es * cl), hi, lo);
-            Fhi[fcol + (AP + Nq + warp) * 4] = hi; Flo[fcol + (AP + Nq + warp) * 4] = lo;
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tab_empty + slot);
-        }
-        {  // ---- weights: 128 samples x 8 quads of 4 bases; thread = (sample, quad parity), 4 Philox blocks each ----
-          const int sl = tid & (kTM - 1), qb = tid >> 7;      // sample row, quad offset 0 / 1
-          const int s = s0 + sl;
-          const bool srow = s < S;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int b4 = qb + 2 * j;                        // quad inside the stage
-            const uint32_t b4g = (uint32_t)t * (kTB / 4) + (uint32_t)b4;
-            float z[4] = {0.f, 0.f, 0.f, 0.f};
-            if (srow && 4 * b4g < (uint32_t)B) {
-              if (GEN) {
-                const uint64_t sg = (uint64_t)s + (uint64_t)a.sample_offset;
-                normal4f(a.seed, a.iteration, 4u, (pairkey * (uint64_t)(1u << 24) + sg) * B4 + b4g, z);
-              } else {
-                const double* src = wp + (size_t)s * B + 4 * b4g;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) z[k] = (float)__ldg(src + min(k, B - 1 - (int)(4 * b4g)));
-              }
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (4 * b4g + k >= (uint32_t)B) z[k] = 0.f;
-            }
-            float4 hi, lo;
-            split_tf32(z[0], hi.x, lo.x); split_tf32(z[1], hi.y, lo.y);
-            split_tf32(z[2], hi.z, lo.z); split_tf32(z[3], hi.w, lo.w);
-            *reinterpret_cast<float4*>(Whi + b4 * kWChunk + sl * 4) = hi;
-            *reinterpret_cast<float4*>(Wlo + b4 * kWChunk + sl * 4) = lo;
+            Fhi[fcol + (AP + Nq + endpoint) * 4] = hi; Flo[fcol + (AP + Nq + endpoint) * 4] = lo;
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
         __syncwarp();
-        if (lane == 0) mbar_arrive(full + slot);
+        if (lane == 0) { mbar_arrive(tab_empty + tslot); mbar_arrive(full + slot); }
         // ---- fold the partial sum that finished one group ago (its MMAs were issued >= 2 stages back) ----
         const int gl = t / kGroup;
         if ((t % kGroup == kGroup - 1 || t == T - 1) && gl >= 1 && folded < gl) fold_next();
@@ -254,26 +285,33 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
       gg += G;
       // ---- write-out through shared memory: every MMA of this item has been folded, so the stages are idle.  The
       // transposes live in the weight areas only (rewritten in full by every stage; the zero padding rows of the feature
-      // areas stay intact): warps 0-3 in stage 0's, warps 4-7 in stage 1's.
-      float* tr = stage0 + (size_t)(warp >> 2) * kStage + (size_t)(warp & 3) * 32 * (AP + 1);   // [32 samples][AP + 1]
+      // areas stay intact): the first half of the warps in stage 0's, the second half in stage 1's.
+      constexpr int kHalfW = kWorkers / 2;
+      float* tr = stage0 + (size_t)(warp / kHalfW) * kStage + (size_t)(warp % kHalfW) * 32 * (CW + 1);   // [32 samples][CW + 1]
 #pragma unroll
-      for (int i = 0; i < NC16 * 16; ++i) tr[lane * (AP + 1) + i] = acc[i];
+      for (int i = 0; i < CW; ++i) tr[lane * (CW + 1) + i] = acc[i];
       __syncwarp();
+      const int hf = cp * CW >= AP ? 1 : 0;                     // cos columns -> f0, sin columns -> h0
       double* dst = hf == 0 ? a.f0 : a.h0;
       if (dst != nullptr) {
-        for (int x = lane; x < A; x += 32) {
+        for (int xl = lane; xl < CW; xl += 32) {
+          const int x = cp * CW + xl - hf * AP;                 // point index
+          if (x >= A) continue;
           double scale = 1.0;
           if (hf == 1) scale = x < Nq ? t0 + dt * x : (x < Nq + 2 ? (double)(x - Nq) : z0 + dz * (x - Nq - 2));
           for (int r = 0; r < 32; ++r) {
             const int s = s0 + q * 32 + r;
-            if (s < S) dst[((size_t)pl * S + s) * A + x] = (double)tr[r * (AP + 1) + x] * scale;
+            if (s < S) dst[((size_t)pl * S + s) * A + x] = (double)tr[r * (CW + 1) + xl] * scale;
           }
         }
       }
       asm volatile("bar.sync 1, %0;" ::"r"(kWorkers * 32) : "memory");   // transposes read: the stages may be refilled
     }
-  } else if (warp == kWorkers) {
-    // =========================================== table producer ===========================================
+  } else if (warp < kWorkers + kTabWarps) {
+    // =========================================== table producers ===========================================
+    // warp j owns table slot j and produces the stages with (global stage counter) mod 4 == j: one warp alone needs
+    // ~8 000 cycles per table (a serial chain of ~1 200 mostly float64 instructions), four in flight keep ahead of the workers
+    const int tw = warp - kWorkers;
     for (int item = blockIdx.x; item < sh.items; item += gridDim.x) {
       const int pl = item / sh.blocks;
       const double ell = a.ls[pl], s2 = a.var[pl];
@@ -282,11 +320,12 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
       const double* om = GEN ? nullptr : a.omega + (size_t)pl * B * D;
       const double* ta = GEN ? nullptr : a.tau + (size_t)pl * B;
       for (int t = 0; t < T; ++t, ++tg) {
-        const int slot = tg & 1, use = tg >> 1;
+        if ((tg & (kTabWarps - 1)) != tw) continue;
+        const int slot = tw, use = tg / kTabWarps;
         const int b = t * kTB + lane;
         const bool live = b < B;
         double c = 0.0, taub = 0.0;
-        if (live) {
+        if (live && !(sh.ablate & 8)) {
           if (GEN) {
             const uint64_t key = pairkey * (uint64_t)B + (uint64_t)b;
             double z[16];
@@ -314,7 +353,10 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
         double big = 0.0;
 #pragma unroll
         for (int k = 0; k < 6; ++k) big = fmax(big, fabs(arg[k]));
-        if (big < 1048576.0) {
+        if (sh.ablate & 8) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) { sv[k] = 0.0; cv[k] = 1.0; }
+        } else if (big < 1048576.0) {
           sincos_bf6(arg, sv, cv);
         } else {
 #pragma unroll
@@ -339,11 +381,11 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
           if (j < sh.nx) { e[(2 * j) * 32] = cx; e[(2 * j + 1) * 32] = sx; cmul(cx, sx, pxc, pxs); }
           else { e[(2 * j) * 32] = cz; e[(2 * j + 1) * 32] = sz; cmul(cz, sz, pzc, pzs); }
         }
-        e[16 * 32] = cv[1]; e[17 * 32] = sv[1];
-        e[18 * 32] = cv[3]; e[19 * 32] = sv[3];
-        e[20 * 32] = ab * cv[4]; e[21 * 32] = ab * sv[4];
-        e[22 * 32] = ab * cv[5]; e[23 * 32] = ab * sv[5];
-        e[24 * 32] = cb * inv_ell;
+        e[kEx * 32] = cv[1]; e[(kEx + 1) * 32] = sv[1];
+        e[kEz * 32] = cv[3]; e[(kEz + 1) * 32] = sv[3];
+        e[kE0 * 32] = ab * cv[4]; e[(kE0 + 1) * 32] = ab * sv[4];
+        e[kE1 * 32] = ab * cv[5]; e[(kE1 + 1) * 32] = ab * sv[5];
+        e[kCl * 32] = cb * inv_ell;
         __syncwarp();
         if (lane == 0) mbar_arrive(tab_full + slot);
       }
@@ -353,20 +395,30 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NROW >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
       constexpr uint32_t lbo_w = kWChunk * 4, lbo_f = FChunk * 4;
+      auto wait_sleepy = [](uint64_t* b, uint32_t parity) {     // one thread polling: leave the issue slots to the workers
+        uint32_t ok;
+        for (;;) {
+          asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                       : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+          if (ok) break;
+          __nanosleep(40);
+        }
+      };
       for (int item = blockIdx.x; item < sh.items; item += gridDim.x) {
         for (int t = 0; t < T; ++t, ++tg) {
           const int slot = tg & 1, use = tg >> 1;
           const int gl = t / kGroup;
           const int gi = gg + gl;
           const bool first = t % kGroup == 0;
-          if (first) mbar_wait(grp_empty + (gi & 1), ((gi >> 1) & 1) ^ 1);   // the partial two groups back has been folded
-          mbar_wait(full + slot, use & 1);
+          if (first) wait_sleepy(grp_empty + (gi & 1), ((gi >> 1) & 1) ^ 1);   // the partial two groups back has been folded
+          wait_sleepy(full + slot, use & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t base = smem_u32(stage0 + (size_t)slot * kStage);
           const uint32_t whi = base, wlo = base + kWOp * 4, fhi = base + 2 * kWOp * 4, flo = fhi + kFOp * 4;
           const uint32_t dcol = tmem + (uint32_t)((gi & 1) * 256);
 #pragma unroll
           for (int ks = 0; ks < kTB / 8; ++ks) {
+            if (sh.ablate & 1) break;
             const uint32_t wo = ks * 2 * lbo_w, fo = ks * 2 * lbo_f;
             const uint64_t dwh = umma_desc(whi + wo, lbo_w), dwl = umma_desc(wlo + wo, lbo_w);
             const uint64_t dfh = umma_desc(fhi + fo, lbo_f), dfl = umma_desc(flo + fo, lbo_f);
@@ -384,13 +436,13 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
   // teardown: every MMA has been folded by the workers before they leave their loop
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == kWorkers + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  if (warp == kWorkers + kTabWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
 size_t tc_smem_bytes(int AP) {
   const size_t fchunk = (size_t)(2 * AP + 1) * 4;
   const size_t stage = 2 * (size_t)(kTB / 4) * kWChunk + 2 * (size_t)(kTB / 4) * fchunk;
-  return 2 * stage * sizeof(float) + 2 * kTE * 32 * sizeof(double) + 16 * sizeof(uint64_t);
+  return 2 * stage * sizeof(float) + (size_t)kTabWarps * kTE * 32 * sizeof(double) + 24 * sizeof(uint64_t);
 }
 
 template <int NC16>
@@ -416,11 +468,12 @@ cudaError_t launch_pathwise_tc(vgpmp_handle* h, const PathwiseArgs& a, int pairs
   TcShape sh;
   const int A = a.Nq + a.M + 2;
   sh.AP = (A + 15) / 16 * 16;
-  sh.nx = std::max(1, std::min(kWorkers - 1, (kWorkers * a.Nq + (a.Nq + a.M) / 2) / (a.Nq + a.M)));
+  sh.nx = std::max(1, std::min(kWorkers - 2, (kWorkers * a.Nq + (a.Nq + a.M) / 2) / (a.Nq + a.M)));   // >= 2 inducing segments: they also place the endpoints
   sh.perx = (a.Nq + sh.nx - 1) / sh.nx;
   sh.perz = (a.M + (kWorkers - sh.nx) - 1) / (kWorkers - sh.nx);
   sh.blocks = (a.S + kTM - 1) / kTM;
   sh.items = pairs * sh.blocks;
+  { const char* ab = getenv("VGPMP_TC_ABLATE"); sh.ablate = ab ? atoi(ab) : 0; }
   switch (sh.AP / 16) {
     case 1: return launch_nc<1>(h, a, sh, meta, s);
     case 2: return launch_nc<2>(h, a, sh, meta, s);

@@ -78,11 +78,18 @@ def grid_geometry(tri, delta, padding):
     return origin, tuple(int(v) for v in shape)
 
 
-def mesh_to_sdf(obj_path, delta: float, padding: int = PADDING, device=None) -> SignedDistanceField:
+def mesh_to_sdf(obj_path, delta: float, padding: int = PADDING, device=None, origin=None, shape=None) -> SignedDistanceField:
+    """`origin` + `shape` (both or neither) replace the SDFGen geometry (mesh bounding box grown by `padding` cells) with an
+    explicit grid, e.g. the 512^3 grid around the robot's reach volume of BASELINE config 5."""
     if not torch.cuda.is_available():
         raise _cabi.VgpmpError("mesh_to_sdf runs on the GPU (vgpmp_mesh_to_sdf); there is no CPU fallback")
     tri, plane, piece_end = load_obj_convex_pieces(obj_path)
-    origin, shape = grid_geometry(tri, delta, padding)
+    if (origin is None) != (shape is None):
+        raise ValueError("give both origin and shape, or neither")
+    if origin is None:
+        origin, shape = grid_geometry(tri, delta, padding)
+    else:
+        origin, shape = np.asarray(origin, dtype=np.float64).reshape(3), tuple(int(v) for v in shape)
     out = np.empty(shape, dtype=np.float64)
     tri_c, plane_c = np.ascontiguousarray(tri.reshape(-1, 9)), np.ascontiguousarray(plane)
     org = np.ascontiguousarray(origin, dtype=np.float64)
