@@ -154,17 +154,19 @@ def test_gp_prepare_chol_qsqrt_kl_vs_oracle(M):
 
 
 def _select_sampler(eng, grid):
-    """grid=5: register-resident warp-specialised DMMA sampler (the float64 default when the points fit 12 row tiles);
+    """grid=5 / 7: register-resident warp-specialised DMMA sampler (the float64 default when the points fit 12 row tiles),
+    one 8-sample tile per CTA pass / up to four (pathwise_rrm_kernel, what 9..63 samples get on a full GPU);
     grid=3: shared-memory DMMA sampler (up to 192 points, else the general kernel); grid=0: general per-point sincos
     kernel.  All three are float64 and stop at the prior draw; preparation + pathwise update run in their own kernel.
     The tensor-core (3xTF32) sampler is switched off here: it has its own tolerance-gated tests."""
     eng.set_option("tc_sampler", 0)
     eng.set_option("grid_fast_path", int(grid > 0))
     eng.set_option("dmma_sampler", int(grid >= 3))
-    eng.set_option("rr_sampler", int(grid == 5))
+    eng.set_option("rr_sampler", int(grid in (5, 7)))
+    eng.set_option("rrm_min_ctas", 0 if grid == 7 else 1 << 30)   # 7: multi-tile passes whenever S > 8; 5: one tile per pass
 
 
-@pytest.mark.parametrize("grid", [5, 3, 0])
+@pytest.mark.parametrize("grid", [7, 5, 3, 0])
 @pytest.mark.parametrize("S,N,M,B", [(7, 70, 24, 64), (3, 5, 1, 3), (20, 50, 7, 40), (9, 150, 12, 33), (8, 2, 2, 32),
                                      (17, 300, 30, 70), (203, 12, 5, 16), (7, 70, 24, 1024), (5, 150, 30, 100)])
 def test_pathwise_sample_vs_oracle(S, N, M, B, grid):
@@ -212,7 +214,7 @@ def test_pathwise_sample_irregular_inputs_fall_back_to_general_kernel():
     ("kuka", "industrial", dict(B=96)),                           # config 3 shapes: S=20, N=50, M=7
     ("ur10", "bookshelves", dict(B=64, S=33)),                    # config 4 robot (D=6), more samples than one tile
 ])
-@pytest.mark.parametrize("grid", [5, 3, 0])
+@pytest.mark.parametrize("grid", [7, 5, 3, 0])
 def test_elbo_and_gradients_vs_oracle(name, env, kw, grid):
     """grid: 5 = register-resident warp-specialised DMMA sampler (default), 3 = shared-memory DMMA sampler,
     0 = general sincos sampler (see _select_sampler)."""
@@ -309,6 +311,60 @@ def test_pipelined_device_draws_training_vs_oracle():
                 pr["q_sqrt"] = np.tril(pr["q_sqrt"])
                 assert H.rel_err(_np(model._q_mu[b]), pr["q_mu"]) < 1e-6, (mode, step)
                 assert H.rel_err(_np(model._lengthscales[b]), O.softplus(pr["raw_ls"])) < 1e-6, (mode, step)
+
+
+def test_full_training_trajectory_of_the_reference_problem_vs_oracle():
+    """The whole optimisation of solve_planning_problem (utils/miscellaneous.py:87-103 with franka.py:91-104's planner_params:
+    130 Adam steps, S=7, N=70, M=24, B=1024) on two Franka problems, every step fed the same explicit draws as the oracle.
+    (a) ALONG the oracle's trajectory: at each of the 130 states the CUDA ELBO and gradients match the oracle's (1e-8 / 1e-5).
+    (b) FREE-RUNNING: both sides are float64, but the dynamics amplify rounding differences (cond(Khat) ~ 1e7 puts ~1e-11
+        into the first gradient; Adam's normalised steps and the nearest-voxel lookup grow it by ~15 % per step): the
+        parameters agree to 1e-6 over the first 50 steps, and the step at which a sphere first lands in a different voxel
+        (a jump in the error) is reported, not asserted."""
+    case = H.make_case("franka", "bookshelves", num_problems=2, B=1024, seed=130, perturb=False)
+    steps = int(case["pp"]["num_steps"])
+    assert steps == 130 and case["S"] == 7 and case["N"] == 70 and case["M"] == 24
+    model, probe = H.make_model(case), H.make_model(case)
+    eng = probe._eng
+    M, lr = case["M"], case["pp"]["learning_rate"]
+    rng = np.random.default_rng(2024)
+    states = [O.AdamState() for _ in case["oracle"]]
+    params = [dict(q_mu=case["q_mu"][b].copy(), q_sqrt=case["q_sqrt"][b].copy(),
+                   raw_ls=O.softplus_inv(case["ls"][b]), raw_var=O.softplus_inv(case["var"][b])) for b in range(2)]
+    tril = np.tril(np.ones((M, M)))
+    sig = lambda x: 1.0 / (1.0 + np.exp(-x))
+    errs = np.zeros((steps, 2))
+    for step in range(steps):
+        draws = [O.make_draws(rng, 7, 7, 1024, M + 2) for _ in range(2)]
+        stacked = {k: np.stack([d[k] for d in draws]) for k in draws[0]}
+        # (a) the CUDA path evaluated AT the oracle's current state
+        probe._q_mu.copy_(eng.dev(np.stack([pr["q_mu"] for pr in params])))
+        probe._q_sqrt.copy_(eng.dev(np.stack([pr["q_sqrt"] for pr in params])))
+        probe._lengthscales.copy_(eng.dev(np.stack([O.softplus(pr["raw_ls"]) for pr in params])))
+        probe._variances.copy_(eng.dev(np.stack([O.softplus(pr["raw_var"]) for pr in params])))
+        at = probe.elbo_and_grads(case["X"], draws=stacked)
+        model.train_step(case["X"], draws=stacked)                       # (b) free-running
+        for b, p in enumerate(case["oracle"]):
+            pr = params[b]
+            ref = O.elbo_and_grads(p, pr["q_mu"], pr["q_sqrt"], O.softplus(pr["raw_ls"]), O.softplus(pr["raw_var"]), draws[b])
+            assert abs(float(at["elbo"][b]) - ref["elbo"]) <= 1e-8 * abs(ref["elbo"]), (step, b)
+            for key in ("q_mu", "q_sqrt", "lengthscales", "variances"):
+                assert H.rel_err(_np(at["d_" + key][b]), ref["d_" + key]) < 1e-5, (step, b, key)
+            O.adam_step(pr, dict(q_mu=-ref["d_q_mu"], q_sqrt=-ref["d_q_sqrt"] * tril,
+                                 raw_ls=-ref["d_lengthscales"] * sig(pr["raw_ls"]),
+                                 raw_var=-ref["d_variances"] * sig(pr["raw_var"])), states[b], lr)
+            pr["q_sqrt"] = np.tril(pr["q_sqrt"])
+            errs[step, b] = max(H.rel_err(_np(model._q_mu[b]), pr["q_mu"]), H.rel_err(_np(model._q_sqrt[b]), pr["q_sqrt"]),
+                                H.rel_err(_np(model._lengthscales[b]), O.softplus(pr["raw_ls"])),
+                                H.rel_err(_np(model._variances[b]), O.softplus(pr["raw_var"])))
+    worst = errs.max(axis=1)
+    first = {tol: (int(np.argmax(worst > tol)) if (worst > tol).any() else None) for tol in (1e-9, 1e-6, 1e-3)}
+    growth = worst[1:] / np.maximum(worst[:-1], 1e-300)
+    jump = int(np.argmax(growth > 20.0)) + 1 if (growth[5:] > 20.0).any() else None
+    print(f"130-step free-running trajectory vs oracle: parameter error after 10/50/100/130 steps "
+          f"{worst[9]:.1e}/{worst[49]:.1e}/{worst[99]:.1e}/{worst[-1]:.1e}; first step beyond 1e-9/1e-6/1e-3: "
+          f"{first[1e-9]}/{first[1e-6]}/{first[1e-3]}; first >20x jump (a voxel flip): step {jump}")
+    assert worst[:50].max() < 1e-6      # (max-norm relative error over each parameter block, see tests/helpers.py:rel_err)
 
 
 def test_trainable_flags_freeze_parameters():
@@ -649,19 +705,21 @@ def test_errors_are_reported_not_swallowed():
         eng.gp_prepare(eng.dims(1, 31, 5, 2, 8), model._params(None))
 
 
-@pytest.mark.parametrize("scenario", ["equispaced", "irregular_inputs", "long_grid", "sample_shard"])
+@pytest.mark.parametrize("scenario", ["equispaced", "irregular_inputs", "long_grid", "sample_shard", "multi_tile"])
 def test_lazy_draws_are_bit_identical_to_materialised_draws(scenario):
     """train_step's default: omega / tau / w are never written to memory, the sampler's producer warps regenerate them from
     the Philox keys (`vgpmp_rng_fill_lazy`).  Same keys, same arithmetic -> the optimisation trajectory must equal, bit for
     bit, the one driven by materialised draws.  irregular_inputs: the device-side probe rejects the grid, the draws are
     written right before the general sampler; long_grid: 150 points do not fit the register-resident sampler, the draws
     are written before the shared-memory DMMA sampler; sample_shard: rank 1 of 2 in the single-problem large-sample mode
-    (non-zero sample offset in the Philox keys, several sample tiles per CTA)."""
+    (non-zero sample offset in the Philox keys, several sample tiles per CTA); multi_tile: the multi-tile sampler."""
     kw = dict(num_problems=3, S=9, N=40, M=10, B=96, seed=17)
     if scenario == "long_grid":
         kw.update(N=150, S=5)
     if scenario == "sample_shard":
         kw.update(num_problems=1, S=38)
+    if scenario == "multi_tile":
+        kw.update(S=27, N=50, M=7)        # 4 tiles of 8 samples per CTA pass (pathwise_rrm_kernel), ragged last tile
     case = H.make_case(**kw)
     X = case["X"].copy()
     if scenario == "irregular_inputs":
@@ -672,6 +730,8 @@ def test_lazy_draws_are_bit_identical_to_materialised_draws(scenario):
         if scenario == "sample_shard":
             model.enable_sample_sharding(1, 2)
         model.lazy_draws = lazy
+        if scenario == "multi_tile":
+            model._eng.set_option("rrm_min_ctas", 0)
         losses = [model.train_step(X).clone() for _ in range(3)]
         runs[lazy] = (torch.stack(losses), model._q_mu.clone(), model._q_sqrt.clone(), model._lengthscales.clone(),
                       model._variances.clone())

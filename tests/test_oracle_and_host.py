@@ -2,6 +2,7 @@
 host-side logic, and the C-ABI library's symbol table.  No GPU compute."""
 import ctypes
 import re
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -298,3 +299,43 @@ def test_oracle_fourier_features_reproduce_the_matern52_kernel():
     r = np.abs(x[:, None] - x[None, :]) / ell
     want = var * O.matern52(O._t(r)).numpy()
     assert np.abs(est - want).max() < 4 * var * np.sqrt(0.5 / omega.size) * 2
+
+
+# ---------------------------------------------------------------- URDF extraction vs the lifted tables
+REFERENCE_ROBOTS = Path("/root/reference/data/robots")
+
+
+@pytest.mark.skipif(not REFERENCE_ROBOTS.exists(), reason="needs the reference checkout (its URDFs are not copied into this repo)")
+@pytest.mark.parametrize("name,urdf", [("franka", "franka_spheres.urdf"), ("kuka", "kuka.urdf"), ("wam", "wam.urdf"),
+                                       ("ur10", "ur10.urdf")])
+def test_robot_from_urdf_reproduces_the_lifted_tables(name, urdf):
+    """`Robot.from_urdf` (replaces the pybullet visual-shape walk of utils/robot.py:482-550) run on the reference's own URDF +
+    config.yaml must give exactly the constants lifted into vgpmp_b200/data/robots.json (what every test and bench uses)."""
+    import yaml
+    from vgpmp_b200.utils.robot import Robot
+    cfg = yaml.safe_load((REFERENCE_ROBOTS / name / "config.yaml").read_text())
+    cfg = cfg["robot"] if "robot" in cfg else cfg
+    a = Robot.from_urdf(name, cfg, REFERENCE_ROBOTS / name / urdf)
+    b = Robot.from_tables(name)
+    assert a.dof == b.dof and a.num_spheres == b.num_spheres and a.craig_notation == b.craig_notation
+    assert list(a.num_spheres_per_link) == list(b.num_spheres_per_link) and list(a.fk_slice) == list(b.fk_slice)
+    assert np.array_equal(np.asarray(a.sphere_offsets), np.asarray(b.sphere_offsets))
+    assert np.array_equal(np.asarray(a.sphere_radii), np.asarray(b.sphere_radii))
+    assert np.array_equal(a.DH, b.DH) and np.array_equal(a.twist, b.twist)
+    assert np.array_equal(np.asarray(a.joint_limits), np.asarray(b.joint_limits))
+    # and, through the Sampler's get_mat remaps, the constants the kernels receive
+    from vgpmp_b200.utils.sampler import Sampler
+    ca, cb = Sampler(None, a).constants(), Sampler(None, b).constants()
+    for f in ("dh", "twist", "base_pose", "sphere_frame", "sphere_offsets", "sphere_radii", "limits_lo", "limits_hi"):
+        assert np.array_equal(getattr(ca, f), getattr(cb, f)), f
+
+
+def test_mesh_sdf_vectorised_matches_the_scalar_checker():
+    """bench.py's CPU arm builds its bookshelves grid with `mesh_sdf_vectorised`; it must equal the scalar brute force that
+    checks the GPU producer."""
+    from vgpmp_b200.utils.gen_sdf import grid_geometry, load_obj_convex_pieces, scene_mesh_path
+    tri, plane, piece_end = load_obj_convex_pieces(scene_mesh_path("bookshelves"))
+    origin, shape = grid_geometry(tri, 0.15, 1)
+    a = O.mesh_sdf_np(tri, plane, piece_end, origin, 0.15, shape)
+    b = O.mesh_sdf_vectorised(tri, plane, piece_end, origin, 0.15, shape, chunk=97)
+    assert (a < 0).any() and np.abs(a - b).max() < 1e-12

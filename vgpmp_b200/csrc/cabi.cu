@@ -81,7 +81,7 @@ GpScratch carve(void* ws, int D, const vgpmp_dims& d, size_t* total, int num_sms
   g.meta = c.take(8);
   g.loss = c.take(Bp);
   g.lik_part = c.take(Bp * (size_t)elbo_reduce_segments(num_sms, (int)Bp, (int)(S * N)));
-  const size_t np = backward_partial_doubles(num_sms, (int)(Bp * D), (int)S);
+  const size_t np = backward_partial_doubles(num_sms, (int)(Bp * D), (int)S, (int)N);
   g.partial = np ? c.take(np) : nullptr;
   *total = c.off;
   return g;
@@ -246,6 +246,7 @@ int vgpmp_set_option(vgpmp_handle* h, const char* name, int value) {
   if (std::strcmp(name, "dmma_sampler") == 0) { h->allow_dmma_path = value != 0; return VGPMP_OK; }
   if (std::strcmp(name, "rr_sampler") == 0) { h->allow_rr_path = value != 0; return VGPMP_OK; }
   if (std::strcmp(name, "lazy_draws") == 0) { h->allow_lazy_draws = value != 0; return VGPMP_OK; }
+  if (std::strcmp(name, "rrm_min_ctas") == 0) { h->rrm_min_ctas = value; return VGPMP_OK; }
   if (std::strcmp(name, "tc_sampler") == 0) { h->allow_tc_path = value != 0; return VGPMP_OK; }
   return fail(h, VGPMP_ERR_INVALID, std::string("set_option: unknown option ") + name);
 }

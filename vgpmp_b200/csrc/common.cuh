@@ -71,6 +71,7 @@ struct vgpmp_handle {
   bool allow_tc_path = true;    // tcgen05 / TMEM 3xTF32 sampler for large sample counts (sampler_tc.cu)
   bool allow_dmma_path = true;  // shared-memory DMMA sampler (N + M + 2 <= 192), else the general kernel
   bool allow_rr_path = true;    // register-resident warp-specialised DMMA sampler (<= 12 point tiles), else the shared-memory one
+  int rrm_min_ctas = -1;        // multi-tile register-resident sampler only if it still launches this many CTAs (-1: 2 per SM)
   bool allow_grid_path = true;  // equispaced rank-1 fast path of the pathwise sampler (vgpmp_set_option)
   bool profiling = false;
   struct Span { int stage; cudaEvent_t a, b; };
@@ -107,7 +108,7 @@ struct GpScratch {  // carved from the caller's workspace by cabi.cu
   double* lik_part; // [Bp * segments] partial sums of the ELBO reduction (few problems, many samples)
   double* partial; // reverse-pass partial sums when the sample loop is split over CTAs (else nullptr)
 };
-size_t backward_partial_doubles(int num_sms, int pairs, int S);
+size_t backward_partial_doubles(int num_sms, int pairs, int S, int N);
 
 cudaError_t launch_kuu(vgpmp_handle* h, const double* Z, const double* ls, const double* var, double jitter, double* K,
                        int Bp, int M, cudaStream_t s);

@@ -905,6 +905,262 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// Register-resident sampler for 9 .. 63 samples (e.g. the reference's S = 20 planner_params of Kuka / WAM / Franka-industrial):
+// NT tiles of 8 samples per CTA pass.  pathwise_rr_kernel above repeats the whole producer pass (Philox, 6 sincos per basis)
+// for every 8-sample tile and issues 2 DMMAs per rotation; here a consumer warp owns a QUARTER OF THE POINT TILES (3 of 12)
+// for ALL NT sample tiles and walks every 4-basis step: one rotation feeds 2 NT DMMAs, accumulators are 12 NT registers,
+// the basis tables are produced once per 8 NT samples, and no cross-warp fold is needed (a warp's tiles are its own).
+// A warp that does not start at row 0 of a grid multiplies the row starts by the group phasor E8^(tile offset) the
+// producers add to the slot.  Slot entry per basis: Sx[8] | E8x | Sz[8] | E8z | e0 | e1 | c/l^2 | pad | P1 P2 P3 | w[8 NT].
+// ---------------------------------------------------------------------------------------------
+constexpr int kRMW = 48;       // first weight of a slot entry
+
+template <int NT, bool GEN>
+__global__ void __launch_bounds__(256, 2) pathwise_rrm_kernel(PathwiseArgs a, const double* __restrict__ meta) {
+  constexpr int kRC = 4, kRP = 4;                // consumer / producer warps
+  constexpr int kTPW = kRT / kRC;                // point tiles per consumer warp
+  constexpr int kEM = kRMW + 8 * NT;             // doubles per basis in a slot
+  constexpr int kSamples = 8 * NT;
+  extern __shared__ __align__(16) double sm[];
+  const int D = a.D, M = a.M, Nq = a.Nq, S = a.S, B = a.B, A = Nq + M + 2;
+  const int JX = (Nq + 2 + 7) / 8;               // tiles holding the query grid and the two conditioned endpoints
+  const int tpw = (JX + (M + 7) / 8 + kRC - 1) / kRC;   // tiles per consumer warp actually in use (<= kTPW): the useful tiles, evenly
+  const int pl = blockIdx.x / a.nchunk;
+  const int s0 = (blockIdx.x % a.nchunk) * a.chunk, ns = min(kSamples, S - s0);   // a.chunk == 8 NT
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt_ = blockDim.x;
+  const int T = (B + kRB - 1) / kRB;
+  constexpr int ROWS = kRT * 8;
+  constexpr size_t kFold = (size_t)2 * kSamples * ROWS, kRing = (size_t)kRS * kRB * kEM;
+  double* tab = sm;                              // [kRS][kRB][kEM]
+  double* red = sm;                              // after the basis loop: [2][8 NT][ROWS]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + (kFold > kRing ? kFold : kRing));
+  uint64_t* empty = full + kRS;
+
+  if (meta[0] == 0.0) return;  // not an equispaced rank-1 grid: the general kernel does the sampling
+  if (tid == 0) {
+    for (int i = 0; i < kRS; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, kRC); }
+  }
+  const double ell = a.ls[pl], s2 = a.var[pl];
+  const double amp = sqrt(2.0 * s2 / (double)B), inv_ell = 1.0 / ell;
+  const double t0 = meta[1], dt = meta[2], z0 = meta[3], dz = meta[4];
+  const int g = lane >> 2, t4 = lane & 3;
+  __syncthreads();
+  if (warp >= kRC) {
+    // ---------------- producer: slots n = pw, pw + kRP, ... ----------------
+    const int pw = warp - kRC;
+    const double* om = GEN ? nullptr : a.omega + (size_t)pl * B * D;
+    const double* ta = GEN ? nullptr : a.tau + (size_t)pl * B;
+    const double* wp = GEN ? nullptr : a.w + (size_t)pl * S * B;
+    const uint64_t pairkey = ((uint64_t)(pl / D) + (uint64_t)a.problem_offset) * (uint64_t)D + (uint64_t)(pl % D);
+    const uint32_t B4 = ((uint32_t)B + 3) / 4;
+    for (int n = pw; n < T; n += kRP) {
+      const int slot = n % kRS, use = n / kRS;
+      const int b = n * kRB + lane;
+      const bool live = b < B;
+      double c = 0.0, taub = 0.0;
+      if (GEN) {
+        if (live) {
+          const uint64_t key = pairkey * (uint64_t)B + (uint64_t)b;
+          double z[16];
+          const int ncall = (5 + D + 3) / 4;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < ncall) normal4(a.seed, a.iteration, 1u, key * 4 + k, z + 4 * k);
+          const double gam = (z[0] * z[0] + z[1] * z[1] + z[2] * z[2] + z[3] * z[3] + z[4] * z[4]) / 5.0;
+          const double rs = rsqrt(gam);
+#pragma unroll
+          for (int d = 0; d < VGPMP_MAX_DOF; ++d)
+            if (d < D) c = __dadd_rn(c, __dmul_rn(z[5 + d], rs));   // as stored then summed by the load path: no FMA
+          uint32_t cc[4] = {(uint32_t)key, (uint32_t)(key >> 32), (uint32_t)a.iteration, 3u};
+          philox4x32(cc, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+          taub = 6.283185307179586476925 * u01(cc[0], cc[1]);
+        }
+      } else if (live) {
+        for (int d = 0; d < D; ++d) c += __ldg(om + (size_t)b * D + d);
+        taub = __ldg(ta + b);
+      }
+      const double cb = c * inv_ell;
+      const double ab = live ? amp : 0.0;
+      const double ax0 = t0 * cb + taub, ax1 = dt * cb, az0 = z0 * cb + taub, az1 = dz * cb, ae1 = cb + taub;
+      const double arg[6] = {ax0, ax1, az0, az1, taub, ae1};
+      double sv[6], cv[6];
+      const double big = fmax(fmax(fabs(ax0), fabs(ax1)), fmax(fmax(fabs(az0), fabs(az1)), fmax(fabs(taub), fabs(ae1))));
+      if (big < 1048576.0) {
+        sincos_bf6(arg, sv, cv);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sincos(arg[k], &sv[k], &cv[k]);
+      }
+      double sdx = sv[1], cdx = cv[1], sdz = sv[3], cdz = cv[3];
+      mbar_wait(empty + slot, (use & 1) ^ 1);            // consumers are done with the slot's previous contents
+      double* e = tab + ((size_t)slot * kRB + lane) * kEM;
+      double c1 = ab * cv[0], s1 = ab * sv[0], c2 = ab * cv[2], s2z = ab * sv[2];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        *reinterpret_cast<double2*>(e + 2 * r) = make_double2(c1, s1);
+        *reinterpret_cast<double2*>(e + 18 + 2 * r) = make_double2(c2, s2z);
+        const double n1 = c1 * cdx - s1 * sdx, n2 = c2 * cdz - s2z * sdz;
+        s1 = s1 * cdx + c1 * sdx; s2z = s2z * cdz + c2 * sdz;
+        c1 = n1; c2 = n2;
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {   // E^8 by three squarings
+        const double n1 = cdx * cdx - sdx * sdx, n2 = cdz * cdz - sdz * sdz;
+        sdx = 2.0 * cdx * sdx; sdz = 2.0 * cdz * sdz;
+        cdx = n1; cdz = n2;
+      }
+      *reinterpret_cast<double2*>(e + 16) = make_double2(cdx, sdx);
+      *reinterpret_cast<double2*>(e + 34) = make_double2(cdz, sdz);
+      *reinterpret_cast<double2*>(e + 36) = make_double2(ab * cv[4], ab * sv[4]);
+      *reinterpret_cast<double2*>(e + 38) = make_double2(ab * cv[5], ab * sv[5]);
+      *reinterpret_cast<double2*>(e + 40) = make_double2(cb * inv_ell, 0.0);
+      // group phasors: consumer warp w starts at tile 3 w, i.e. E8x^(3w) on the query grid or E8z^(3w - JX) on the inducing grid
+      {
+        double px = 1.0, qx = 0.0, pz = 1.0, qz = 0.0;
+        int jx = 0, jz = 0;                              // powers reached so far
+#pragma unroll
+        for (int w = 1; w < kRC; ++w) {
+          const int j0 = w * tpw;
+          double oc, os;
+          if (j0 < JX) {
+            while (jx < j0) { const double nn = px * cdx - qx * sdx; qx = qx * cdx + px * sdx; px = nn; ++jx; }
+            oc = px; os = qx;
+          } else {
+            while (jz < j0 - JX) { const double nn = pz * cdz - qz * sdz; qz = qz * cdz + pz * sdz; pz = nn; ++jz; }
+            oc = pz; os = qz;
+          }
+          *reinterpret_cast<double2*>(e + 40 + 2 * w) = make_double2(oc, os);
+        }
+      }
+      // weights of the 8 NT samples
+      if (GEN) {
+        const uint32_t b4 = (uint32_t)n * (kRB / 4) + (uint32_t)(lane >> 2);
+        double* eq = tab + ((size_t)slot * kRB + (lane & ~3)) * kEM + kRMW + (lane & 3);   // row of basis 4*quad, column of sample r
+#pragma unroll
+        for (int hh = 0; hh < 2 * NT; ++hh) {
+          const int i = (lane & 3) + 4 * hh;
+          double z4[4] = {0.0, 0.0, 0.0, 0.0};
+          if (i < ns && 4 * b4 < (uint32_t)B) {
+            const uint64_t sg = (uint64_t)(s0 + i) + (uint64_t)a.sample_offset;
+            normal4(a.seed, a.iteration, 4u, (pairkey * (uint64_t)(1u << 24) + sg) * B4 + b4, z4);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool okb = n * kRB + (lane & ~3) + k < B;
+            eq[(size_t)k * kEM + 4 * hh] = okb ? z4[k] : 0.0;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < kSamples; ++i)
+          e[kRMW + i] = (live && i < ns) ? __ldg(wp + (size_t)(s0 + i) * B + b) : 0.0;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full + slot);
+    }
+  } else {
+    // ---------------- consumer: point tiles [3 warp, 3 warp + 3), every 4-basis step ----------------
+    double acc[kTPW][2][NT][2];
+#pragma unroll
+    for (int j = 0; j < kTPW; ++j)
+#pragma unroll
+      for (int i = 0; i < NT; ++i) acc[j][0][i][0] = acc[j][0][i][1] = acc[j][1][i][0] = acc[j][1][i][1] = 0.0;
+    const int j0 = warp * tpw;
+    // per-tile roles of this lane's row (loop invariant): 0 chain value, 1 / 2 conditioned endpoint 0 / 1, 3 padding (zero);
+    // sw: the inducing grid starts at this tile (reload the row start, no group offset)
+    int mode[kTPW];
+    bool sw[kTPW];
+#pragma unroll
+    for (int jj = 0; jj < kTPW; ++jj) {
+      const int j = j0 + jj, ex = 8 * j + g - Nq;
+      mode[jj] = (j < JX && ex >= 0) ? (ex < 2 ? 1 + ex : 3) : 0;
+      sw[jj] = jj > 0 && j == JX;
+    }
+    const bool startx = j0 < JX;
+    const int Q = T * (kRB / 4);
+    // (fetching a step's operands one step ahead was tried: 3.40 -> 3.88 ms at 1024 Kuka problems, the extra live registers
+    // cost more than the exposed shared-memory round trip)
+    int cur = -1;
+    for (int q = 0; q < Q; ++q) {
+      const int n = q / (kRB / 4);
+      if (n != cur) {
+        if (cur >= 0) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(empty + cur % kRS);
+        }
+        mbar_wait(full + n % kRS, (n / kRS) & 1);
+        cur = n;
+      }
+      const double* e = tab + ((size_t)(n % kRS) * kRB + (q % (kRB / 4)) * 4 + t4) * kEM;
+      double wk[NT], wq[NT];
+      const double cl = e[40];
+#pragma unroll
+      for (int i = 0; i < NT; ++i) { wk[i] = e[kRMW + 8 * i + g]; wq[i] = wk[i] * cl; }
+      double2 ph = *reinterpret_cast<const double2*>(e + (startx ? 0 : 18) + 2 * g);
+      double2 st = *reinterpret_cast<const double2*>(e + (startx ? 16 : 34));
+      if (warp > 0) {
+        const double2 po = *reinterpret_cast<const double2*>(e + 40 + 2 * warp);
+        const double c2 = ph.x * po.x - ph.y * po.y;
+        ph.y = ph.y * po.x + ph.x * po.y;
+        ph.x = c2;
+      }
+#pragma unroll
+      for (int jj = 0; jj < kTPW; ++jj) {
+        if (jj >= tpw) break;
+        if (sw[jj]) {
+          ph = *reinterpret_cast<const double2*>(e + 18 + 2 * g);
+          st = *reinterpret_cast<const double2*>(e + 34);
+        }
+        double ac = ph.x, as = ph.y;
+        if (mode[jj] != 0) {
+          const double2 ep = mode[jj] < 3 ? *reinterpret_cast<const double2*>(e + 36 + 2 * (mode[jj] - 1)) : make_double2(0.0, 0.0);
+          ac = ep.x; as = ep.y;
+        }
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+          dmma884(acc[jj][0][i][0], acc[jj][0][i][1], ac, wk[i]);
+          dmma884(acc[jj][1][i][0], acc[jj][1][i][1], as, wq[i]);
+        }
+        const double c2 = ph.x * st.x - ph.y * st.y;
+        ph.y = ph.y * st.x + ph.x * st.y;
+        ph.x = c2;
+      }
+    }
+    __syncwarp();
+    if (cur >= 0 && lane == 0) mbar_arrive(empty + cur % kRS);
+    // the ring is dead only after ALL consumers left the loop
+    asm volatile("bar.sync 1, %0;" ::"r"(kRC * 32) : "memory");
+#pragma unroll
+    for (int jj = 0; jj < kTPW; ++jj)
+#pragma unroll
+      for (int f = 0; f < 2; ++f)
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+#pragma unroll
+          for (int e2 = 0; e2 < 2; ++e2)
+            if (jj < tpw) red[((size_t)f * kSamples + 8 * i + 2 * t4 + e2) * ROWS + (j0 + jj) * 8 + g] = acc[jj][f][i][e2];
+  }
+  __syncthreads();
+  // rows -> points: query rows x < Nq, endpoints Nq, Nq+1, inducing rows after
+  for (int idx = tid; idx < 2 * kSamples * ROWS; idx += nt_) {
+    const int wh = idx / (kSamples * ROWS), i = (idx / ROWS) % kSamples, row = idx % ROWS;
+    int point = -1;
+    double coord = 0.0;
+    if (row < JX * 8) {
+      if (row < Nq) { point = row; coord = t0 + dt * row; }
+      else if (row < Nq + 2) { point = row; coord = (double)(row - Nq); }
+    } else {
+      const int m = row - JX * 8;
+      if (m < M) { point = Nq + 2 + m; coord = z0 + dz * m; }
+    }
+    if (i < ns && point >= 0) {
+      if (wh == 0) { if (a.f0 != nullptr) a.f0[((size_t)pl * S + s0 + i) * A + point] = red[idx]; }
+      else if (a.h0 != nullptr) a.h0[((size_t)pl * S + s0 + i) * A + point] = red[idx] * coord;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // GP preparation fused with the pathwise update (used behind the DMMA sampler, which only needs the draws and the
 // lengthscale): one CTA of 128 threads per (problem, latent[, sample chunk]).  gp_prepare_body leaves L, L^-1, q_sqrt_full,
 // mu and Zy in shared memory; every warp then finishes whole samples on its own, no CTA barrier between them:
@@ -1353,6 +1609,191 @@ __global__ void __launch_bounds__(256, 4) gp_backward_kernel(BackwardArgs a) {
   if (tid >= 2 && tid < Mp) a.d_q_mu[((size_t)p * M + tid - 2) * D + l] = gmu[tid];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sample phase of the reverse pass for many samples per (problem, latent) (num_samples >= 64): the same sums as the sample
+// loop of gp_backward_kernel, organised as small GEMMs over tiles of 32 samples on the FP64 tensor path (DMMA m8n8k4):
+//   GV = DF Kfu            [32 x N][N x Mp]        gv[s,m] = sum_n Kfu[n,m] df[s,n]
+//   GR = (GV Li^T) Li      [32 x Mp][Mp x Mp] x2   gr = Khat^-1 gv
+//   T += DF^T V            [N x 32][32 x Mp]       hyper-parameter path through Kfu (contracted with dKfu/dtheta at the end)
+//   G -= GR^T V,  GS += GR^T EPS                   d ELBO / d Khat, d ELBO / d q_sqrt_full
+//   gmu += sum_s GR,  prior path: <[DF | -GR], f0>, <[DF | -GR], h0>
+// One CTA of 256 threads per (pair, chunk of samples); T, G, GS live in DMMA accumulator registers for the whole chunk.  The
+// result goes out in gp_backward_kernel's partial-sum format; gp_backward_kernel<2> folds the chunks in fixed order and
+// runs the sample-independent phase.  (The 8-sample tiles, six CTA barriers per tile and per-tile Matern evaluations of
+// gp_backward_kernel cost 57 ms per step at 8192 problems x 256 samples.)
+// ---------------------------------------------------------------------------------------------
+constexpr int kBS = 32;    // samples per tile of the batched reverse pass
+constexpr int kLD = 36;    // leading dimension of 32-wide DMMA operands: the 8 rows x 4 lanes of a fragment hit 16 distinct double banks
+
+__host__ __device__ inline int dmma_ld(int n) {   // smallest ld >= n with ld % 16 == 4 (same bank argument for wider operands)
+  const int n4 = (n + 3) & ~3;
+  return n4 + ((4 - (n4 & 15)) + 16) % 16;
+}
+
+// C[8x8] += A[8 x 4 KS] B[4 KS x 8];  A row-major (this warp's 8 rows), Bn "n-major": element (k, n) at Bn[n * ldb + k]
+template <int KS>
+__device__ __forceinline__ void wmma_rn(double& c0, double& c1, const double* __restrict__ A, int lda,
+                                        const double* __restrict__ Bn, int ldb, int g, int t) {
+#pragma unroll
+  for (int k = 0; k < KS; ++k) dmma884(c0, c1, A[g * lda + 4 * k + t], Bn[g * ldb + 4 * k + t]);
+}
+// same with A given transposed: element (row, k) at At[k * lda + row]
+template <int KS>
+__device__ __forceinline__ void wmma_tn(double& c0, double& c1, const double* __restrict__ At, int lda,
+                                        const double* __restrict__ Bn, int ldb, int g, int t) {
+#pragma unroll
+  for (int k = 0; k < KS; ++k) dmma884(c0, c1, At[(4 * k + t) * lda + g], Bn[g * ldb + 4 * k + t]);
+}
+
+template <int NTILES>   // point tiles of 8 (N <= 8 NTILES)
+__global__ void __launch_bounds__(256, 2) gp_backward_samples_kernel(BackwardArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const int D = a.D, M = a.M, Mp = M + 2, N = a.N, S = a.S, A = N + Mp;
+  const int pl = blockIdx.x / a.nchunk, p = pl / D, l = pl % D;
+  const int s_begin = (blockIdx.x % a.nchunk) * a.chunk, s_end = min(S, s_begin + a.chunk);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  constexpr int NP = NTILES * 8;
+  const int ldN = dmma_ld(NP);
+  double* Li = sm;                       // [32][kLD]   L^-1 (lower)
+  double* LiT = Li + 32 * kLD;           // [32][kLD]   its transpose
+  double* KT = LiT + 32 * kLD;           // [32][ldN]   Kfu transposed: KT[m][n]
+  double* DF = KT + 32 * ldN;            // [32][ldN]   this tile's d ELBO / d f
+  double* VT = DF + 32 * ldN;            // [32][kLD]   v transposed: VT[m][s]
+  double* ET = VT + 32 * kLD;            // [32][kLD]   eps_u transposed
+  double* B1 = ET + 32 * kLD;            // [32][kLD]   GV, then GR
+  double* B2 = B1 + 32 * kLD;            // [32][kLD]   Y = GV Li^T
+  double* gmu = B2 + 32 * kLD;           // [32]
+  double* zy = gmu + 32;                 // [32]
+  double* red = zy + 32;                 // [8]
+  const double ell = a.ls[pl], s2 = a.var[pl], inv_ell = 1.0 / ell;
+  for (int idx = tid; idx < 2 * 32 * kLD + 32 * ldN; idx += nt) sm[idx] = 0.0;     // Li, LiT, KT (padding must be zero)
+  if (tid < 32) { zy[tid] = tid < Mp ? zy_at(a.Z, D, l, tid) : 0.0; gmu[tid] = 0.0; }
+  __syncthreads();
+  for (int i = warp; i < Mp; i += nw)
+    if (lane < Mp) {
+      const double v = a.Linv[(size_t)pl * Mp * Mp + i * Mp + lane];
+      Li[i * kLD + lane] = v;
+      LiT[lane * kLD + i] = v;
+    }
+  for (int idx = tid; idx < Mp * N; idx += nt) {
+    const int m = idx / N, n = idx - m * N;
+    KT[m * ldN + n] = s2 * vg_matern52(fabs(a.X[(size_t)n * D + l] - zy[m]) * inv_ell);
+  }
+  // persistent accumulators: T tiles (NTILES x 4), G and GS tiles (4 x 4 each) dealt round-robin to the 8 warps
+  constexpr int kTT = (NTILES * 4 + 7) / 8;
+  double accT[kTT][2], accG[2][2], accS[2][2];
+#pragma unroll
+  for (int i = 0; i < kTT; ++i) accT[i][0] = accT[i][1] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) accG[i][0] = accG[i][1] = accS[i][0] = accS[i][1] = 0.0;
+  double acc_ls = 0.0, acc_var = 0.0;
+  const double* dfp = a.df + (size_t)p * S * N * D + l;
+
+  for (int s0 = s_begin; s0 < s_end; s0 += kBS) {
+    const int ns = min(kBS, s_end - s0);
+    __syncthreads();                                    // previous tile fully consumed
+    for (int idx = tid; idx < kBS * NP; idx += nt) {    // DF[s][n], zero padded
+      const int i = idx / NP, n = idx - i * NP;
+      DF[i * ldN + n] = (i < ns && n < N) ? dfp[((size_t)(s0 + i) * N + n) * D] : 0.0;
+    }
+    for (int idx = tid; idx < kBS * 32; idx += nt) {    // VT[m][s], ET[m][s]
+      const int i = idx >> 5, m = idx & 31;
+      const bool ok = i < ns && m < Mp;
+      VT[m * kLD + i] = ok ? a.v[((size_t)pl * S + s0 + i) * Mp + m] : 0.0;
+      ET[m * kLD + i] = ok ? a.eps_u[((size_t)pl * S + s0 + i) * Mp + m] : 0.0;
+    }
+    __syncthreads();
+    // GV = DF KT^T: 4 x 4 output tiles, 2 per warp
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int tile = warp * 2 + u, mi = tile >> 2, ni = tile & 3;
+      double c0 = 0.0, c1 = 0.0;
+      wmma_rn<NTILES * 2>(c0, c1, DF + mi * 8 * ldN, ldN, KT + ni * 8 * ldN, ldN, g, t);
+      *reinterpret_cast<double2*>(B1 + (mi * 8 + g) * kLD + ni * 8 + 2 * t) = make_double2(c0, c1);
+    }
+    __syncthreads();
+    // Y = GV Li^T  (element (k, n) of the right operand = Li[n][k]: Li itself is n-major)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int tile = warp * 2 + u, mi = tile >> 2, ni = tile & 3;
+      double c0 = 0.0, c1 = 0.0;
+      wmma_rn<8>(c0, c1, B1 + mi * 8 * kLD, kLD, Li + ni * 8 * kLD, kLD, g, t);
+      *reinterpret_cast<double2*>(B2 + (mi * 8 + g) * kLD + ni * 8 + 2 * t) = make_double2(c0, c1);
+    }
+    __syncthreads();
+    // GR = Y Li  (right operand element (k, n) = Li[k][n] = LiT[n][k])
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int tile = warp * 2 + u, mi = tile >> 2, ni = tile & 3;
+      double c0 = 0.0, c1 = 0.0;
+      wmma_rn<8>(c0, c1, B2 + mi * 8 * kLD, kLD, LiT + ni * 8 * kLD, kLD, g, t);
+      *reinterpret_cast<double2*>(B1 + (mi * 8 + g) * kLD + ni * 8 + 2 * t) = make_double2(c0, c1);
+    }
+    __syncthreads();
+    // T += DF^T V ; G -= GR^T V ; GS += GR^T EPS   (K = the 32 samples of the tile)
+#pragma unroll
+    for (int u = 0; u < kTT; ++u) {
+      const int tile = warp + 8 * u;
+      if (tile < NTILES * 4) {
+        const int ni_ = tile >> 2, mi_ = tile & 3;      // point tile, inducing tile
+        wmma_tn<8>(accT[u][0], accT[u][1], DF + ni_ * 8, ldN, VT + mi_ * 8 * kLD, kLD, g, t);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int tile = warp * 2 + u, ii = tile >> 2, jj = tile & 3;
+      wmma_tn<8>(accG[u][0], accG[u][1], B1 + ii * 8, kLD, VT + jj * 8 * kLD, kLD, g, t);
+      wmma_tn<8>(accS[u][0], accS[u][1], B1 + ii * 8, kLD, ET + jj * 8 * kLD, kLD, g, t);
+    }
+    if (tid < 32) {
+      double tsum = 0.0;
+      for (int i = 0; i < ns; ++i) tsum += B1[i * kLD + tid];
+      gmu[tid] += tsum;
+    }
+    // prior path: d f0(X) = df, d f0(Zy) = -gr
+    for (int idx = tid; idx < ns * A; idx += nt) {
+      const int i = idx / A, xx = idx - i * A;
+      const double gg = xx < N ? DF[i * ldN + xx] : -B1[i * kLD + xx - N];
+      const size_t o = ((size_t)pl * S + s0 + i) * A + xx;
+      acc_var += gg * a.f0[o] / (2.0 * s2);
+      acc_ls += gg * a.h0[o];
+    }
+  }
+  // hyper-parameter path through Kfu: sum_{n,m} T[n,m] dKfu[n,m]/dtheta
+#pragma unroll
+  for (int u = 0; u < kTT; ++u) {
+    const int tile = warp + 8 * u;
+    if (tile < NTILES * 4) {
+      const int n = (tile >> 2) * 8 + g;
+#pragma unroll
+      for (int e2 = 0; e2 < 2; ++e2) {
+        const int m = (tile & 3) * 8 + 2 * t + e2;
+        if (n < N && m < Mp) {
+          const double r = fabs(a.X[(size_t)n * D + l] - zy[m]) * inv_ell;
+          double k, dk;
+          matern52_both(r, k, dk);
+          acc_var += accT[u][e2] * k;
+          acc_ls += accT[u][e2] * s2 * dk * (-r * inv_ell);
+        }
+      }
+    }
+  }
+  // publish the chunk's partial sums in gp_backward_kernel's format: G | GS (32 x 32 each) | gmu | acc_var | acc_ls
+  double* part = a.partial + (size_t)blockIdx.x * kPartial;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int tile = warp * 2 + u, i = (tile >> 2) * 8 + g, j = (tile & 3) * 8 + 2 * t;
+    part[i * 32 + j] = -accG[u][0];          part[i * 32 + j + 1] = -accG[u][1];
+    part[1024 + i * 32 + j] = accS[u][0];    part[1024 + i * 32 + j + 1] = accS[u][1];
+  }
+  __syncthreads();
+  if (tid < 32) part[2048 + tid] = gmu[tid];
+  const double tv = block_sum(acc_var, red);
+  const double tl = block_sum(acc_ls, red);
+  if (tid == 0) { part[2080] = tv; part[2081] = tl; }
+}
+
 // SVGP posterior mean at Xq (GPflow posterior().predict_f with whiten=False, models/vgpmp.py:315):
 //   mean[n,l] = Kfu[n,:] Khat^-1 q_mu_full[:,l]        one CTA per (problem, latent)
 __global__ void __launch_bounds__(128) predict_mean_kernel(int D, int M, int Nq, vgpmp_params P,
@@ -1653,6 +2094,27 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
     if (tc_path) {
       if ((e = launch_pathwise_tc(h, a, pairs, meta, s)) != cudaSuccess) return e;
     } else if (rr_path) {
+      // 9 .. 63 samples: NT tiles of 8 samples per CTA pass (pathwise_rrm_kernel), as long as that leaves enough CTAs
+      const int tiles = (a.S + kST - 1) / kST;
+      int NT = std::min(4, tiles);
+      const size_t min_ctas = h->rrm_min_ctas >= 0 ? (size_t)h->rrm_min_ctas : (size_t)2 * h->num_sms;
+      while (NT > 1 && (size_t)pairs * ((tiles + NT - 1) / NT) < min_ctas) --NT;
+      if (NT > 1) {
+        NT = (tiles + ((tiles + NT - 1) / NT) - 1) / ((tiles + NT - 1) / NT);     // balance the passes
+        a.chunk = NT * kST;
+        a.nchunk = (a.S + a.chunk - 1) / a.chunk;
+        const size_t ring = (size_t)kRS * kRB * (kRMW + 8 * NT), fold = (size_t)2 * 8 * NT * kRT * 8;
+        const size_t smem_r = sizeof(double) * (std::max(ring, fold) + 2 * kRS);
+        void (*kern)(PathwiseArgs, const double*) = nullptr;
+        switch (NT) {
+          case 2: kern = a.gen_draws ? pathwise_rrm_kernel<2, true> : pathwise_rrm_kernel<2, false>; break;
+          case 3: kern = a.gen_draws ? pathwise_rrm_kernel<3, true> : pathwise_rrm_kernel<3, false>; break;
+          default: kern = a.gen_draws ? pathwise_rrm_kernel<4, true> : pathwise_rrm_kernel<4, false>; break;
+        }
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)) != cudaSuccess) return e;
+        kern<<<pairs * a.nchunk, 256, smem_r, s>>>(a, meta);
+        h->launches++;
+      } else {
       const size_t ring = (size_t)kRS * kRB * kRE, fold = (size_t)4 * 2 * kST * kRT * 8;
       const size_t smem_r = sizeof(double) * (std::max(ring, fold) + 2 * kRS);
       void (*kern)(PathwiseArgs, const double*) = nullptr;
@@ -1672,6 +2134,7 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
       if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)) != cudaSuccess) return e;
       kern<<<pairs * a.nchunk, 256, smem_r, s>>>(a, meta);
       h->launches++;
+      }
     } else {
       const int PT = A <= 96 ? 3 : 6, ROWS = 32 * PT;
       const size_t main_view = (size_t)2 * ROWS * kDBP + 3 * kDB * kWS + 3 * 4 * kDB + 3 * kDB + 8 * kDB * 2 + 2 * (2 * kDB * 2);
@@ -1723,19 +2186,32 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
 }
 
 // split of the reverse pass's sample loop: only when there are too few (problem, latent) pairs to fill the GPU
-void backward_chunks(int num_sms, int pairs, int S, int* nchunk, int* chunk) {
+// How the reverse pass splits its sample loop.  S >= 64 (and N <= 96): the DMMA-batched sample kernel over (pair, chunk)
+// CTAs, chunks a multiple of its 32-sample tile, then the fold kernel.  Otherwise the fused kernel, split into
+// partial-sum CTAs only when there are too few (problem, latent) pairs to fill the GPU.
+bool backward_plan(int num_sms, int pairs, int S, int N, int* nchunk, int* chunk) {
+  const bool batched = S >= 64 && N <= 96;
+  if (batched) {
+    const int want = std::max(1, (4 * num_sms + pairs - 1) / std::max(1, pairs));
+    const int n = std::max(1, std::min(want, (S + 63) / 64));
+    const int c = (((S + n - 1) / n) + kBS - 1) / kBS * kBS;
+    *chunk = c;
+    *nchunk = (S + c - 1) / c;
+    return true;
+  }
   const int tiles = (S + kBT - 1) / kBT;
   int want = (2 * num_sms) / std::max(1, pairs);
   int n = std::max(1, std::min(tiles / 4, want));      // at least 4 tiles per chunk, else the fused kernel wins
   const int c = ((tiles + n - 1) / n) * kBT;
   *chunk = c;
   *nchunk = (S + c - 1) / c;
+  return false;
 }
 
-size_t backward_partial_doubles(int num_sms, int pairs, int S) {
+size_t backward_partial_doubles(int num_sms, int pairs, int S, int N) {
   int n, c;
-  backward_chunks(num_sms, pairs, S, &n, &c);
-  return n > 1 ? (size_t)pairs * n * kPartial : 0;
+  const bool batched = backward_plan(num_sms, pairs, S, N, &n, &c);
+  return (batched || n > 1) ? (size_t)pairs * n * kPartial : 0;
 }
 
 cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
@@ -1753,10 +2229,35 @@ cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp
   const size_t smem = sizeof(double) * (3 * 32 * LDM + kreg + 4 * kBT * 32 + 4 * 32 + 16 + (size_t)kBT * a.N);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   const int pairs = d.num_problems * a.D;
-  backward_chunks(h->num_sms, pairs, a.S, &a.nchunk, &a.chunk);
+  const bool batched = backward_plan(h->num_sms, pairs, a.S, a.N, &a.nchunk, &a.chunk) && ws.partial != nullptr;
   a.partial = ws.partial;
   cudaError_t e;
-  if (a.nchunk <= 1 || ws.partial == nullptr) {
+  if (batched) {
+    const int ntiles = (a.N + 7) / 8;
+    const size_t smem_b = sizeof(double) * (6 * 32 * kLD + 2 * 32 * (size_t)dmma_ld(ntiles * 8) + 72);
+    void (*kern)(BackwardArgs) = nullptr;
+    switch (ntiles) {
+      case 1: kern = gp_backward_samples_kernel<1>; break;
+      case 2: kern = gp_backward_samples_kernel<2>; break;
+      case 3: kern = gp_backward_samples_kernel<3>; break;
+      case 4: kern = gp_backward_samples_kernel<4>; break;
+      case 5: kern = gp_backward_samples_kernel<5>; break;
+      case 6: kern = gp_backward_samples_kernel<6>; break;
+      case 7: kern = gp_backward_samples_kernel<7>; break;
+      case 8: kern = gp_backward_samples_kernel<8>; break;
+      case 9: kern = gp_backward_samples_kernel<9>; break;
+      case 10: kern = gp_backward_samples_kernel<10>; break;
+      case 11: kern = gp_backward_samples_kernel<11>; break;
+      default: kern = gp_backward_samples_kernel<12>; break;
+    }
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(gp_backward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+      return e;
+    kern<<<pairs * a.nchunk, 256, smem_b, s>>>(a);
+    gp_backward_kernel<2><<<pairs, 256, smem, s>>>(a);
+    h->launches += 2;
+  } else if (a.nchunk <= 1 || ws.partial == nullptr) {
+    if (ws.partial == nullptr) { a.nchunk = 1; a.chunk = a.S; }
     if ((e = cudaFuncSetAttribute(gp_backward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
       return e;
     gp_backward_kernel<0><<<pairs, 256, smem, s>>>(a);
