@@ -360,7 +360,8 @@ def test_full_training_trajectory_of_the_reference_problem_vs_oracle():
     worst = errs.max(axis=1)
     first = {tol: (int(np.argmax(worst > tol)) if (worst > tol).any() else None) for tol in (1e-9, 1e-6, 1e-3)}
     growth = worst[1:] / np.maximum(worst[:-1], 1e-300)
-    jump = int(np.argmax(growth > 20.0)) + 1 if (growth[5:] > 20.0).any() else None
+    late = np.nonzero(growth[20:] > 20.0)[0]                 # (the first steps grow fast from ~1e-12; a flip shows later as a jump)
+    jump = int(late[0]) + 21 if late.size else None
     print(f"130-step free-running trajectory vs oracle: parameter error after 10/50/100/130 steps "
           f"{worst[9]:.1e}/{worst[49]:.1e}/{worst[99]:.1e}/{worst[-1]:.1e}; first step beyond 1e-9/1e-6/1e-3: "
           f"{first[1e-9]}/{first[1e-6]}/{first[1e-3]}; first >20x jump (a voxel flip): step {jump}")

@@ -652,7 +652,8 @@ __global__ void __launch_bounds__(256, 3) pathwise_dmma_kernel(PathwiseArgs a, c
 //              into a 4-slot ring handed over with mbarriers (one arrival per warp).
 // ---------------------------------------------------------------------------------------------
 constexpr int kRB = 32;        // bases per table slot
-constexpr int kRE = 50;        // doubles per basis in a slot: Sx[8] | E8x | Sz[8] | E8z | e0 | e1 | c/l | pad | w[8 samples]
+constexpr int kRE = 52;        // doubles per basis in a slot: Sx[8] | E8x | Sz[8] | E8z | e0 | e1 | c/l | pad | w[8 samples] | pad
+                               // (kRE % 16 == 4: the 4 bases x 8 rows a consumer warp reads at once hit distinct banks)
 constexpr int kRS = 4;         // ring slots
 constexpr int kRT = 12;        // point tiles (rows / 8) a consumer carries
 
@@ -919,7 +920,8 @@ template <int NT, bool GEN>
 __global__ void __launch_bounds__(256, 2) pathwise_rrm_kernel(PathwiseArgs a, const double* __restrict__ meta) {
   constexpr int kRC = 4, kRP = 4;                // consumer / producer warps
   constexpr int kTPW = kRT / kRC;                // point tiles per consumer warp
-  constexpr int kEM = kRMW + 8 * NT;             // doubles per basis in a slot
+  constexpr int kEM = (kRMW + 8 * NT + 11) / 16 * 16 + 4;   // doubles per basis in a slot, padded to 4 mod 16: the 4 bases x 8
+                                                           // rows a consumer warp reads at once then hit distinct banks
   constexpr int kSamples = 8 * NT;
   extern __shared__ __align__(16) double sm[];
   const int D = a.D, M = a.M, Nq = a.Nq, S = a.S, B = a.B, A = Nq + M + 2;
@@ -1068,30 +1070,33 @@ __global__ void __launch_bounds__(256, 2) pathwise_rrm_kernel(PathwiseArgs a, co
     const int j0 = warp * tpw;
     // per-tile roles of this lane's row (loop invariant): 0 chain value, 1 / 2 conditioned endpoint 0 / 1, 3 padding (zero);
     // sw: the inducing grid starts at this tile (reload the row start, no group offset)
-    int mode[kTPW];
-    bool sw[kTPW];
+    // (packed into one word: 2 bits of role + 1 bit of sw per tile - kept as arrays the compiler re-derived them in every
+    // step of the basis loop, 12 % of the kernel's instructions)
+    unsigned roles = 0;
 #pragma unroll
     for (int jj = 0; jj < kTPW; ++jj) {
       const int j = j0 + jj, ex = 8 * j + g - Nq;
-      mode[jj] = (j < JX && ex >= 0) ? (ex < 2 ? 1 + ex : 3) : 0;
-      sw[jj] = jj > 0 && j == JX;
+      const unsigned md = (j < JX && ex >= 0) ? (ex < 2 ? 1u + ex : 3u) : 0u;
+      roles |= (md | ((jj > 0 && j == JX) ? 4u : 0u)) << (3 * jj);
     }
+    asm volatile("" : "+r"(roles));                // opaque from here on: one register, extracted by shifts
     const bool startx = j0 < JX;
     const int Q = T * (kRB / 4);
     // (fetching a step's operands one step ahead was tried: 3.40 -> 3.88 ms at 1024 Kuka problems, the extra live registers
     // cost more than the exposed shared-memory round trip)
     int cur = -1;
-    for (int q = 0; q < Q; ++q) {
-      const int n = q / (kRB / 4);
-      if (n != cur) {
+    const double* e = tab;
+    for (int q = 0; q < Q; ++q, e += 4 * kEM) {
+      if ((q & (kRB / 4 - 1)) == 0) {                 // first step of slot n = q / 8
+        const int n = q / (kRB / 4);
         if (cur >= 0) {
           __syncwarp();
           if (lane == 0) mbar_arrive(empty + cur % kRS);
         }
         mbar_wait(full + n % kRS, (n / kRS) & 1);
         cur = n;
+        e = tab + ((size_t)(n % kRS) * kRB + t4) * kEM;
       }
-      const double* e = tab + ((size_t)(n % kRS) * kRB + (q % (kRB / 4)) * 4 + t4) * kEM;
       double wk[NT], wq[NT];
       const double cl = e[40];
 #pragma unroll
@@ -1107,13 +1112,15 @@ __global__ void __launch_bounds__(256, 2) pathwise_rrm_kernel(PathwiseArgs a, co
 #pragma unroll
       for (int jj = 0; jj < kTPW; ++jj) {
         if (jj >= tpw) break;
-        if (sw[jj]) {
+        const unsigned role = (roles >> (3 * jj)) & 7u;
+        if (role & 4u) {
           ph = *reinterpret_cast<const double2*>(e + 18 + 2 * g);
           st = *reinterpret_cast<const double2*>(e + 34);
         }
         double ac = ph.x, as = ph.y;
-        if (mode[jj] != 0) {
-          const double2 ep = mode[jj] < 3 ? *reinterpret_cast<const double2*>(e + 36 + 2 * (mode[jj] - 1)) : make_double2(0.0, 0.0);
+        if (role & 3u) {
+          const unsigned md = role & 3u;
+          const double2 ep = md < 3u ? *reinterpret_cast<const double2*>(e + 36 + 2 * (md - 1)) : make_double2(0.0, 0.0);
           ac = ep.x; as = ep.y;
         }
 #pragma unroll
@@ -1794,6 +1801,110 @@ __global__ void __launch_bounds__(256, 2) gp_backward_samples_kernel(BackwardArg
   if (tid == 0) { part[2080] = tv; part[2081] = tl; }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pathwise update for many samples per (problem, latent), batched as small GEMMs on the FP64 tensor path (the S >= 64
+// companion of the tensor-core sampler; pathwise_update_kernel above is its warp-per-sample form, ~9x the instructions):
+//   U = mu + EPS S^T;  R = U - F0(Zy) - sqrt(jitter) EPSJ;  Y = R Li^T;  V = Y Li;  F = F0(X) + V Kfu^T
+// One CTA of 256 threads per (pair, chunk of samples); a warp owns a tile of 8 samples end to end (its operands chain
+// through a private shared-memory tile, so the sample loop has no CTA barrier).
+// ---------------------------------------------------------------------------------------------
+template <int NTILES>   // point tiles of 8 (Nq <= 8 NTILES)
+__global__ void __launch_bounds__(256, 2) pathwise_update_mma_kernel(PathwiseArgs a, const double* __restrict__ meta, int chunk) {
+  extern __shared__ __align__(16) double sm[];
+  if (meta[0] == 0.0) return;                         // general sampler does its own update
+  const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, A = Nq + Mp;
+  const int nchunk = (S + chunk - 1) / chunk;
+  const int pl = blockIdx.x / nchunk, p = pl / D, l = pl % D;
+  const int s_begin = (blockIdx.x % nchunk) * chunk, s_end = min(S, s_begin + chunk);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  double* Ss = sm;                                    // [32][kLD]  q_sqrt_full, n-major for U = EPS S^T
+  double* Li = Ss + 32 * kLD;                         // [32][kLD]  L^-1
+  double* LiT = Li + 32 * kLD;                        // [32][kLD]
+  double* KF = LiT + 32 * kLD;                        // [8 NTILES][kLD]  Kfu[n][m] (n-major for F = V Kfu^T)
+  double* mu = KF + (size_t)NTILES * 8 * kLD;         // [32]
+  double* zy = mu + 32;                               // [32]
+  double* tiles = zy + 32;                            // [nw][2][8][kLD] per-warp operand tiles
+  const double ell = a.ls[pl], s2 = a.var[pl], sqrtj = sqrt(a.jitter), inv_ell = 1.0 / ell;
+  for (int idx = tid; idx < (3 * 32 + NTILES * 8) * kLD; idx += nt) sm[idx] = 0.0;
+  if (tid < 32) {
+    zy[tid] = tid < Mp ? zy_at(a.Z, D, l, tid) : 0.0;
+    mu[tid] = tid >= Mp ? 0.0 : (tid < 2 ? a.query_latent[((size_t)p * 2 + tid) * D + l] : a.q_mu[((size_t)p * M + tid - 2) * D + l]);
+  }
+  __syncthreads();
+  for (int i = warp; i < Mp; i += nw)
+    if (lane < Mp) {
+      const double v = a.Linv[(size_t)pl * Mp * Mp + i * Mp + lane];
+      Li[i * kLD + lane] = v;
+      LiT[lane * kLD + i] = v;
+      Ss[i * kLD + lane] = a.Sfull[(size_t)pl * Mp * Mp + i * Mp + lane];
+    }
+  for (int idx = tid; idx < Nq * Mp; idx += nt) {
+    const int n = idx / Mp, m = idx - n * Mp;
+    KF[n * kLD + m] = s2 * vg_matern52(fabs(a.Xq[(size_t)n * D + l] - zy[m]) * inv_ell);
+  }
+  __syncthreads();
+  double* T0 = tiles + (size_t)warp * 2 * 8 * kLD;    // [8][kLD]
+  double* T1 = T0 + 8 * kLD;
+  for (int s0 = s_begin + warp * 8; s0 < s_end; s0 += nw * 8) {
+    const int ns = min(8, s_end - s0);
+    const size_t ps0 = (size_t)pl * S + s0;
+    // T0 <- EPS tile [8 samples][32]
+    for (int idx = lane; idx < 8 * 32; idx += 32) {
+      const int i = idx >> 5, m = idx & 31;
+      T0[i * kLD + m] = (i < ns && m < Mp) ? a.eps_u[(ps0 + i) * Mp + m] : 0.0;
+    }
+    __syncwarp();
+    // R = mu + EPS S^T - F0(Zy) - sqrt(jitter) EPSJ  -> T1      (right operand element (k, n) = S[n][k]: Ss is n-major)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      double c0 = 0.0, c1 = 0.0;
+      wmma_rn<8>(c0, c1, T0, kLD, Ss + ni * 8 * kLD, kLD, g, t);
+      const int m0 = ni * 8 + 2 * t;
+      double r0 = 0.0, r1 = 0.0;
+      if (g < ns) {
+        if (m0 < Mp) r0 = mu[m0] + c0 - a.f0[(ps0 + g) * A + Nq + m0] - sqrtj * a.eps_j[(ps0 + g) * Mp + m0];
+        if (m0 + 1 < Mp) r1 = mu[m0 + 1] + c1 - a.f0[(ps0 + g) * A + Nq + m0 + 1] - sqrtj * a.eps_j[(ps0 + g) * Mp + m0 + 1];
+      }
+      *reinterpret_cast<double2*>(T1 + g * kLD + m0) = make_double2(r0, r1);
+    }
+    __syncwarp();
+    // Y = R Li^T -> T0
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      double c0 = 0.0, c1 = 0.0;
+      wmma_rn<8>(c0, c1, T1, kLD, Li + ni * 8 * kLD, kLD, g, t);
+      *reinterpret_cast<double2*>(T0 + g * kLD + ni * 8 + 2 * t) = make_double2(c0, c1);
+    }
+    __syncwarp();
+    // V = Y Li -> T1 (and to memory for the reverse pass)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      double c0 = 0.0, c1 = 0.0;
+      wmma_rn<8>(c0, c1, T0, kLD, LiT + ni * 8 * kLD, kLD, g, t);
+      const int m0 = ni * 8 + 2 * t;
+      *reinterpret_cast<double2*>(T1 + g * kLD + m0) = make_double2(c0, c1);
+      if (a.v != nullptr && g < ns) {
+        if (m0 < Mp) a.v[(ps0 + g) * Mp + m0] = c0;
+        if (m0 + 1 < Mp) a.v[(ps0 + g) * Mp + m0 + 1] = c1;
+      }
+    }
+    __syncwarp();
+    // F = F0(X) + V Kfu^T        (right operand element (k = m, n) = Kfu[n][m]: KF is n-major)
+#pragma unroll
+    for (int ni = 0; ni < NTILES; ++ni) {
+      double c0 = 0.0, c1 = 0.0;
+      wmma_rn<8>(c0, c1, T1, kLD, KF + ni * 8 * kLD, kLD, g, t);
+      const int n0 = ni * 8 + 2 * t;
+      if (g < ns) {
+        if (n0 < Nq) a.f[(((size_t)p * S + s0 + g) * Nq + n0) * D + l] = c0 + a.f0[(ps0 + g) * A + n0];
+        if (n0 + 1 < Nq) a.f[(((size_t)p * S + s0 + g) * Nq + n0 + 1) * D + l] = c1 + a.f0[(ps0 + g) * A + n0 + 1];
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // SVGP posterior mean at Xq (GPflow posterior().predict_f with whiten=False, models/vgpmp.py:315):
 //   mean[n,l] = Kfu[n,:] Khat^-1 q_mu_full[:,l]        one CTA per (problem, latent)
 __global__ void __launch_bounds__(128) predict_mean_kernel(int D, int M, int Nq, vgpmp_params P,
@@ -2103,7 +2214,7 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
         NT = (tiles + ((tiles + NT - 1) / NT) - 1) / ((tiles + NT - 1) / NT);     // balance the passes
         a.chunk = NT * kST;
         a.nchunk = (a.S + a.chunk - 1) / a.chunk;
-        const size_t ring = (size_t)kRS * kRB * (kRMW + 8 * NT), fold = (size_t)2 * 8 * NT * kRT * 8;
+        const size_t ring = (size_t)kRS * kRB * ((kRMW + 8 * NT + 11) / 16 * 16 + 4), fold = (size_t)2 * 8 * NT * kRT * 8;
         const size_t smem_r = sizeof(double) * (std::max(ring, fold) + 2 * kRS);
         void (*kern)(PathwiseArgs, const double*) = nullptr;
         switch (NT) {
@@ -2150,10 +2261,32 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
       // many samples per pair: the Cholesky once per pair, then the update over (pair, sample chunk) CTAs
       if ((e = launch_gp_prepare(h, d, p, Lc, Sfull, kl_l, kvec, Linv, s)) != cudaSuccess) return e;
       const int chunk = (size_t)pairs * ((a.S + 127) / 128) >= (size_t)8 * h->num_sms ? 128 : 64;
+      const int ntiles = (Nq + 7) / 8;
+      if (ntiles <= 12) {
+        const size_t smem_u = sizeof(double) * ((size_t)(3 * 32 + ntiles * 8) * kLD + 64 + (size_t)8 * 2 * 8 * kLD);
+        void (*kern)(PathwiseArgs, const double*, int) = nullptr;
+        switch (ntiles) {
+          case 1: kern = pathwise_update_mma_kernel<1>; break;
+          case 2: kern = pathwise_update_mma_kernel<2>; break;
+          case 3: kern = pathwise_update_mma_kernel<3>; break;
+          case 4: kern = pathwise_update_mma_kernel<4>; break;
+          case 5: kern = pathwise_update_mma_kernel<5>; break;
+          case 6: kern = pathwise_update_mma_kernel<6>; break;
+          case 7: kern = pathwise_update_mma_kernel<7>; break;
+          case 8: kern = pathwise_update_mma_kernel<8>; break;
+          case 9: kern = pathwise_update_mma_kernel<9>; break;
+          case 10: kern = pathwise_update_mma_kernel<10>; break;
+          case 11: kern = pathwise_update_mma_kernel<11>; break;
+          default: kern = pathwise_update_mma_kernel<12>; break;
+        }
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u)) != cudaSuccess) return e;
+        kern<<<pairs * ((a.S + chunk - 1) / chunk), 256, smem_u, s>>>(a, meta, chunk);
+      } else {
       const size_t smem_u = sizeof(double) * (2 * 32 * LDM + (size_t)Mp * (Nq | 1) + 64 + 8 * 32);
       if ((e = cudaFuncSetAttribute(pathwise_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u)) != cudaSuccess)
         return e;
       pathwise_update_kernel<<<pairs * ((a.S + chunk - 1) / chunk), 256, smem_u, s>>>(a, meta, chunk);
+      }
     } else {
       gp_prepare_update_kernel<<<pairs * a.nchunk, 128, 0, s>>>(a, p, Lc, Sfull, kl_l, kvec, Linv, meta);
     }

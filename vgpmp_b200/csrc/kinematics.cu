@@ -97,6 +97,55 @@ __device__ __forceinline__ Voxel sdf_voxel(const SdfDev& s, double x, double y, 
   return v;
 }
 
+// The same index for a coordinate that is ALREADY relative to the grid origin, without the double<->int conversions
+// (quarter-rate on sm_100): q + 1.5 * 2^52 leaves rint(q) in the low mantissa word, r = q - rint(q) gives floor and the
+// distance to the nearest integer in full-rate FP64 adds.  Negative q clips to 0 under trunc and under floor alike.  Returns
+// false when q sits within 1e-9 of an integer (or is absurdly large / NaN): the caller then takes the exact path above.
+__device__ __forceinline__ bool voxel_index_fast(double a, double inv_delta, int n, int& idx) {
+  const double q = a * inv_delta;
+  const double t = q + 6755399441055744.0;
+  const double r = q - (t - 6755399441055744.0);
+  int i = __double2loint(t);
+  if (r < 0.0) --i;
+  idx = min(max(i, 0), n - 1);
+  return fabs(r) > 1e-9 && fabs(q) < 1.0e9;
+}
+
+// grid-relative position -> voxel (fast path for all three axes, exact path if any of them asks for it)
+__device__ __forceinline__ Voxel sdf_voxel_rel(const SdfDev& s, double x, double y, double z) {
+  Voxel v;
+  const bool ok = voxel_index_fast(x, s.inv_delta, s.nx, v.ix) & voxel_index_fast(y, s.inv_delta, s.ny, v.iy) &
+                  voxel_index_fast(z, s.inv_delta, s.nz, v.iz);
+  if (!ok) {
+    v.ix = voxel_index(x, s.delta, s.inv_delta, s.nx);
+    v.iy = voxel_index(y, s.delta, s.inv_delta, s.ny);
+    v.iz = voxel_index(z, s.delta, s.inv_delta, s.nz);
+  }
+  return v;
+}
+
+// one branch-free double sincos for |x| < 2^20 (joint angles): three-term Cody-Waite reduction by pi/2, Taylor kernels on
+// [-pi/4, pi/4] truncated below 1e-17 (the arithmetic of sincos_bf6 in device_utils.cuh); the library sincos carries a
+// Payne-Hanek slow path and ~2x the instructions
+__device__ __forceinline__ void sincos_small(double x, double& sn, double& cs) {
+  const double nq = rint(x * 0.63661977236758134308);
+  const int q = __double2int_rn(nq);
+  const double r = fma(-nq, 6.123233995736766e-17, fma(-nq, 1.5707963267948966, x));
+  const double z = r * r;
+  double ps = 1.0 / 1307674368000.0, pc = 1.0 / 20922789888000.0;
+  ps = fma(ps, -z, 1.0 / 6227020800.0);  pc = fma(pc, -z, 1.0 / 87178291200.0);
+  ps = fma(ps, -z, 1.0 / 39916800.0);    pc = fma(pc, -z, 1.0 / 479001600.0);
+  ps = fma(ps, -z, 1.0 / 362880.0);      pc = fma(pc, -z, 1.0 / 3628800.0);
+  ps = fma(ps, -z, 1.0 / 5040.0);        pc = fma(pc, -z, 1.0 / 40320.0);
+  ps = fma(ps, -z, 1.0 / 120.0);         pc = fma(pc, -z, 1.0 / 720.0);
+  ps = fma(ps, -z, 1.0 / 6.0);           pc = fma(pc, -z, 1.0 / 24.0);
+  pc = fma(pc, -z, 0.5);
+  const double s = fma(-z * r, ps, r), c = fma(-z, pc, 1.0);
+  const double a = (q & 1) ? c : s, b = (q & 1) ? s : c;
+  sn = (q & 2) ? -a : a;
+  cs = ((q + 1) & 2) ? -b : b;
+}
+
 __device__ __forceinline__ size_t sdf_cell(const SdfDev& s, int ix, int iy, int iz) {
   return ((size_t)ix * s.ny + iy) * s.nz + iz;
 }
@@ -324,15 +373,158 @@ __global__ void __launch_bounds__(kThreads, 3) loglik_kernel(RobotDev rb, SdfDev
   }
 }
 
+// Fused likelihood WITH its reverse pass, two sweeps over the kinematic chain.  (The one-sweep form above parks 8 doubles per
+// joint and thread in shared memory for the final joint-gradient formula: 56 KB per CTA, i.e. 3 CTAs per SM and, with the
+// carve-out that takes, little L1 left for the record loads - which matters once the grid lives in HBM.)
+//   sweep 1  joints + spheres in chain order, as above: log-probability, total wrench (F, T), and per joint the prefix term
+//            p_j = z_j . T_{<j} - (z_j x o_j) . F_{<j} in REGISTERS (the joint loop is unrolled); sin / cos of the joint angle
+//            and the squash derivative go to shared memory (3 doubles per joint: 21 KB per CTA at D = 7);
+//   sweep 2  the chain again from the stored sin / cos (frame products only, no transcendental, no sphere):
+//            d theta_j = z_j . T - (z_j x o_j) . F - p_j.
+// Sphere positions come from exactly the same operations as before, so voxel indices (hence parity) are unchanged.
+__device__ __forceinline__ void frame_step_sc(const RobotDev& rb, int j, double st, double ct, Frame& A) {
+  const double d = rb.dh[j][0], a = rb.dh[j][1];
+  const double ca = rb.cos_alpha[j], sa = rb.sin_alpha[j];
+  double T[12];
+  if (rb.craig) {
+    T[0] = ct;      T[1] = -st;     T[2] = 0.0;  T[3] = a;
+    T[4] = st * ca; T[5] = ct * ca; T[6] = -sa;  T[7] = -d * sa;
+    T[8] = st * sa; T[9] = ct * sa; T[10] = ca;  T[11] = d * ca;
+  } else {
+    T[0] = ct;  T[1] = -st * ca; T[2] = st * sa;  T[3] = a * ct;
+    T[4] = st;  T[5] = ct * ca;  T[6] = -ct * sa; T[7] = a * st;
+    T[8] = 0.0; T[9] = sa;       T[10] = ca;      T[11] = d;
+  }
+  Frame B;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double r0 = A.r[3 * i], r1 = A.r[3 * i + 1], r2 = A.r[3 * i + 2];
+    B.r[3 * i + 0] = r0 * T[0] + r1 * T[4] + r2 * T[8];
+    B.r[3 * i + 1] = r0 * T[1] + r1 * T[5] + r2 * T[9];
+    B.r[3 * i + 2] = r0 * T[2] + r1 * T[6] + r2 * T[10];
+    B.t[i] = r0 * T[3] + r1 * T[7] + r2 * T[11] + A.t[i];
+  }
+  A = B;
+}
+
+template <int D, int NB, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) loglik_bwd_kernel(RobotDev rb, SdfDev sdf, LikDev lk,
+                                                                   const double* __restrict__ in, int squash, double upstream,
+                                                                   double* __restrict__ logp, double* __restrict__ d_in,
+                                                                   int64_t n) {
+  extern __shared__ double trig[];  // [D][4][kThreads]  sin, cos of the joint angle, d theta / d in, prefix term
+  const int tid = threadIdx.x;
+  const int64_t c = (int64_t)blockIdx.x * kThreads + tid;
+  if (c >= n) return;
+
+  // The chain is walked in GRID coordinates (base translation shifted by -(scene offset + grid origin)): a sphere centre
+  // is then directly the voxel coordinate numerator, and the joint-gradient formula is invariant under a common shift of
+  // sphere centres and axis points.
+  const double shx = lk.offset[0] + sdf.origin[0], shy = lk.offset[1] + sdf.origin[1], shz = lk.offset[2] + sdf.origin[2];
+  Frame A;
+  frame_from_base(rb, A);
+  A.t[0] -= shx; A.t[1] -= shy; A.t[2] -= shz;
+  double Fw[3] = {0.0, 0.0, 0.0}, Tw[3] = {0.0, 0.0, 0.0};  // running wrench of the spheres seen so far
+  double lp = 0.0;
+  const double inv_sigma = 1.0 / lk.sigma_obs;
+  double xnext = in[c * D];   // joint inputs are fetched one joint ahead of their use
+
+#pragma unroll 1
+  for (int k = 0; k <= D; ++k) {
+    if (k > 0) {
+      const int j = k - 1;
+      const double xin = xnext;
+      if (k < D) xnext = in[c * D + k];
+      lp += xin - xin;     // 0 for a finite input; NaN / Inf inputs must not vanish in the voxel clip and the hinge's fmax
+      double thj = xin, dsq = 1.0;
+      if (squash) {
+        const double sg = stable_sigmoid(xin), span = rb.hi[j] - rb.lo[j];
+        thj = rb.lo[j] + span * sg;
+        dsq = span * sg * (1.0 - sg);
+      }
+      double st, ct;
+      const double ang = thj + rb.twist[j];
+      if (fabs(ang) < 1048576.0) sincos_small(ang, st, ct);
+      else sincos(ang, &st, &ct);
+      double* slot = trig + (size_t)j * 4 * kThreads + tid;
+      slot[0] = st; slot[kThreads] = ct; slot[2 * kThreads] = dsq;
+      double zx, zy, zz, ox, oy, oz;
+      if (!rb.craig) {  // Spong: joint j turns about z of frame j-1, through its origin
+        zx = A.r[2]; zy = A.r[5]; zz = A.r[8]; ox = A.t[0]; oy = A.t[1]; oz = A.t[2];
+      }
+      frame_step_sc(rb, j, st, ct, A);
+      if (rb.craig) {   // Craig: joint j turns about z of frame j (its own frame), through its origin
+        zx = A.r[2]; zy = A.r[5]; zz = A.r[8]; ox = A.t[0]; oy = A.t[1]; oz = A.t[2];
+      }
+      const double nx = zy * oz - zz * oy, ny = zz * ox - zx * oz, nz = zx * oy - zy * ox;
+      slot[3 * kThreads] = zx * Tw[0] + zy * Tw[1] + zz * Tw[2] - (nx * Fw[0] + ny * Fw[1] + nz * Fw[2]);
+    }
+    const int pend = rb.frame_end[k];
+    for (int p = (k == 0 ? 0 : rb.frame_end[k - 1]); p < pend; p += NB) {
+      SphereBatch<NB> sb;
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        const int q = min(p + i, pend - 1);  // tail lanes of the batch repeat the last sphere (weight 0 below)
+        const double ox = rb.sphere_off[q][0], oy = rb.sphere_off[q][1], oz = rb.sphere_off[q][2];
+        sb.x[i] = A.r[0] * ox + A.r[1] * oy + A.r[2] * oz + A.t[0];
+        sb.y[i] = A.r[3] * ox + A.r[4] * oy + A.r[5] * oz + A.t[1];
+        sb.z[i] = A.r[6] * ox + A.r[7] * oy + A.r[8] * oz + A.t[2];
+        const Voxel v = sdf_voxel_rel(sdf, sb.x[i], sb.y[i], sb.z[i]);
+        sb.r[i] = sdf_record(sdf, v);
+      }
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        if (p + i < pend) {
+          const double dist = sb.r[i].x - rb.sphere_rad[p + i];
+          const double hinge = fmax(lk.epsilon - dist, 0.0);
+          lp -= 0.5 * (hinge * inv_sigma) * hinge;
+          if (hinge > 0.0) {
+            double gx = sb.r[i].y, gy = sb.r[i].z, gz = sb.r[i].w;
+            const double w = hinge * inv_sigma;
+            gx *= w; gy *= w; gz *= w;
+            Fw[0] += gx; Fw[1] += gy; Fw[2] += gz;
+            Tw[0] += sb.y[i] * gz - sb.z[i] * gy;
+            Tw[1] += sb.z[i] * gx - sb.x[i] * gz;
+            Tw[2] += sb.x[i] * gy - sb.y[i] * gx;
+          }
+        }
+      }
+    }
+  }
+  logp[c] = lp;
+  // sweep 2: joint axes again (frame products from the stored sin / cos), now against the TOTAL wrench
+  frame_from_base(rb, A);
+  A.t[0] -= shx; A.t[1] -= shy; A.t[2] -= shz;
+#pragma unroll 1
+  for (int j = 0; j < D; ++j) {
+    const double* slot = trig + (size_t)j * 4 * kThreads + tid;
+    const double st = slot[0], ct = slot[kThreads], dsq = slot[2 * kThreads], pj = slot[3 * kThreads];
+    double zx, zy, zz, ox, oy, oz;
+    if (!rb.craig) { zx = A.r[2]; zy = A.r[5]; zz = A.r[8]; ox = A.t[0]; oy = A.t[1]; oz = A.t[2]; }
+    frame_step_sc(rb, j, st, ct, A);
+    if (rb.craig) { zx = A.r[2]; zy = A.r[5]; zz = A.r[8]; ox = A.t[0]; oy = A.t[1]; oz = A.t[2]; }
+    const double nx = zy * oz - zz * oy, ny = zz * ox - zx * oz, nz = zx * oy - zy * ox;
+    const double dth = zx * Tw[0] + zy * Tw[1] + zz * Tw[2] - (nx * Fw[0] + ny * Fw[1] + nz * Fw[2]) - pj;
+    d_in[c * D + j] = upstream * dth * dsq;
+  }
+}
+
 constexpr int kSphereBatch = 4;
+#ifndef VGPMP_BWD_BATCH
+#define VGPMP_BWD_BATCH 3
+#endif
+#ifndef VGPMP_BWD_MINB
+#define VGPMP_BWD_MINB 4
+#endif
+constexpr int kBwdBatch = VGPMP_BWD_BATCH, kBwdMinBlocks = VGPMP_BWD_MINB;
 
 template <int D>
 cudaError_t launch_loglik_d(vgpmp_handle* h, const double* in, int squash, double upstream, double* logp, double* d_in,
                             int64_t n, cudaStream_t s) {
   const unsigned blocks = (unsigned)((n + kThreads - 1) / kThreads);
   if (d_in != nullptr) {
-    const size_t smem = sizeof(double) * D * 8 * kThreads;
-    auto kern = loglik_kernel<D, true, kSphereBatch>;
+    const size_t smem = sizeof(double) * D * 4 * kThreads;
+    auto kern = loglik_bwd_kernel<D, kBwdBatch, kBwdMinBlocks>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<blocks, kThreads, smem, s>>>(h->robot, h->sdf, h->lik, in, squash, upstream, logp, d_in, n);
