@@ -179,6 +179,7 @@ int vgpmp_create(vgpmp_handle** out, int device, const vgpmp_robot_desc* robot, 
   for (int k = 0; k < 3; ++k) h->lik.offset[k] = lik->scene_offset[k];
 
   const size_t cells = (size_t)sdf->nx * sdf->ny * sdf->nz;
+  if (cells >= ((size_t)1 << 32)) { delete h; return fail(nullptr, VGPMP_ERR_INVALID, "SDF grids are limited to 2^32 - 1 cells (128 GiB of records)"); }
   h->sdf.nx = sdf->nx; h->sdf.ny = sdf->ny; h->sdf.nz = sdf->nz;
   for (int k = 0; k < 3; ++k) h->sdf.origin[k] = sdf->origin[k];
   h->sdf.delta = sdf->delta;

@@ -101,14 +101,13 @@ __device__ __forceinline__ Voxel sdf_voxel(const SdfDev& s, double x, double y, 
 // (quarter-rate on sm_100): q + 1.5 * 2^52 leaves rint(q) in the low mantissa word, r = q - rint(q) gives floor and the
 // distance to the nearest integer in full-rate FP64 adds.  Negative q clips to 0 under trunc and under floor alike.  Returns
 // false when q sits within 1e-9 of an integer (or is absurdly large / NaN): the caller then takes the exact path above.
+// (5 FP64 instructions + 2 integer min/max per axis; the conversion-based form was 14.)
 __device__ __forceinline__ bool voxel_index_fast(double a, double inv_delta, int n, int& idx) {
-  const double q = a * inv_delta;
-  const double t = q + 6755399441055744.0;
-  const double r = q - (t - 6755399441055744.0);
-  int i = __double2loint(t);
-  if (r < 0.0) --i;
-  idx = min(max(i, 0), n - 1);
-  return fabs(r) > 1e-9 && fabs(q) < 1.0e9;
+  const double qh = fma(a, inv_delta, -0.5);           // q - 1/2: rint(q - 1/2) = floor(q) unless q is an integer
+  const double t = qh + 6755399441055744.0;            // 1.5 * 2^52: the low mantissa word of t is rint(qh)
+  const double r = qh - (t - 6755399441055744.0);      // in [-1/2, 1/2]; |r| -> 1/2 when q approaches an integer
+  idx = min(max(__double2loint(t), 0), n - 1);
+  return fabs(r) < 0.5 - 1e-9 && fabs(qh) < 1.0e9;
 }
 
 // grid-relative position -> voxel (fast path for all three axes, exact path if any of them asks for it)
@@ -147,7 +146,7 @@ __device__ __forceinline__ void sincos_small(double x, double& sn, double& cs) {
 }
 
 __device__ __forceinline__ size_t sdf_cell(const SdfDev& s, int ix, int iy, int iz) {
-  return ((size_t)ix * s.ny + iy) * s.nz + iz;
+  return (size_t)(((unsigned)ix * (unsigned)s.ny + (unsigned)iy) * (unsigned)s.nz + (unsigned)iz);   // vgpmp_create: cells < 2^32
 }
 
 __device__ __forceinline__ double sdf_value(const SdfDev& s, const Voxel& v) {
@@ -261,9 +260,16 @@ __global__ void __launch_bounds__(kThreads) clearance_kernel(RobotDev rb, SdfDev
 }
 
 __device__ __forceinline__ double stable_sigmoid(double x) {
-  if (x >= 0.0) return 1.0 / (1.0 + exp(-x));
-  const double e = exp(x);
-  return e / (1.0 + e);
+  // one path for both signs: e = exp(-|x|) in (0, 1], sigmoid = (x >= 0 ? 1 : e) / (1 + e); the reciprocal of 1 + e in
+  // [1, 2] is a MUFU seed + two Newton steps (no IEEE division sequence, no divergent branch)
+  const double e = exp(-fabs(x));
+  const double d = 1.0 + e;
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  r = fma(r, fma(-d, r, 1.0), r);
+  r = fma(r, fma(-d, r, 1.0), r);
+  r = fma(r, fma(-d, r, 1.0), r);
+  return (x >= 0.0 ? 1.0 : e) * r;
 }
 
 // Fused likelihood: squash -> FK -> spheres -> SDF stencil -> hinge -> logp, plus the reverse pass to the input.
@@ -477,16 +483,13 @@ __global__ void __launch_bounds__(kThreads, MINB) loglik_bwd_kernel(RobotDev rb,
         if (p + i < pend) {
           const double dist = sb.r[i].x - rb.sphere_rad[p + i];
           const double hinge = fmax(lk.epsilon - dist, 0.0);
-          lp -= 0.5 * (hinge * inv_sigma) * hinge;
-          if (hinge > 0.0) {
-            double gx = sb.r[i].y, gy = sb.r[i].z, gz = sb.r[i].w;
-            const double w = hinge * inv_sigma;
-            gx *= w; gy *= w; gz *= w;
-            Fw[0] += gx; Fw[1] += gy; Fw[2] += gz;
-            Tw[0] += sb.y[i] * gz - sb.z[i] * gy;
-            Tw[1] += sb.z[i] * gx - sb.x[i] * gz;
-            Tw[2] += sb.x[i] * gy - sb.y[i] * gx;
-          }
+          const double w = hinge * inv_sigma;          // 0 outside the hinge: the wrench update needs no branch
+          lp -= 0.5 * w * hinge;
+          const double gx = sb.r[i].y * w, gy = sb.r[i].z * w, gz = sb.r[i].w * w;
+          Fw[0] += gx; Fw[1] += gy; Fw[2] += gz;
+          Tw[0] += sb.y[i] * gz - sb.z[i] * gy;
+          Tw[1] += sb.z[i] * gx - sb.x[i] * gz;
+          Tw[2] += sb.x[i] * gy - sb.y[i] * gx;
         }
       }
     }
