@@ -292,6 +292,9 @@ double vgpmp_probe_fp64_tflops(int device);
  *                     float32-class accuracy, gated by the tolerance tests (ELBO 1e-4, gradients 1e-3).  0 = float64 DMMA.
  *   "rr_sampler"      register-resident warp-specialised DMMA sampler (points must fit 12 tiles of 8 rows, e.g. N=70, M=24);
  *                     0 = the variant that passes the features through shared memory.
+ *   "step_graph"      vgpmp_train_step_host[_begin] captures the step's launches into a CUDA graph once per argument signature
+ *                     and replays it (the iteration counter and Adam's bias-corrected rate live in device memory); 0 = plain
+ *                     launches every step.  Needs lazy draws and an explicit (non-NULL) stream.
  *   "rrm_min_ctas"    9..63 samples: the register-resident sampler processes up to 4 tiles of 8 samples per CTA pass (basis
  *                     tables produced once per pass) as long as at least this many CTAs remain (default -1 = 2 per SM).
  *   "dmma_sampler"    shared-memory DMMA sampler for up to 192 points; 0 = the general kernel takes those shapes.

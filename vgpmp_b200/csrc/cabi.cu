@@ -247,6 +247,7 @@ int vgpmp_set_option(vgpmp_handle* h, const char* name, int value) {
   if (std::strcmp(name, "dmma_sampler") == 0) { h->allow_dmma_path = value != 0; return VGPMP_OK; }
   if (std::strcmp(name, "rr_sampler") == 0) { h->allow_rr_path = value != 0; return VGPMP_OK; }
   if (std::strcmp(name, "lazy_draws") == 0) { h->allow_lazy_draws = value != 0; return VGPMP_OK; }
+  if (std::strcmp(name, "step_graph") == 0) { h->allow_step_graph = value != 0; return VGPMP_OK; }
   if (std::strcmp(name, "rrm_min_ctas") == 0) { h->rrm_min_ctas = value; return VGPMP_OK; }
   if (std::strcmp(name, "tc_sampler") == 0) { h->allow_tc_path = value != 0; return VGPMP_OK; }
   return fail(h, VGPMP_ERR_INVALID, std::string("set_option: unknown option ") + name);
@@ -291,6 +292,8 @@ int vgpmp_destroy(vgpmp_handle* h) {
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
   }
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
+  if (h->step_dev) cudaFree(h->step_dev);
   h->rec_owner.reset();
   delete h;
   return VGPMP_OK;
@@ -549,6 +552,69 @@ int vgpmp_rng_release(vgpmp_handle* h, int slot, void* stream) {
   return check_cuda(h, cudaEventRecord(h->ev_consumed[slot], (cudaStream_t)stream), "rng_release");
 }
 
+// The body of one host-buffer step, enqueued on `s`.  With graph_mode the iteration number and Adam's bias-corrected rate are
+// read from device memory (h->capture_iter_dev / capture_lr_dev), so that the enqueued work is the same for every step and
+// can be captured once and replayed.
+static int enqueue_train_step(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* st, const double* query_latent, const double* Z,
+                              const double* X_host, double* X_dev, uint64_t seed, int64_t problem_offset, double* draws_ws,
+                              size_t draws_bytes, const vgpmp_grads* g, double* elbo_dev, double* loss_host, void* ws,
+                              size_t ws_bytes, cudaStream_t s, bool graph_mode) {
+  const int D = h->robot.dof;
+  const bool compact = draws_bytes < vgpmp_draws_bytes(dims, D);
+  const size_t Bp = dims->num_problems, B = dims->num_bases, S = dims->num_samples, Mp = dims->num_inducing + 2;
+  int rc;
+  void* stream = (void*)s;
+  if ((rc = check_cuda(h, cudaMemcpyAsync(X_dev, X_host, sizeof(double) * dims->num_timesteps * D, cudaMemcpyHostToDevice, s),
+                       "H2D X")))
+    return rc;
+  const size_t one_set = vgpmp_draws_bytes(dims, D);
+  const bool pipelined = !graph_mode && draws_bytes >= 2 * one_set;   // two draw sets: step t+1 is drawn on the side stream during step t
+  const int slot = pipelined ? (st->step & 1) : 0;
+  const uint64_t iteration = graph_mode ? 0 : (uint64_t)st->step;     // graph mode: the kernels add the device-resident counter
+  double *omega, *tau, *w, *eps_u, *eps_j;
+  auto carve_set = [&](int which) {
+    Carver c(static_cast<char*>(static_cast<void*>(draws_ws)) + (size_t)which * one_set);
+    omega = compact ? nullptr : c.take(Bp * D * B * D);
+    tau = compact ? nullptr : c.take(Bp * D * B);
+    w = compact ? nullptr : c.take(Bp * D * S * B);
+    eps_u = c.take(Bp * D * S * Mp);
+    eps_j = c.take(Bp * D * S * Mp);
+  };
+  carve_set(slot);
+  const bool lazy_ok = h->allow_lazy_draws;   // draws generated inside the sampler: no prefetch pipeline needed
+  if (lazy_ok) {
+    if ((rc = vgpmp_rng_fill_lazy(h, dims, seed, iteration, problem_offset, 0, omega, tau, w, eps_u, eps_j, stream))) return rc;
+  } else if (pipelined && h->prefetched_step == (int64_t)st->step && h->prefetched_seed == seed) {
+    if ((rc = vgpmp_rng_join(h, slot, stream))) return rc;
+  } else {
+    if ((rc = vgpmp_rng_fill(h, dims, seed, iteration, problem_offset, 0, omega, tau, w, eps_u, eps_j, stream))) return rc;
+  }
+  vgpmp_params p{st->q_mu, st->q_sqrt, st->lengthscales, st->variances, query_latent, Z, X_dev};
+  vgpmp_draws r{omega, tau, w, eps_u, eps_j};
+  if ((rc = vgpmp_elbo_fwd_bwd(h, dims, &p, &r, elbo_dev, g, nullptr, ws, ws_bytes, stream))) return rc;
+  if ((rc = vgpmp_adam_step(h, dims, st, g, stream))) return rc;   // st->step is now the NEXT step
+  if (graph_mode && (rc = check_cuda(h, launch_step_epilogue(h, s), "step epilogue"))) return rc;
+  if (pipelined && !lazy_ok) {
+    if ((rc = vgpmp_rng_release(h, slot, stream))) return rc;
+    carve_set(slot ^ 1);
+    if ((rc = vgpmp_rng_fill_async(h, dims, seed, (uint64_t)st->step, problem_offset, 0, omega, tau, w, eps_u, eps_j, slot ^ 1))) return rc;
+    h->prefetched_step = st->step;
+    h->prefetched_seed = seed;
+  }
+  {
+    size_t need = 0;
+    GpScratch gsc = carve(ws, D, *dims, &need, h->num_sms);   // loss = -ELBO was written by the ELBO reduction
+    if ((rc = check_cuda(h, cudaMemcpyAsync(loss_host, gsc.loss, sizeof(double) * Bp, cudaMemcpyDeviceToHost, s), "D2H loss")))
+      return rc;
+  }
+  return VGPMP_OK;
+}
+
+static uint64_t mix64(uint64_t hsh, uint64_t v) {
+  hsh ^= v + 0x9E3779B97F4A7C15ull + (hsh << 6) + (hsh >> 2);
+  return hsh;
+}
+
 int vgpmp_train_step_host_begin(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_adam* st, const double* query_latent,
                                 const double* Z, const double* X_host, double* X_dev, uint64_t seed, int64_t problem_offset,
                                 double* draws_ws, size_t draws_bytes, const vgpmp_grads* g, double* elbo_dev,
@@ -566,48 +632,73 @@ int vgpmp_train_step_host_begin(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_a
   if (compact && (draws_bytes < vgpmp_draws_bytes_lazy(dims, D) || !h->allow_lazy_draws))
     return fail(h, VGPMP_ERR_WORKSPACE, "train_step_host: draws buffer too small");
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t Bp = dims->num_problems, B = dims->num_bases, S = dims->num_samples, Mp = dims->num_inducing + 2;
-  if ((rc = check_cuda(h, cudaMemcpyAsync(X_dev, X_host, sizeof(double) * dims->num_timesteps * D, cudaMemcpyHostToDevice, s),
-                       "H2D X")))
-    return rc;
-  const size_t one_set = vgpmp_draws_bytes(dims, D);
-  const bool pipelined = draws_bytes >= 2 * one_set;   // two draw sets: step t+1 is drawn on the side stream during step t
-  const int slot = pipelined ? (st->step & 1) : 0;
-  double *omega, *tau, *w, *eps_u, *eps_j;
-  auto carve_set = [&](int which) {
-    Carver c(static_cast<char*>(static_cast<void*>(draws_ws)) + (size_t)which * one_set);
-    omega = compact ? nullptr : c.take(Bp * D * B * D);
-    tau = compact ? nullptr : c.take(Bp * D * B);
-    w = compact ? nullptr : c.take(Bp * D * S * B);
-    eps_u = c.take(Bp * D * S * Mp);
-    eps_j = c.take(Bp * D * S * Mp);
-  };
-  carve_set(slot);
-  const bool lazy_ok = h->allow_lazy_draws;   // draws generated inside the sampler: no prefetch pipeline needed
-  if (lazy_ok) {
-    if ((rc = vgpmp_rng_fill_lazy(h, dims, seed, (uint64_t)st->step, problem_offset, 0, omega, tau, w, eps_u, eps_j, stream))) return rc;
-  } else if (pipelined && h->prefetched_step == (int64_t)st->step && h->prefetched_seed == seed) {
-    if ((rc = vgpmp_rng_join(h, slot, stream))) return rc;
-  } else {
-    if ((rc = vgpmp_rng_fill(h, dims, seed, (uint64_t)st->step, problem_offset, 0, omega, tau, w, eps_u, eps_j, stream))) return rc;
+  // CUDA-graph replay: with lazy draws every step enqueues the same launches on the same buffers; only the iteration number
+  // changes, and that lives in device memory.  Captured once per argument signature, replayed with one cudaGraphLaunch.
+  const bool want_graph = h->allow_step_graph && h->allow_lazy_draws && !h->profiling && s != nullptr;
+  if (!want_graph)
+    return enqueue_train_step(h, dims, st, query_latent, Z, X_host, X_dev, seed, problem_offset, draws_ws, draws_bytes, g,
+                              elbo_dev, loss_host, ws, ws_bytes, s, false);
+  uint64_t sig = 0x1234567ull;
+  const uint64_t words[] = {(uint64_t)dims->num_problems, (uint64_t)dims->num_inducing, (uint64_t)dims->num_timesteps,
+                            (uint64_t)dims->num_samples, (uint64_t)dims->num_bases, (uint64_t)(uintptr_t)st->q_mu,
+                            (uint64_t)(uintptr_t)st->q_sqrt, (uint64_t)(uintptr_t)st->raw_lengthscales,
+                            (uint64_t)(uintptr_t)st->raw_variances, (uint64_t)(uintptr_t)st->lengthscales,
+                            (uint64_t)(uintptr_t)st->variances, (uint64_t)(uintptr_t)st->m, (uint64_t)(uintptr_t)st->v,
+                            (uint64_t)(uintptr_t)query_latent, (uint64_t)(uintptr_t)Z, (uint64_t)(uintptr_t)X_host,
+                            (uint64_t)(uintptr_t)X_dev, seed, (uint64_t)problem_offset, (uint64_t)(uintptr_t)draws_ws,
+                            (uint64_t)draws_bytes, (uint64_t)(uintptr_t)g->d_q_mu, (uint64_t)(uintptr_t)g->d_q_sqrt,
+                            (uint64_t)(uintptr_t)g->d_lengthscales, (uint64_t)(uintptr_t)g->d_variances,
+                            (uint64_t)(uintptr_t)elbo_dev, (uint64_t)(uintptr_t)loss_host, (uint64_t)(uintptr_t)ws,
+                            (uint64_t)ws_bytes, (uint64_t)(uintptr_t)s, (uint64_t)st->train_q_mu, (uint64_t)st->train_q_sqrt,
+                            (uint64_t)st->train_lengthscales, (uint64_t)st->train_variances,
+                            (uint64_t)(h->allow_tc_path | (h->allow_rr_path << 1) | (h->allow_dmma_path << 2) | (h->allow_grid_path << 3)),
+                            (uint64_t)(int64_t)h->rrm_min_ctas};
+  for (uint64_t wv : words) sig = mix64(sig, wv);
+  double dw[6] = {st->learning_rate, st->beta1, st->beta2, st->eps, st->variance_lower, 0.0};
+  for (double dv : dw) { uint64_t bits; std::memcpy(&bits, &dv, 8); sig = mix64(sig, bits); }
+  if (h->step_dev == nullptr) {
+    if ((rc = check_cuda(h, cudaMalloc(&h->step_dev, 32), "step counter"))) return rc;
   }
-  vgpmp_params p{st->q_mu, st->q_sqrt, st->lengthscales, st->variances, query_latent, Z, X_dev};
-  vgpmp_draws r{omega, tau, w, eps_u, eps_j};
-  if ((rc = vgpmp_elbo_fwd_bwd(h, dims, &p, &r, elbo_dev, g, nullptr, ws, ws_bytes, stream))) return rc;
-  if ((rc = vgpmp_adam_step(h, dims, st, g, stream))) return rc;   // st->step is now the NEXT step
-  if (pipelined && !lazy_ok) {
-    if ((rc = vgpmp_rng_release(h, slot, stream))) return rc;
-    carve_set(slot ^ 1);
-    if ((rc = vgpmp_rng_fill_async(h, dims, seed, (uint64_t)st->step, problem_offset, 0, omega, tau, w, eps_u, eps_j, slot ^ 1))) return rc;
-    h->prefetched_step = st->step;
-    h->prefetched_seed = seed;
+  if (h->step_graph == nullptr || h->step_graph_sig != sig) {
+    if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; }
+    h->capture_iter_dev = h->step_dev;
+    const uint64_t launches0 = h->launches;
+    const int step0 = st->step;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+    int rc2 = VGPMP_OK;
+    if (e == cudaSuccess) {
+      rc2 = enqueue_train_step(h, dims, st, query_latent, Z, X_host, X_dev, seed, problem_offset, draws_ws, draws_bytes, g,
+                               elbo_dev, loss_host, ws, ws_bytes, s, true);
+      e = cudaStreamEndCapture(s, &graph);
+    }
+    h->capture_iter_dev = nullptr;
+    st->step = step0;                                   // nothing ran yet
+    h->step_graph_launches = (int)(h->launches - launches0);
+    h->launches = launches0;
+    if (e == cudaSuccess && rc2 == VGPMP_OK && graph != nullptr) e = cudaGraphInstantiate(&h->step_graph, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess || rc2 != VGPMP_OK || h->step_graph == nullptr) {
+      // capture is an optimisation: fall back to plain launches for good on this handle
+      (void)cudaGetLastError();
+      h->step_graph = nullptr;
+      h->allow_step_graph = false;
+      return enqueue_train_step(h, dims, st, query_latent, Z, X_host, X_dev, seed, problem_offset, draws_ws, draws_bytes, g,
+                                elbo_dev, loss_host, ws, ws_bytes, s, false);
+    }
+    h->step_graph_sig = sig;
+    h->step_graph_next = -1;
   }
-  {
-    size_t need = 0;
-    GpScratch gsc = carve(ws, D, *dims, &need, h->num_sms);   // loss = -ELBO was written by the ELBO reduction
-    if ((rc = check_cuda(h, cudaMemcpyAsync(loss_host, gsc.loss, sizeof(double) * Bp, cudaMemcpyDeviceToHost, s), "D2H loss")))
-      return rc;
+  if (h->step_graph_next != (int64_t)st->step) {        // (re)synchronise the device-resident counter with the caller's step
+    const unsigned long long v = (unsigned long long)st->step;
+    if ((rc = check_cuda(h, cudaMemcpyAsync(h->step_dev, &v, sizeof(v), cudaMemcpyHostToDevice, s), "step counter upload"))) return rc;
+    if ((rc = check_cuda(h, cudaStreamSynchronize(s), "step counter upload"))) return rc;   // `v` is a stack variable
   }
+  if ((rc = check_cuda(h, cudaGraphLaunch(h->step_graph, s), "graph launch"))) return rc;
+  h->launches += (uint64_t)h->step_graph_launches;
+  st->step += 1;
+  h->step_graph_next = st->step;
+  h->lazy.valid = false;
   return VGPMP_OK;   // the loss copy is in flight: vgpmp_train_step_host_end waits for it
 }
 

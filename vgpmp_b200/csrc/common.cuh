@@ -71,6 +71,14 @@ struct vgpmp_handle {
   bool allow_tc_path = true;    // tcgen05 / TMEM 3xTF32 sampler for large sample counts (sampler_tc.cu)
   bool allow_dmma_path = true;  // shared-memory DMMA sampler (N + M + 2 <= 192), else the general kernel
   bool allow_rr_path = true;    // register-resident warp-specialised DMMA sampler (<= 12 point tiles), else the shared-memory one
+  // CUDA-graph replay of vgpmp_train_step_host (one captured graph per argument signature)
+  const unsigned long long* capture_iter_dev = nullptr;   // non-null only while capturing: kernels read the iteration from it
+  unsigned long long* step_dev = nullptr;                 // [1] step counter
+  cudaGraphExec_t step_graph = nullptr;
+  uint64_t step_graph_sig = 0;
+  int64_t step_graph_next = -1;                           // the value the device counter holds
+  int step_graph_launches = 0;
+  bool allow_step_graph = true;
   int rrm_min_ctas = -1;        // multi-tile register-resident sampler only if it still launches this many CTAs (-1: 2 per SM)
   bool allow_grid_path = true;  // equispaced rank-1 fast path of the pathwise sampler (vgpmp_set_option)
   bool profiling = false;
@@ -128,6 +136,7 @@ int elbo_reduce_segments(int num_sms, int Bp, int SN);
 cudaError_t launch_elbo_reduce(vgpmp_handle* h, const vgpmp_dims& d, const double* logp, const double* kl_l,
                                double* elbo, double* kl_out, double* loss_out, double* partial, cudaStream_t s);
 cudaError_t launch_adam(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_adam& st, const vgpmp_grads& g, cudaStream_t s);
+cudaError_t launch_step_epilogue(vgpmp_handle* h, cudaStream_t s);
 cudaError_t launch_rng_fill(vgpmp_handle* h, const vgpmp_dims& d, uint64_t seed, uint64_t iteration,
                             int64_t problem_offset, int64_t sample_offset, double* omega, double* tau, double* w,
                             double* eps_u, double* eps_j, cudaStream_t s, const double* skip_if_grid = nullptr);

@@ -7,6 +7,7 @@ struct PathwiseArgs {
   int D, M, Nq, S, B, XG, KS;
   int gen_draws;       // 1: omega / tau / w are not in memory, the register-resident sampler generates them from the key below
   uint64_t seed, iteration;
+  const unsigned long long* iter_dev;   // CUDA-graph replay: the iteration lives in device memory and is ADDED to `iteration`
   int64_t problem_offset, sample_offset;
   int items;           // work items of the general sampler (pairs x nchunk)
   int nchunk, chunk;   // the S samples are split into nchunk CTAs per (problem, latent), `chunk` samples each (multiple of kST)

@@ -676,6 +676,7 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
   uint64_t* empty = full + kRS;                                                          // [kRS] slot drained
 
   if (meta[0] == 0.0) return;  // not an equispaced rank-1 grid: the general kernel does the sampling
+  if (GEN && a.iter_dev != nullptr) a.iteration += *a.iter_dev;
   if (tid == 0) {
     for (int i = 0; i < kRS; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, kRC); }   // one arrival per warp
   }
@@ -939,6 +940,7 @@ __global__ void __launch_bounds__(256, 2) pathwise_rrm_kernel(PathwiseArgs a, co
   uint64_t* empty = full + kRS;
 
   if (meta[0] == 0.0) return;  // not an equispaced rank-1 grid: the general kernel does the sampling
+  if (GEN && a.iter_dev != nullptr) a.iteration += *a.iter_dev;
   if (tid == 0) {
     for (int i = 0; i < kRS; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, kRC); }
   }
@@ -1973,7 +1975,16 @@ __global__ void elbo_finish_kernel(int D, int Bp, double scale, double klw, cons
 // Keras Adam on the unconstrained variables, loss = -ELBO.
 __device__ __forceinline__ double softplus_d(double x) { return x > 30.0 ? x : log1p(exp(x)); }
 
-__global__ void adam_kernel(int D, int M, int Bp, vgpmp_adam st, vgpmp_grads g, double lr_t) {
+__global__ void adam_kernel(int D, int M, int Bp, vgpmp_adam st, vgpmp_grads g, const unsigned long long* __restrict__ step_dev) {
+  // bias-corrected rate of this step, lr * sqrt(1 - beta2^t) / (1 - beta1^t): evaluated on the device (once per CTA) in both
+  // the plain and the CUDA-graph path, so that the two are bit-identical; in graph replay the step counter is device-resident
+  __shared__ double lr_sh;
+  if (threadIdx.x == 0) {
+    const double t = (double)((step_dev != nullptr ? *step_dev : (unsigned long long)st.step) + 1ull);
+    lr_sh = st.learning_rate * sqrt(1.0 - pow(st.beta2, t)) / (1.0 - pow(st.beta1, t));
+  }
+  __syncthreads();
+  const double lr_t = lr_sh;
   const int per = M * D + D * M * M + 2 * D;
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (size_t)Bp * per) return;
@@ -2021,6 +2032,7 @@ struct RngArgs {
   int D, B, S, Mp, Bp;
   int64_t problem_offset, sample_offset;
   uint64_t seed, iteration;
+  const unsigned long long* iter_dev;   // CUDA-graph replay: added to `iteration`
   double *omega, *tau, *w, *eps_u, *eps_j;
 };
 
@@ -2031,6 +2043,7 @@ __global__ void __launch_bounds__(256) rng_fill_kernel(RngArgs a, uint32_t bpp, 
                                                        const double* __restrict__ skip_if_grid) {
   // lazy draws: this launch only matters when the equispaced sampler did NOT run (it generated its own omega / tau / w)
   if (skip_if_grid != nullptr && skip_if_grid[0] != 0.0) return;
+  if (a.iter_dev != nullptr) a.iteration += *a.iter_dev;
   const uint32_t B = a.B, S = a.S, D = a.D, Mp = a.Mp, B4 = (B + 3) / 4, M2 = (Mp + 1) / 2;
   const uint32_t nA = a.omega != nullptr ? B : 0, nW = a.w != nullptr ? S * B4 : 0, nE = a.eps_u != nullptr ? S * M2 : 0;
   for (uint32_t vb = blockIdx.x; vb < nblocks; vb += gridDim.x) {   // (the gated launch uses a small grid: it usually exits above)
@@ -2188,6 +2201,7 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
   const bool have_buffers = r.omega != nullptr && r.tau != nullptr && r.w != nullptr;
   if (!lazy && !have_buffers) return cudaErrorInvalidValue;   // NULL draw buffers are only legal right after vgpmp_rng_fill_lazy
   a.gen_draws = 0; a.seed = 0; a.iteration = 0; a.problem_offset = 0; a.sample_offset = 0;
+  a.iter_dev = h->capture_iter_dev;
   if (lazy && (tc_path || rr_path)) {
     a.gen_draws = 1;
     a.seed = lz.seed; a.iteration = lz.iteration; a.problem_offset = lz.problem_offset; a.sample_offset = lz.sample_offset;
@@ -2435,12 +2449,20 @@ cudaError_t launch_elbo_reduce(vgpmp_handle* h, const vgpmp_dims& d, const doubl
   return cudaGetLastError();
 }
 
+// CUDA-graph replay of the training step: the step counter lives in device memory; the samplers and the draw generator add
+// it to their Philox iteration, Adam reads it, and this epilogue advances it.
+__global__ void step_epilogue_kernel(unsigned long long* __restrict__ step) { *step += 1ull; }
+
+cudaError_t launch_step_epilogue(vgpmp_handle* h, cudaStream_t s) {
+  step_epilogue_kernel<<<1, 1, 0, s>>>(const_cast<unsigned long long*>(h->capture_iter_dev));
+  h->launches++;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_adam(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_adam& st, const vgpmp_grads& g, cudaStream_t s) {
   const int D = h->robot.dof, M = d.num_inducing;
   const size_t total = (size_t)d.num_problems * (M * D + D * M * M + 2 * D);
-  const int t = st.step + 1;
-  const double lr_t = st.learning_rate * sqrt(1.0 - pow(st.beta2, t)) / (1.0 - pow(st.beta1, t));
-  adam_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(D, M, d.num_problems, st, g, lr_t);
+  adam_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(D, M, d.num_problems, st, g, h->capture_iter_dev);
   h->launches++;
   return cudaGetLastError();
 }
@@ -2451,6 +2473,7 @@ cudaError_t launch_rng_fill(vgpmp_handle* h, const vgpmp_dims& d, uint64_t seed,
   RngArgs a;
   a.D = h->robot.dof; a.B = d.num_bases; a.S = d.num_samples; a.Mp = d.num_inducing + 2; a.Bp = d.num_problems;
   a.problem_offset = problem_offset; a.sample_offset = sample_offset; a.seed = seed; a.iteration = iteration;
+  a.iter_dev = h->capture_iter_dev;
   a.omega = omega; a.tau = tau; a.w = w; a.eps_u = eps_u; a.eps_j = eps_j;
   const size_t per_pair = (omega ? (size_t)a.B : 0) + (w ? (size_t)a.S * ((a.B + 3) / 4) : 0) +
                           (eps_u ? (size_t)a.S * ((a.Mp + 1) / 2) : 0);

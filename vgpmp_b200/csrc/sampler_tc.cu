@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   if (meta[0] == 0.0) return;       // not an equispaced rank-1 grid: the general kernel does the sampling
+  if (GEN && a.iter_dev != nullptr) a.iteration += *a.iter_dev;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = a.D, M = a.M, Nq = a.Nq, S = a.S, B = a.B, A = Nq + M + 2;
   const int T = (B + kTB - 1) / kTB;             // stages per item

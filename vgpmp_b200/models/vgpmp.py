@@ -402,19 +402,28 @@ class VGPMP:
         if hs["pending"]:
             raise RuntimeError("train_step_host(wait=False) was called twice without train_step_host_wait(): the pinned "
                                "loss buffer of the step in flight would be overwritten")
-        g = hs["g"]
-        gs = _cabi.Grads(g["d_q_mu"].data_ptr(), g["d_q_sqrt"].data_ptr(), g["d_lengthscales"].data_ptr(),
-                         g["d_variances"].data_ptr())
-        st = self._adam_struct()
-        ws = eng.workspace(dims)
-        eng._chk(eng.lib.vgpmp_train_step_host_begin(eng.h, C.byref(dims), C.byref(st), self._query_states.data_ptr(),
-                                                     self._Z.data_ptr(), X_host.data_ptr(), hs["X_dev"].data_ptr(),
-                                                     self.seed, int(self.problem_offset), hs["draws"].data_ptr(),
-                                                     hs["draws"].numel(), C.byref(gs), hs["elbo"].data_ptr(),
-                                                     hs["loss"].data_ptr(), ws.data_ptr(), ws.numel(), eng._stream()),
-                 "train_step_host_begin")
-        self._step = st.step
-        hs["dims"], hs["stream"], hs["pending"] = dims, eng._stream(), True
+        stream = torch.cuda.current_stream(eng.device).cuda_stream
+        call = hs.get("call")
+        o = self.optimizer
+        key = (X_host.data_ptr(), stream, tuple(sorted(self.trainable.items())), self.seed, self.problem_offset,
+               o.learning_rate, o.beta_1, o.beta_2, o.epsilon)
+        if call is None or call["key"] != key:
+            # the argument block of the C call is built once per (host buffer, stream): per step only Adam's step counter changes
+            g = hs["g"]
+            gs = _cabi.Grads(g["d_q_mu"].data_ptr(), g["d_q_sqrt"].data_ptr(), g["d_lengthscales"].data_ptr(),
+                             g["d_variances"].data_ptr())
+            st = self._adam_struct()
+            ws = eng.workspace(dims)
+            call = dict(key=key, st=st, gs=gs, dims=dims, stream=C.c_void_p(stream), keep=(ws, X_host),
+                        args=(eng.h, C.byref(dims), C.byref(st), self._query_states.data_ptr(), self._Z.data_ptr(),
+                              X_host.data_ptr(), hs["X_dev"].data_ptr(), self.seed, int(self.problem_offset),
+                              hs["draws"].data_ptr(), hs["draws"].numel(), C.byref(gs), hs["elbo"].data_ptr(),
+                              hs["loss"].data_ptr(), ws.data_ptr(), ws.numel(), C.c_void_p(stream)))
+            hs["call"] = call
+        call["st"].step = self._step
+        eng._chk(eng.lib.vgpmp_train_step_host_begin(*call["args"]), "train_step_host_begin")
+        self._step = call["st"].step
+        hs["dims"], hs["stream"], hs["pending"] = call["dims"], call["stream"], True
         if not wait:
             return None
         return self.train_step_host_wait()
