@@ -233,8 +233,11 @@ __device__ void gp_prepare_body(int D, int M, double jitter, const vgpmp_params&
     if (lane <= a_) {
       const double v = q[a_ * M + lane];
       part += v * v;
-      if (lane == a_) part -= log(v * v);
     }
+  }
+  if (tid < M) {                         // log of the diagonal: one pass of one warp (inside the row loop every row paid for it)
+    const double v = q[tid * M + tid];
+    part -= log(v * v);
   }
   const double tot = block_sum(part, red);   // (its barriers also retire the last readers of K)
   if (tid == 0 && kl_l != nullptr) kl_l[pl] = 0.5 * (tot - (double)M);
@@ -1182,6 +1185,7 @@ __global__ void __launch_bounds__(128, 7) gp_prepare_update_kernel(PathwiseArgs 
                                                                   const double* __restrict__ meta) {
   __shared__ __align__(16) double prep[kPrepSmem];    // gp_prepare_body's block: K -> q -> q_sqrt_full | L | L^-1 | zy | mu | ...
   __shared__ double vsm[kST * 32];                    // v of one tile of samples
+  __shared__ double ez[2 * 32];                       // exp(+c zy[m]) | exp(-c zy[m]), c = sqrt(5) / lengthscale
   const int D = a.D, M = a.M, Mp = M + 2, Nq = a.Nq, S = a.S, A = Nq + Mp;
   const int pl = blockIdx.x / a.nchunk, chunk = blockIdx.x % a.nchunk, p = pl / D, l = pl % D;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
@@ -1195,6 +1199,15 @@ __global__ void __launch_bounds__(128, 7) gp_prepare_update_kernel(PathwiseArgs 
   const double* mu = zy + 32;
   const double ell = a.ls[pl], s2 = a.var[pl], sqrtj = sqrt(a.jitter);
   const int s_begin = chunk * a.chunk, s_end = min(S, s_begin + a.chunk);
+  // Matern-5/2 in the update below: exp(-c |x - z|) = exp(-c x) exp(c z) for x >= z (and mirrored), so a thread needs two
+  // exponentials for its query point instead of one per inducing point (the exp was 15 % of this kernel's instructions).
+  // |c x|, |c z| < 300 keeps both factors far from overflow; otherwise the direct form is used.
+  const double cexp = VG_SQRT5 / ell;
+  if (tid < 32) {
+    const double z = tid < Mp ? zy[tid] : 0.0;
+    ez[tid] = exp(cexp * z);
+    ez[32 + tid] = fabs(cexp * z) < 300.0 ? exp(-cexp * z) : -1.0;     // negative marks "use the direct form"
+  }
   for (int s0 = s_begin; s0 < s_end; s0 += kST) {
     const int ns = min(kST, s_end - s0);
     __syncthreads();   // q_sqrt_full complete / previous tile's vsm consumed
@@ -1230,8 +1243,14 @@ __global__ void __launch_bounds__(128, 7) gp_prepare_update_kernel(PathwiseArgs 
       double acc[kST];
 #pragma unroll
       for (int i = 0; i < kST; ++i) acc[i] = i < ns ? a.f0[((size_t)pl * S + s0 + i) * A + n] : 0.0;
+      const bool sep = fabs(cexp * xn) < 300.0;
+      const double exp_p = sep ? exp(cexp * xn) : 0.0, exp_m = sep ? exp(-cexp * xn) : 0.0;
       for (int m = 0; m < Mp; ++m) {
-        const double kv = s2 * vg_matern52(fabs(xn - zy[m]) / ell);
+        const double dx = xn - zy[m], av = cexp * fabs(dx);
+        double ev;
+        if (sep && ez[32 + m] > 0.0) ev = dx >= 0.0 ? exp_m * ez[m] : exp_p * ez[32 + m];
+        else ev = exp(-av);
+        const double kv = s2 * ((1.0 + av + (1.0 / 3.0) * av * av) * ev);     // (5/3) r^2 = a^2 / 3 with a = sqrt(5) r
 #pragma unroll
         for (int i = 0; i < kST; ++i) acc[i] += kv * vsm[i * 32 + m];
       }
@@ -1375,9 +1394,27 @@ __global__ void __launch_bounds__(256, 4) gp_backward_kernel(BackwardArgs a) {
   __syncthreads();
   for (int i = warp; i < Mp; i += nw)
     if (lane < Mp) Lism[i * LDM + lane] = a.Linv[(size_t)pl * Mp * Mp + i * Mp + lane];
-  if (s_begin < s_end)
+  if (s_begin < s_end) {
+    // Kfu through the separable form of exp(-c |x - z|) (see gp_prepare_update_kernel): 2 N + 2 Mp exponentials per CTA
+    // instead of N Mp; the tables borrow the df tile, which is only filled inside the sample loop
+    const double cexp = VG_SQRT5 * inv_ell;
+    double* exn = dft;                                   // [2][N]  exp(+c x_n) | exp(-c x_n)
+    for (int n = tid; n < N; n += nt) {
+      const double cx = cexp * a.X[(size_t)n * D + l];
+      exn[n] = exp(cx);
+      exn[N + n] = fabs(cx) < 300.0 ? exp(-cx) : -1.0;   // negative marks "use the direct form"
+    }
+    const double cz = cexp * zy[lane & 31];
+    const double ezp = exp(cz), ezm = exp(-cz);
+    const bool zok = fabs(cz) < 300.0;
+    __syncthreads();
     for (int n = warp; n < N; n += nw)
-      if (lane < Mp) Kfu[n * Mp + lane] = s2 * vg_matern52(fabs(a.X[(size_t)n * D + l] - zy[lane]) * inv_ell);
+      if (lane < Mp) {
+        const double dx = a.X[(size_t)n * D + l] - zy[lane], av = cexp * fabs(dx);
+        const double ev = (zok && exn[N + n] > 0.0) ? (dx >= 0.0 ? exn[N + n] * ezp : exn[n] * ezm) : exp(-av);
+        Kfu[n * Mp + lane] = s2 * ((1.0 + av + (1.0 / 3.0) * av * av) * ev);
+      }
+  }
   __syncthreads();
 
   double acc_ls = 0.0, acc_var = 0.0;  // per-thread partial hyper-parameter gradients
@@ -1423,11 +1460,11 @@ __global__ void __launch_bounds__(256, 4) gp_backward_kernel(BackwardArgs a) {
       if (lane < Mp) {
         double t = 0.0;
         for (int i = 0; i < ns; ++i) t += dft[(size_t)i * N + n] * vsm[i * 32 + lane];
-        const double r = fabs(a.X[(size_t)n * D + l] - zy[lane]) * inv_ell;
-        double k, dk;
-        matern52_both(r, k, dk);
-        acc_var += t * k;
-        acc_ls += t * s2 * dk * (-r * inv_ell);
+        // k = s2 (1 + a + a^2/3) e^-a is in Kfu; dk/dr = -(5/3) r (1 + a) e^-a follows from it by a division (no second exp)
+        const double r = fabs(a.X[(size_t)n * D + l] - zy[lane]) * inv_ell, av = VG_SQRT5 * r;
+        const double ks = Kfu[n * Mp + lane];
+        acc_var += t * (ks / s2);
+        acc_ls += t * ks * ((5.0 / 3.0) * r * r * (1.0 + av) / (1.0 + av + (1.0 / 3.0) * av * av)) * inv_ell;
       }
     }
     // (4) G -= gr v^T ; (6) GS += gr eps_u^T ; gmu += gr
@@ -1696,15 +1733,22 @@ __global__ void __launch_bounds__(256, 2) gp_backward_samples_kernel(BackwardArg
   for (int i = 0; i < kTT; ++i) accT[i][0] = accT[i][1] = 0.0;
 #pragma unroll
   for (int i = 0; i < 2; ++i) accG[i][0] = accG[i][1] = accS[i][0] = accS[i][1] = 0.0;
-  double acc_ls = 0.0, acc_var = 0.0;
+  double acc_ls = 0.0, acc_var = 0.0, acc_f0 = 0.0;   // acc_f0: sum g f0, scaled by 1 / (2 s2) once at the end
   const double* dfp = a.df + (size_t)p * S * N * D + l;
 
   for (int s0 = s_begin; s0 < s_end; s0 += kBS) {
     const int ns = min(kBS, s_end - s0);
     __syncthreads();                                    // previous tile fully consumed
-    for (int idx = tid; idx < kBS * NP; idx += nt) {    // DF[s][n], zero padded
-      const int i = idx / NP, n = idx - i * NP;
-      DF[i * ldN + n] = (i < ns && n < N) ? dfp[((size_t)(s0 + i) * N + n) * D] : 0.0;
+    for (int idx = tid; idx < kBS * NP; idx += nt) {    // DF[s][n], zero padded; its share of the prior path rides along
+      const int i = idx / NP, n = idx - i * NP;           // (d f0(X) = df: the f0 / h0 loads overlap with the df loads)
+      double dv = 0.0;
+      if (i < ns && n < N) {
+        dv = dfp[((size_t)(s0 + i) * N + n) * D];
+        const size_t o = ((size_t)pl * S + s0 + i) * A + n;
+        acc_f0 += dv * a.f0[o];
+        acc_ls += dv * a.h0[o];
+      }
+      DF[i * ldN + n] = dv;
     }
     for (int idx = tid; idx < kBS * 32; idx += nt) {    // VT[m][s], ET[m][s]
       const int i = idx >> 5, m = idx & 31;
@@ -1760,15 +1804,16 @@ __global__ void __launch_bounds__(256, 2) gp_backward_samples_kernel(BackwardArg
       for (int i = 0; i < ns; ++i) tsum += B1[i * kLD + tid];
       gmu[tid] += tsum;
     }
-    // prior path: d f0(X) = df, d f0(Zy) = -gr
-    for (int idx = tid; idx < ns * A; idx += nt) {
-      const int i = idx / A, xx = idx - i * A;
-      const double gg = xx < N ? DF[i * ldN + xx] : -B1[i * kLD + xx - N];
-      const size_t o = ((size_t)pl * S + s0 + i) * A + xx;
-      acc_var += gg * a.f0[o] / (2.0 * s2);
-      acc_ls += gg * a.h0[o];
-    }
+    // prior path at the inducing points: d f0(Zy) = -gr   (sample = warp-strided, inducing point = lane: no index division)
+    for (int i = warp; i < ns; i += nw)
+      if (lane < Mp) {
+        const double gg = -B1[i * kLD + lane];
+        const size_t o = ((size_t)pl * S + s0 + i) * A + N + lane;
+        acc_f0 += gg * a.f0[o];
+        acc_ls += gg * a.h0[o];
+      }
   }
+  acc_var += acc_f0 / (2.0 * s2);
   // hyper-parameter path through Kfu: sum_{n,m} T[n,m] dKfu[n,m]/dtheta
 #pragma unroll
   for (int u = 0; u < kTT; ++u) {

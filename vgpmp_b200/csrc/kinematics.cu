@@ -483,18 +483,26 @@ __global__ void __launch_bounds__(kThreads, MINB) loglik_bwd_kernel(RobotDev rb,
         if (p + i < pend) {
           const double dist = sb.r[i].x - rb.sphere_rad[p + i];
           const double hinge = fmax(lk.epsilon - dist, 0.0);
-          const double w = hinge * inv_sigma;          // 0 outside the hinge: the wrench update needs no branch
+          const double w = hinge * inv_sigma;          // 0 outside the hinge: the wrench update needs no per-lane branch
           lp -= 0.5 * w * hinge;
-          const double gx = sb.r[i].y * w, gy = sb.r[i].z * w, gz = sb.r[i].w * w;
-          Fw[0] += gx; Fw[1] += gy; Fw[2] += gz;
-          Tw[0] += sb.y[i] * gz - sb.z[i] * gy;
-          Tw[1] += sb.z[i] * gx - sb.x[i] * gz;
-          Tw[2] += sb.x[i] * gy - sb.y[i] * gx;
+          if (__any_sync(__activemask(), hinge > 0.0)) {   // lanes = neighbouring timesteps: usually all in or all out
+            const double gx = sb.r[i].y * w, gy = sb.r[i].z * w, gz = sb.r[i].w * w;
+            Fw[0] += gx; Fw[1] += gy; Fw[2] += gz;
+            Tw[0] += sb.y[i] * gz - sb.z[i] * gy;
+            Tw[1] += sb.z[i] * gx - sb.x[i] * gz;
+            Tw[2] += sb.x[i] * gy - sb.y[i] * gx;
+          }
         }
       }
     }
   }
   logp[c] = lp;
+  // no sphere of this warp's configurations inside the hinge: every joint gradient is zero, sweep 2 has nothing to do
+  if (!__any_sync(__activemask(), Fw[0] != 0.0 || Fw[1] != 0.0 || Fw[2] != 0.0 || Tw[0] != 0.0 || Tw[1] != 0.0 || Tw[2] != 0.0)) {
+#pragma unroll 1
+    for (int j = 0; j < D; ++j) d_in[c * D + j] = 0.0;
+    return;
+  }
   // sweep 2: joint axes again (frame products from the stored sin / cos), now against the TOTAL wrench
   frame_from_base(rb, A);
   A.t[0] -= shx; A.t[1] -= shy; A.t[2] -= shz;
