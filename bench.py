@@ -376,7 +376,7 @@ class Job:
         nbytes = evals * 32
         ach = nbytes / (st["ms_per_step"] * 1e-3) / 1e9
         rec_mib = self.sdf.data.nbytes * 4 / 2**20
-        out = {"kernel": f"loglik_kernel<{self.D},true,4> (FK + one 256-bit {{value,gradient}} record load per sphere + hinge + reverse pass)",
+        out = {"kernel": f"loglik_bwd_kernel<{self.D},3,4> (FK + one 256-bit {{value,gradient}} record load per sphere + hinge + reverse pass)",
                "bound": "hbm" if rec_mib > 126 else "l2", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": nbytes,
                "ms_per_launch": st["ms_per_step"], "share_of_step": st["share"], "records_MiB": rec_mib,
@@ -384,8 +384,9 @@ class Job:
         tr = ROOT / "profiles" / "roofline_traffic.json"
         if tr.exists() and traffic_key:
             t = json.loads(tr.read_text()).get(traffic_key)
-            if t:
-                out["traffic"] = t["dram_bytes_per_launch"]
+            if t:       # DRAM bytes of the ncu capture, for the problems this stage time covers
+                out["traffic"] = t["dram_bytes_per_launch"] * self.Bp / t["problems_in_launch"] if "dram_bytes_per_launch" in t \
+                    else t["dram_bytes_per_problem"] * self.Bp
                 out["traffic_source"] = t["source"]
                 if "gather_probe" in t:     # measured ceiling of 32-byte gathers from an L2-resident grid (context for `frac`)
                     out["gather_probe"] = t["gather_probe"]
