@@ -390,7 +390,11 @@ class Job:
                 out["traffic_source"] = t["source"]
                 if "gather_probe" in t:     # measured ceiling of 32-byte gathers from an L2-resident grid (context for `frac`)
                     out["gather_probe"] = t["gather_probe"]
-                    out["frac_of_gather_probe"] = ach / t["gather_probe"]["l2_resident_grid_GBps"]
+                    # the probe gathers at RANDOM; neighbouring timesteps of a trajectory share sectors, so an HBM-resident
+                    # grid can exceed the random-gather figure
+                    key = "hbm_resident_grid_GBps" if rec_mib > 126 else "l2_resident_grid_GBps"
+                    out["frac_of_gather_probe"] = ach / t["gather_probe"][key]
+                    out["gather_probe_used"] = key
         return out
 
 
@@ -531,7 +535,7 @@ def run_b200(args):
                 peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
                 peak = 0.5 * float(peaks.get("bf16_tflops", 1590.0))
                 flops = head.Bp * head.D * 3 * 2 * 2 * head.S * A * head.B
-                kern = "pathwise_tc_kernel (tcgen05.mma kind::tf32, 3-pass split) + gp_prepare_update_kernel"
+                kern = "pathwise_tc_kernel (tcgen05.mma kind::tf32, 3-pass split, TMEM partial sums) + gp_prepare_kernel + pathwise_update_mma_kernel"
                 bound, src = "tensor", "0.5 x measured bf16 dense peak (MEASURED_PEAKS.json) = TF32 dense rate"
             else:
                 peak = float(eng.lib.vgpmp_probe_fp64_tflops(local))
