@@ -27,6 +27,7 @@ class StreamedVGPMP:
         dev = models[0]._eng.device
         self.streams = [torch.cuda.Stream(device=dev) for _ in models]
         self.num_problems = sum(m.num_problems for m in models)
+        self._host_loss = None
 
     @classmethod
     def initialize(cls, query_states, num_streams: int = 2, **kw) -> "StreamedVGPMP":
@@ -69,11 +70,23 @@ class StreamedVGPMP:
 
     def train_step_host(self, X_host: torch.Tensor) -> torch.Tensor:
         """Host-buffer step (`vgpmp_train_step_host_begin/_end` per sub-batch): all sub-batches are enqueued before the
-        first one is waited for.  Returns a CPU tensor [Bp]."""
-        for m, s in zip(self.models, self.streams):
-            with torch.cuda.stream(s):
-                m.train_step_host(X_host, wait=False)
-        return torch.cat([m.train_step_host_wait().reshape(-1) for m in self.models])
+        first one is waited for; their losses land in slices of ONE pinned buffer.  Returns a CPU tensor [Bp] (a copy)."""
+        if self._host_loss is None:
+            self._host_loss = torch.empty(self.num_problems, dtype=torch.float64).pin_memory()
+            parts, lo = [], 0
+            for m in self.models:
+                parts.append(self._host_loss[lo:lo + m.num_problems])
+                lo += m.num_problems
+            self._host_parts = parts
+            for m, s, part in zip(self.models, self.streams, parts):      # first step: allocations under the right stream
+                with torch.cuda.stream(s):
+                    m.train_step_host(X_host, wait=False, stream=s.cuda_stream, loss_out=part)
+        else:
+            for m, s, part in zip(self.models, self.streams, self._host_parts):
+                m.train_step_host(X_host, wait=False, stream=s.cuda_stream, loss_out=part)
+        for m in self.models:
+            m.train_step_host_wait(copy=False)
+        return self._host_loss.clone()
 
     # ------------------------------------------------------------------ gathered state
     def _cat(self, name):

@@ -371,11 +371,43 @@ class VGPMP:
         st = self._adam_struct(lo, hi)
         eng._chk(eng.lib.vgpmp_adam_step(eng.h, C.byref(dims), C.byref(st), C.byref(gs), eng._stream()), "adam_step")
 
-    def train_step_host(self, X_host: torch.Tensor, wait: bool = True):
+    def train_step_host(self, X_host: torch.Tensor, wait: bool = True, stream: int = None, loss_out: torch.Tensor = None):
         """The same optimisation step driven from HOST buffers through `vgpmp_train_step_host`: X [N,D] is read from
         (pinned) host memory, copied to the device, the step's randomness is drawn on the device, and loss = -ELBO [Bp]
         is copied back to pinned host memory before the call returns (like `loss = tf_optimization_step(...)` feeding
-        the tqdm readout, utils/miscellaneous.py:101-103).  Returns a CPU tensor (a copy of the pinned loss buffer)."""
+        the tqdm readout, utils/miscellaneous.py:101-103).  Returns a CPU tensor (a copy of the pinned loss buffer).
+        `stream` (a raw CUDA stream handle; default: torch's current stream) and `loss_out` (a pinned float64 [Bp] buffer the
+        loss is written to instead of the model's own) are for callers that drive several models, see StreamedVGPMP.
+
+        The steady state is ONE ctypes call: the argument block is cached per (host buffer, stream, optimiser settings)."""
+        hs = getattr(self, "_host_state", None)
+        o, t = self.optimizer, self.trainable
+        sid = stream if stream is not None else torch.cuda.current_stream(self._eng.device).cuda_stream
+        key = (X_host.data_ptr(), X_host.numel(), sid, self.seed, self.problem_offset, o.learning_rate, o.beta_1, o.beta_2,
+               o.epsilon, t["q_mu"], t["q_sqrt"], t["lengthscales"], t["kernel_variance"],
+               None if loss_out is None else loss_out.data_ptr())
+        call = hs["call"] if hs is not None else None
+        if call is None or call["key"] != key:
+            call = self._host_call(X_host, sid, loss_out, key)
+        if hs is None:
+            hs = self._host_state
+        if hs["pending"]:
+            raise RuntimeError("train_step_host(wait=False) was called twice without train_step_host_wait(): the pinned "
+                               "loss buffer of the step in flight would be overwritten")
+        st = call["st"]
+        st.step = self._step
+        rc = call["begin"](*call["args"])
+        if rc:
+            self._eng._chk(rc, "train_step_host_begin")
+        self._step = st.step
+        hs["pending"] = True
+        if not wait:
+            return None
+        return self.train_step_host_wait()
+
+    def _host_call(self, X_host, sid, loss_out, key):
+        """Slow path of `train_step_host`: checks the host tensor, (re)allocates the per-shape device state and builds the
+        argument block of the C call."""
         eng, D = self._eng, self.num_latent_gps
         if self._shard is not None:
             raise NotImplementedError("train_step_host does not all-reduce: a sample-sharded model steps with train_step")
@@ -383,6 +415,8 @@ class VGPMP:
             raise TypeError("train_step_host expects a contiguous float64 CPU tensor (pinned for async copies)")
         N = X_host.numel() // D
         dims = self._dims(N)
+        if len(self._plan(eng.dev(X_host.reshape(N, D)), False)[0]) != 1:
+            raise NotImplementedError("train_step_host serves batches that fit one workspace chunk; use train_step")
         hs = getattr(self, "_host_state", None)
         if hs is None or hs["N"] != N:
             Xc = X_host.reshape(N, D)
@@ -394,48 +428,41 @@ class VGPMP:
                 else 2 * int(eng.lib.vgpmp_draws_bytes(C.byref(dims), D))
             hs = dict(N=N, X_dev=eng.empty(N, D), draws=torch.empty(nbytes, dtype=torch.uint8, device=eng.device),
                       elbo=eng.empty(self.num_problems),
-                      loss=torch.empty(self.num_problems, dtype=torch.float64).pin_memory(), pending=False,
+                      loss=torch.empty(self.num_problems, dtype=torch.float64).pin_memory(), pending=False, call=None,
                       g=dict(d_q_mu=eng.empty(self.num_problems, self.num_inducing, D),
                              d_q_sqrt=eng.empty(self.num_problems, D, self.num_inducing, self.num_inducing),
                              d_lengthscales=eng.empty(self.num_problems, D), d_variances=eng.empty(self.num_problems, D)))
             self._host_state = hs
-        if hs["pending"]:
-            raise RuntimeError("train_step_host(wait=False) was called twice without train_step_host_wait(): the pinned "
-                               "loss buffer of the step in flight would be overwritten")
-        stream = torch.cuda.current_stream(eng.device).cuda_stream
-        call = hs.get("call")
-        o = self.optimizer
-        key = (X_host.data_ptr(), stream, tuple(sorted(self.trainable.items())), self.seed, self.problem_offset,
-               o.learning_rate, o.beta_1, o.beta_2, o.epsilon)
-        if call is None or call["key"] != key:
-            # the argument block of the C call is built once per (host buffer, stream): per step only Adam's step counter changes
-            g = hs["g"]
-            gs = _cabi.Grads(g["d_q_mu"].data_ptr(), g["d_q_sqrt"].data_ptr(), g["d_lengthscales"].data_ptr(),
-                             g["d_variances"].data_ptr())
-            st = self._adam_struct()
-            ws = eng.workspace(dims)
-            call = dict(key=key, st=st, gs=gs, dims=dims, stream=C.c_void_p(stream), keep=(ws, X_host),
-                        args=(eng.h, C.byref(dims), C.byref(st), self._query_states.data_ptr(), self._Z.data_ptr(),
-                              X_host.data_ptr(), hs["X_dev"].data_ptr(), self.seed, int(self.problem_offset),
-                              hs["draws"].data_ptr(), hs["draws"].numel(), C.byref(gs), hs["elbo"].data_ptr(),
-                              hs["loss"].data_ptr(), ws.data_ptr(), ws.numel(), C.c_void_p(stream)))
-            hs["call"] = call
-        call["st"].step = self._step
-        eng._chk(eng.lib.vgpmp_train_step_host_begin(*call["args"]), "train_step_host_begin")
-        self._step = call["st"].step
-        hs["dims"], hs["stream"], hs["pending"] = call["dims"], call["stream"], True
-        if not wait:
-            return None
-        return self.train_step_host_wait()
+        if loss_out is not None and (loss_out.device.type != "cpu" or loss_out.dtype != torch.float64
+                                     or loss_out.numel() != self.num_problems or not loss_out.is_contiguous()):
+            raise TypeError("loss_out must be a contiguous float64 CPU tensor with one entry per problem")
+        loss = hs["loss"] if loss_out is None else loss_out
+        g = hs["g"]
+        gs = _cabi.Grads(g["d_q_mu"].data_ptr(), g["d_q_sqrt"].data_ptr(), g["d_lengthscales"].data_ptr(),
+                         g["d_variances"].data_ptr())
+        st = self._adam_struct()
+        ws = eng.workspace(dims)
+        stream = C.c_void_p(sid)
+        call = dict(key=key, st=st, gs=gs, dims=dims, stream=stream, keep=(ws, X_host, loss), loss=loss,
+                    begin=eng.lib.vgpmp_train_step_host_begin, end=eng.lib.vgpmp_train_step_host_end,
+                    args=(eng.h, C.byref(dims), C.byref(st), self._query_states.data_ptr(), self._Z.data_ptr(),
+                          X_host.data_ptr(), hs["X_dev"].data_ptr(), self.seed, int(self.problem_offset),
+                          hs["draws"].data_ptr(), hs["draws"].numel(), C.byref(gs), hs["elbo"].data_ptr(),
+                          loss.data_ptr(), ws.data_ptr(), ws.numel(), stream),
+                    end_args=(eng.h, C.byref(dims), loss.data_ptr(), stream))
+        hs["call"] = call
+        return call
 
-    def train_step_host_wait(self):
+    def train_step_host_wait(self, copy: bool = True):
         """Second half of `train_step_host(..., wait=False)`: blocks until the loss of the step in flight is in host
-        memory and returns a copy of it (the pinned buffer is re-used by the next step)."""
-        eng, hs = self._eng, self._host_state
-        eng._chk(eng.lib.vgpmp_train_step_host_end(eng.h, C.byref(hs["dims"]), hs["loss"].data_ptr(), hs["stream"]),
-                 "train_step_host_end")
+        memory and returns a copy of it (the pinned buffer is re-used by the next step; `copy=False` returns the buffer)."""
+        hs = self._host_state
+        call = hs["call"]
+        rc = call["end"](*call["end_args"])
+        if rc:
+            self._eng._chk(rc, "train_step_host_end")
         hs["pending"] = False
-        return hs["loss"].clone()
+        return call["loss"].clone() if copy else call["loss"]
 
     def predict_f_samples(self, X, num_samples=None, draws=None):
         """temporary_paths + predict_f_samples (models/vgpmp.py:281-282): [S,N,D] latent samples."""
