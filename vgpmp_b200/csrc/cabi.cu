@@ -342,7 +342,7 @@ int vgpmp_sdf_lookup(vgpmp_handle* h, const double* pts, double* dist, double* g
 int vgpmp_loglik_fwd_bwd(vgpmp_handle* h, const double* in, int squash, double upstream, double* logp, double* d_in,
                          int64_t n, void* stream) {
   if (!h || n < 0 || (n > 0 && (!in || !logp))) return fail(h, VGPMP_ERR_INVALID, "loglik_fwd_bwd: bad argument");
-  return check_cuda(h, launch_loglik(h, in, squash, upstream, logp, d_in, n, (cudaStream_t)stream), "loglik_fwd_bwd");
+  return check_cuda(h, launch_loglik(h, in, squash, upstream, logp, d_in, n, 0, (cudaStream_t)stream), "loglik_fwd_bwd");
 }
 
 int vgpmp_clearance(vgpmp_handle* h, const double* joints, double* clearance, int64_t n, void* stream) {
@@ -411,7 +411,7 @@ int vgpmp_pathwise_sample(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_p
   GpScratch g = carve(ws, h->robot.dof, dq, &need, h->num_sms);
   if (ws_bytes < need) return fail(h, VGPMP_ERR_WORKSPACE, "pathwise_sample: workspace too small (size it with num_timesteps = num_query)");
   cudaStream_t s = (cudaStream_t)stream;
-  return check_cuda(h, launch_pathwise(h, dq, *p, *r, Xq, num_query, g.Lc, g.Sfull, g.Linv, g.kl_l, g.kvec, f, nullptr, g.f0, nullptr, g.meta, s),
+  return check_cuda(h, launch_pathwise(h, dq, *p, *r, Xq, num_query, g.Lc, g.Sfull, g.Linv, g.kl_l, g.kvec, f, nullptr, g.f0, nullptr, g.meta, 0, s),
                     "pathwise_sample");
 }
 
@@ -427,7 +427,12 @@ int vgpmp_elbo_fwd_bwd(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_para
   cudaStream_t s = (cudaStream_t)stream;
   const int D = h->robot.dof;
   const int64_t ncfg = (int64_t)dims->num_problems * dims->num_samples * dims->num_timesteps;
-  double* f = (aux && aux->f) ? aux->f : g.f;
+  // Inside the step the samples and their cotangents are latent-major, [Bp,D,S,N]: the GP kernels (one CTA per problem and
+  // latent) and the likelihood (lanes = consecutive timesteps) then read and write contiguous runs.  A caller who asks for
+  // the samples (aux->f) gets the reference's [Bp,S,N,D].
+  static const int planar_env = getenv("VGPMP_F_PLANAR") ? atoi(getenv("VGPMP_F_PLANAR")) : 1;   // experiment switch
+  const int planar = (aux && aux->f) ? 0 : planar_env;
+  double* f = planar ? g.f : aux->f;
   double* logp = (aux && aux->logp) ? aux->logp : g.logp;
   const bool bwd = gr != nullptr;
   {
@@ -435,13 +440,14 @@ int vgpmp_elbo_fwd_bwd(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_para
     StageSpan sp(h, ST_PATHWISE, s);
     if ((rc = check_cuda(h, launch_pathwise(h, *dims, *p, *r, p->X, dims->num_timesteps, g.Lc, g.Sfull, g.Linv, g.kl_l,
                                             g.kvec, f, bwd ? g.v : nullptr, g.f0, bwd ? g.h0 : nullptr,
-                                            g.meta, s), "pathwise")))
+                                            g.meta, planar, s), "pathwise")))
       return rc;
   }
   {
     StageSpan sp(h, ST_LOGLIK, s);
     if ((rc = check_cuda(h, launch_loglik(h, f, 1, h->lik.alpha / (double)(dims->total_samples > 0 ? dims->total_samples : dims->num_samples), logp,
-                                          bwd ? g.df : nullptr, ncfg, s), "loglik")))
+                                          bwd ? g.df : nullptr, ncfg,
+                                          planar ? (int64_t)dims->num_samples * dims->num_timesteps : 0, s), "loglik")))
       return rc;
   }
   {
@@ -452,6 +458,7 @@ int vgpmp_elbo_fwd_bwd(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_para
   if (bwd) {
     GpScratch gs = g;
     gs.f = f;
+    gs.planar = planar;
     StageSpan sp(h, ST_BACKWARD, s);
     if ((rc = check_cuda(h, launch_gp_backward(h, *dims, *p, *r, gs, *gr, s), "gp_backward"))) return rc;
   }

@@ -95,8 +95,9 @@ cudaError_t launch_fk_spheres(vgpmp_handle* h, const double* joints, double* cen
 cudaError_t launch_sdf_build(vgpmp_handle* h, const double* raw_dev, cudaStream_t s);
 cudaError_t launch_sdf_lookup(vgpmp_handle* h, const double* pts, double* dist, double* grad, int64_t n, cudaStream_t s);
 cudaError_t launch_clearance(vgpmp_handle* h, const double* joints, double* clearance, int64_t n, cudaStream_t s);
+// planar_sn = 0: in / d_in are [n,D]; else in / d_in are [n / planar_sn][D][planar_sn] (latent-major per problem)
 cudaError_t launch_loglik(vgpmp_handle* h, const double* in, int squash, double upstream, double* logp, double* d_in,
-                          int64_t n, cudaStream_t s);
+                          int64_t n, int64_t planar_sn, cudaStream_t s);
 
 // ---- launchers implemented in gp.cu ---------------------------------------------------------
 struct GpScratch {  // carved from the caller's workspace by cabi.cu
@@ -108,8 +109,9 @@ struct GpScratch {  // carved from the caller's workspace by cabi.cu
   double* v;       // [Bp,D,S,Mp]
   double* f0;      // [Bp,D,S,A]   prior draws at X then Zy
   double* h0;      // [Bp,D,S,A]   d f0 / d lengthscale
-  double* f;       // [Bp,S,N,D]
-  double* df;      // [Bp,S,N,D]
+  double* f;       // [Bp,D,S,N] inside the fused step (planar != 0), [Bp,S,N,D] when the caller supplied the buffer
+  double* df;      // same layout as f
+  int planar;
   double* logp;    // [Bp,S,N]
   double* meta;    // [8] input-structure probe {grid flag, t0, dt, z0, dz}
   double* loss;    // [Bp] -ELBO, what vgpmp_train_step_host copies back
@@ -126,7 +128,7 @@ cudaError_t launch_gp_prepare(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_
                               double* kl_l, double* kvec, double* Linv, cudaStream_t s);
 cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
                             const double* Xq, int Nq, double* Lc, double* Sfull, double* Linv, double* kl_l, double* kvec,
-                            double* f, double* v, double* f0, double* h0, double* meta, cudaStream_t s);
+                            double* f, double* v, double* f0, double* h0, double* meta, int f_planar, cudaStream_t s);
 int sampler_generates_draws(const vgpmp_handle* h, const vgpmp_dims& d);
 cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
                                const GpScratch& ws, const vgpmp_grads& g, cudaStream_t s);

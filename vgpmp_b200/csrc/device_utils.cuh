@@ -16,7 +16,13 @@ struct PathwiseArgs {
   const double *omega, *tau, *w, *eps_u, *eps_j;
   const double *Lc, *Sfull, *Linv;
   double *f, *v, *f0, *h0;
+  int f_planar;        // 0: f [Bp,S,Nq,D] (the reference's layout, public entry points); 1: f [Bp,D,S,Nq] (inside the fused step)
 };
+
+// element (problem p, sample s, point n, latent l) of the latent samples / their cotangents in either layout
+__device__ __forceinline__ size_t f_index(int planar, int p, int s, int n, int l, int S, int N, int D) {
+  return planar ? (((size_t)p * D + l) * S + s) * N + n : (((size_t)p * S + s) * N + n) * D + l;
+}
 
 // sampler_tc.cu: equispaced sampler on the 5th-generation tensor cores (tcgen05.mma kind::tf32, 3-pass hi/lo split,
 // accumulators in TMEM).  `supported` = shape and sample count it is built for; the launcher stops at f0 / h0.

@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(768) pathwise_kernel(PathwiseArgs a, const dou
       const int i = idx / Nq, n = idx % Nq;
       double fv = red[(size_t)i * XP + n];
       for (int m = 0; m < Mp; ++m) fv += Kfu[n * Mp + m] * vs[i * 32 + m];
-      a.f[(((size_t)p * S + s0 + i) * Nq + n) * D + l] = fv;
+      a.f[f_index(a.f_planar, p, s0 + i, n, l, S, Nq, D)] = fv;
     }
     __syncthreads();
   }
@@ -1256,7 +1256,7 @@ __global__ void __launch_bounds__(128, 7) gp_prepare_update_kernel(PathwiseArgs 
       }
 #pragma unroll
       for (int i = 0; i < kST; ++i)
-        if (i < ns) a.f[(((size_t)p * S + s0 + i) * Nq + n) * D + l] = acc[i];
+        if (i < ns) a.f[f_index(a.f_planar, p, s0 + i, n, l, S, Nq, D)] = acc[i];
     }
   }
 }
@@ -1329,7 +1329,7 @@ __global__ void __launch_bounds__(256) pathwise_update_kernel(PathwiseArgs a, co
     for (int n = lane; n < Nq; n += 32) {
       double acc = a.f0[ps * A + n];
       for (int m = 0; m < Mp; ++m) acc += KT[m * NP + n] * row[m];
-      a.f[(((size_t)p * S + s) * Nq + n) * D + l] = acc;
+      a.f[f_index(a.f_planar, p, s, n, l, S, Nq, D)] = acc;
     }
     __syncwarp();
   }
@@ -1346,6 +1346,7 @@ struct BackwardArgs {
   const double *Z, *X, *ls, *var, *q_sqrt;
   const double *eps_u;
   const double *Lc, *Linv, *kvec, *v, *f0, *h0, *df;
+  int df_planar;       // layout of df, as PathwiseArgs::f_planar
   double *d_q_mu, *d_q_sqrt, *d_ls, *d_var;
 };
 
@@ -1418,14 +1419,16 @@ __global__ void __launch_bounds__(256, 4) gp_backward_kernel(BackwardArgs a) {
   __syncthreads();
 
   double acc_ls = 0.0, acc_var = 0.0;  // per-thread partial hyper-parameter gradients
-  const double* dfp = a.df + (size_t)p * S * N * D + l;  // df[s,n] at dfp[(s*N+n)*D]
+  // df[s,n] at dfp[(s*N+n)*dfs]
+  const double* dfp = a.df + (size_t)p * S * N * D + (a.df_planar ? (size_t)l * S * N : (size_t)l);
+  const int dfs = a.df_planar ? 1 : D;
 
   for (int s0 = s_begin; s0 < s_end; s0 += kBT) {
     const int ns = min(kBT, s_end - s0);
     // stage this tile's df (strided in global: [s,n,D]), v and eps_u in shared memory
     for (int idx = tid; idx < kBT * N; idx += nt) {
       const int i = idx / N, n = idx - i * N;
-      dft[idx] = i < ns ? dfp[((size_t)(s0 + i) * N + n) * D] : 0.0;
+      dft[idx] = i < ns ? dfp[((size_t)(s0 + i) * N + n) * dfs] : 0.0;
     }
     for (int idx = tid; idx < kBT * 32; idx += nt) {
       const int i = idx >> 5, m = idx & 31;
@@ -1734,7 +1737,8 @@ __global__ void __launch_bounds__(256, 2) gp_backward_samples_kernel(BackwardArg
 #pragma unroll
   for (int i = 0; i < 2; ++i) accG[i][0] = accG[i][1] = accS[i][0] = accS[i][1] = 0.0;
   double acc_ls = 0.0, acc_var = 0.0, acc_f0 = 0.0;   // acc_f0: sum g f0, scaled by 1 / (2 s2) once at the end
-  const double* dfp = a.df + (size_t)p * S * N * D + l;
+  const double* dfp = a.df + (size_t)p * S * N * D + (a.df_planar ? (size_t)l * S * N : (size_t)l);
+  const int dfs = a.df_planar ? 1 : D;
 
   for (int s0 = s_begin; s0 < s_end; s0 += kBS) {
     const int ns = min(kBS, s_end - s0);
@@ -1743,7 +1747,7 @@ __global__ void __launch_bounds__(256, 2) gp_backward_samples_kernel(BackwardArg
       const int i = idx / NP, n = idx - i * NP;           // (d f0(X) = df: the f0 / h0 loads overlap with the df loads)
       double dv = 0.0;
       if (i < ns && n < N) {
-        dv = dfp[((size_t)(s0 + i) * N + n) * D];
+        dv = dfp[((size_t)(s0 + i) * N + n) * dfs];
         const size_t o = ((size_t)pl * S + s0 + i) * A + n;
         acc_f0 += dv * a.f0[o];
         acc_ls += dv * a.h0[o];
@@ -1944,8 +1948,8 @@ __global__ void __launch_bounds__(256, 2) pathwise_update_mma_kernel(PathwiseArg
       wmma_rn<8>(c0, c1, T1, kLD, KF + ni * 8 * kLD, kLD, g, t);
       const int n0 = ni * 8 + 2 * t;
       if (g < ns) {
-        if (n0 < Nq) a.f[(((size_t)p * S + s0 + g) * Nq + n0) * D + l] = c0 + a.f0[(ps0 + g) * A + n0];
-        if (n0 + 1 < Nq) a.f[(((size_t)p * S + s0 + g) * Nq + n0 + 1) * D + l] = c1 + a.f0[(ps0 + g) * A + n0 + 1];
+        if (n0 < Nq) a.f[f_index(a.f_planar, p, s0 + g, n0, l, S, Nq, D)] = c0 + a.f0[(ps0 + g) * A + n0];
+        if (n0 + 1 < Nq) a.f[f_index(a.f_planar, p, s0 + g, n0 + 1, l, S, Nq, D)] = c1 + a.f0[(ps0 + g) * A + n0 + 1];
       }
     }
     __syncwarp();
@@ -2206,7 +2210,7 @@ int sampler_generates_draws(const vgpmp_handle* h, const vgpmp_dims& d) {
 
 cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_params& p, const vgpmp_draws& r,
                             const double* Xq, int Nq, double* Lc, double* Sfull, double* Linv, double* kl_l, double* kvec,
-                            double* f, double* v, double* f0, double* h0, double* meta, cudaStream_t s) {
+                            double* f, double* v, double* f0, double* h0, double* meta, int f_planar, cudaStream_t s) {
   // Schedule: [draw materialisation if needed] -> input probe -> equispaced sampler (stops at the prior draw f0 / h0; it
   // needs no GP factor) -> gp_prepare_update_kernel (Kuu, Cholesky, L^-1, q_sqrt_full, KL, then the pathwise update) ->
   // general sampler, which exits at once unless the probe found X / Z not to be an equispaced rank-1 grid.
@@ -2229,7 +2233,7 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
   }
   a.Z = p.Z; a.Xq = Xq; a.ls = p.lengthscales; a.var = p.variances; a.q_mu = p.q_mu; a.query_latent = p.query_latent;
   a.omega = r.omega; a.tau = r.tau; a.w = r.w; a.eps_u = r.eps_u; a.eps_j = r.eps_j;
-  a.Lc = Lc; a.Sfull = Sfull; a.Linv = Linv; a.f = f; a.v = v; a.f0 = f0; a.h0 = h0;
+  a.Lc = Lc; a.Sfull = Sfull; a.Linv = Linv; a.f = f; a.v = v; a.f0 = f0; a.h0 = h0; a.f_planar = f_planar;
   cudaError_t e;
   const int pairs = d.num_problems * a.D;
   const SamplerKind kind = f0 != nullptr ? pick_sampler(h, a) : SAMPLER_GENERAL;
@@ -2414,7 +2418,7 @@ cudaError_t launch_gp_backward(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp
   a.klw = d.kl_shards > 1 ? 1.0 / (double)d.kl_shards : 1.0;
   a.Z = p.Z; a.X = p.X; a.ls = p.lengthscales; a.var = p.variances; a.q_sqrt = p.q_sqrt;
   a.eps_u = r.eps_u;
-  a.Lc = ws.Lc; a.Linv = ws.Linv; a.kvec = ws.kvec; a.v = ws.v; a.f0 = ws.f0; a.h0 = ws.h0; a.df = ws.df;
+  a.Lc = ws.Lc; a.Linv = ws.Linv; a.kvec = ws.kvec; a.v = ws.v; a.f0 = ws.f0; a.h0 = ws.h0; a.df = ws.df; a.df_planar = ws.planar;
   a.d_q_mu = g.d_q_mu; a.d_q_sqrt = g.d_q_sqrt; a.d_ls = g.d_lengthscales; a.d_var = g.d_variances;
   const int Mp = a.M + 2;
   const size_t kreg = std::max((size_t)a.N * Mp, (size_t)2 * 32 * LDM);   // Kfu inside the sample loop, L | GL after it

@@ -276,6 +276,22 @@ __device__ __forceinline__ double stable_sigmoid(double x) {
 // Spheres of a frame are handled NB at a time: all NB record loads (one 256-bit load per sphere) are issued before the first
 // one is consumed.  The joint axes needed by the reverse pass (7 doubles per
 // joint) are parked in shared memory, [value][thread] so that a warp's accesses are contiguous.
+// Where the D joint inputs of configuration c live: [n,D] (planar_sn = 0), or latent-major per problem,
+// [n / planar_sn][D][planar_sn] (the fused step's layout: a warp's lanes then read consecutive doubles).
+struct JointLayout {
+  size_t base, stride;
+};
+__device__ __forceinline__ JointLayout joint_layout(int64_t c, int D, int64_t planar_sn) {
+  JointLayout jl;
+  if (planar_sn == 0) {
+    jl.base = (size_t)c * D; jl.stride = 1;
+  } else {
+    const int64_t p = (c >> 32) == 0 && (planar_sn >> 32) == 0 ? (int64_t)((unsigned)c / (unsigned)planar_sn) : c / planar_sn;
+    jl.base = (size_t)p * planar_sn * D + (size_t)(c - p * planar_sn); jl.stride = (size_t)planar_sn;
+  }
+  return jl;
+}
+
 template <int NB>
 struct SphereBatch {
   double x[NB], y[NB], z[NB];
@@ -286,11 +302,12 @@ template <int D, bool BWD, int NB>
 __global__ void __launch_bounds__(kThreads, 3) loglik_kernel(RobotDev rb, SdfDev sdf, LikDev lk,
                                                          const double* __restrict__ in, int squash, double upstream,
                                                          double* __restrict__ logp, double* __restrict__ d_in,
-                                                         int64_t n) {
+                                                         int64_t n, int64_t planar_sn) {
   extern __shared__ double axes[];  // BWD only: [D][8][kThreads]  (axis z, axis x point n, prefix term, d theta/d in)
   const int tid = threadIdx.x;
   const int64_t c = (int64_t)blockIdx.x * kThreads + tid;
   if (c >= n) return;
+  const JointLayout jl = joint_layout(c, D, planar_sn);   // joint k of this configuration: in[jl.base + k * jl.stride]
 
   Frame A;
   frame_from_base(rb, A);
@@ -298,14 +315,14 @@ __global__ void __launch_bounds__(kThreads, 3) loglik_kernel(RobotDev rb, SdfDev
   double lp = 0.0;
   const double inv_sigma = 1.0 / lk.sigma_obs;
   int p = 0;
-  double xnext = in[c * D];   // joint inputs are fetched one joint ahead of their use
+  double xnext = in[jl.base];   // joint inputs are fetched one joint ahead of their use
 
 #pragma unroll 1
   for (int k = 0; k <= D; ++k) {
     if (k > 0) {
       const int j = k - 1;
       const double xin = xnext;
-      if (k < D) xnext = in[c * D + k];
+      if (k < D) xnext = in[jl.base + k * jl.stride];
       lp += xin - xin;     // 0 for a finite input; NaN / Inf inputs must not vanish in the voxel clip and the hinge's fmax
       double thj = xin, dsq = 1.0;
       if (squash) {
@@ -374,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 3) loglik_kernel(RobotDev rb, SdfDev
       const double dth = slot[0] * Tw[0] + slot[kThreads] * Tw[1] + slot[2 * kThreads] * Tw[2] -
                          (slot[3 * kThreads] * Fw[0] + slot[4 * kThreads] * Fw[1] + slot[5 * kThreads] * Fw[2]) -
                          slot[6 * kThreads];
-      d_in[c * D + j] = upstream * dth * slot[7 * kThreads];
+      d_in[jl.base + j * jl.stride] = upstream * dth * slot[7 * kThreads];
     }
   }
 }
@@ -417,11 +434,12 @@ template <int D, int NB, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) loglik_bwd_kernel(RobotDev rb, SdfDev sdf, LikDev lk,
                                                                    const double* __restrict__ in, int squash, double upstream,
                                                                    double* __restrict__ logp, double* __restrict__ d_in,
-                                                                   int64_t n) {
+                                                                   int64_t n, int64_t planar_sn) {
   extern __shared__ double trig[];  // [D][4][kThreads]  sin, cos of the joint angle, d theta / d in, prefix term
   const int tid = threadIdx.x;
   const int64_t c = (int64_t)blockIdx.x * kThreads + tid;
   if (c >= n) return;
+  const JointLayout jl = joint_layout(c, D, planar_sn);   // joint k of this configuration: in[jl.base + k * jl.stride]
 
   // The chain is walked in GRID coordinates (base translation shifted by -(scene offset + grid origin)): a sphere centre
   // is then directly the voxel coordinate numerator, and the joint-gradient formula is invariant under a common shift of
@@ -433,14 +451,14 @@ __global__ void __launch_bounds__(kThreads, MINB) loglik_bwd_kernel(RobotDev rb,
   double Fw[3] = {0.0, 0.0, 0.0}, Tw[3] = {0.0, 0.0, 0.0};  // running wrench of the spheres seen so far
   double lp = 0.0;
   const double inv_sigma = 1.0 / lk.sigma_obs;
-  double xnext = in[c * D];   // joint inputs are fetched one joint ahead of their use
+  double xnext = in[jl.base];   // joint inputs are fetched one joint ahead of their use
 
 #pragma unroll 1
   for (int k = 0; k <= D; ++k) {
     if (k > 0) {
       const int j = k - 1;
       const double xin = xnext;
-      if (k < D) xnext = in[c * D + k];
+      if (k < D) xnext = in[jl.base + k * jl.stride];
       lp += xin - xin;     // 0 for a finite input; NaN / Inf inputs must not vanish in the voxel clip and the hinge's fmax
       double thj = xin, dsq = 1.0;
       if (squash) {
@@ -500,7 +518,7 @@ __global__ void __launch_bounds__(kThreads, MINB) loglik_bwd_kernel(RobotDev rb,
   // no sphere of this warp's configurations inside the hinge: every joint gradient is zero, sweep 2 has nothing to do
   if (!__any_sync(__activemask(), Fw[0] != 0.0 || Fw[1] != 0.0 || Fw[2] != 0.0 || Tw[0] != 0.0 || Tw[1] != 0.0 || Tw[2] != 0.0)) {
 #pragma unroll 1
-    for (int j = 0; j < D; ++j) d_in[c * D + j] = 0.0;
+    for (int j = 0; j < D; ++j) d_in[jl.base + j * jl.stride] = 0.0;
     return;
   }
   // sweep 2: joint axes again (frame products from the stored sin / cos), now against the TOTAL wrench
@@ -516,7 +534,7 @@ __global__ void __launch_bounds__(kThreads, MINB) loglik_bwd_kernel(RobotDev rb,
     if (rb.craig) { zx = A.r[2]; zy = A.r[5]; zz = A.r[8]; ox = A.t[0]; oy = A.t[1]; oz = A.t[2]; }
     const double nx = zy * oz - zz * oy, ny = zz * ox - zx * oz, nz = zx * oy - zy * ox;
     const double dth = zx * Tw[0] + zy * Tw[1] + zz * Tw[2] - (nx * Fw[0] + ny * Fw[1] + nz * Fw[2]) - pj;
-    d_in[c * D + j] = upstream * dth * dsq;
+    d_in[jl.base + j * jl.stride] = upstream * dth * dsq;
   }
 }
 
@@ -531,17 +549,17 @@ constexpr int kBwdBatch = VGPMP_BWD_BATCH, kBwdMinBlocks = VGPMP_BWD_MINB;
 
 template <int D>
 cudaError_t launch_loglik_d(vgpmp_handle* h, const double* in, int squash, double upstream, double* logp, double* d_in,
-                            int64_t n, cudaStream_t s) {
+                            int64_t n, int64_t planar_sn, cudaStream_t s) {
   const unsigned blocks = (unsigned)((n + kThreads - 1) / kThreads);
   if (d_in != nullptr) {
     const size_t smem = sizeof(double) * D * 4 * kThreads;
     auto kern = loglik_bwd_kernel<D, kBwdBatch, kBwdMinBlocks>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<blocks, kThreads, smem, s>>>(h->robot, h->sdf, h->lik, in, squash, upstream, logp, d_in, n);
+    kern<<<blocks, kThreads, smem, s>>>(h->robot, h->sdf, h->lik, in, squash, upstream, logp, d_in, n, planar_sn);
   } else {
     loglik_kernel<D, false, kSphereBatch><<<blocks, kThreads, 0, s>>>(h->robot, h->sdf, h->lik, in, squash, upstream,
-                                                                     logp, d_in, n);
+                                                                     logp, d_in, n, planar_sn);
   }
   return cudaGetLastError();
 }
@@ -586,18 +604,18 @@ cudaError_t launch_clearance(vgpmp_handle* h, const double* joints, double* clea
 }
 
 cudaError_t launch_loglik(vgpmp_handle* h, const double* in, int squash, double upstream, double* logp, double* d_in,
-                          int64_t n, cudaStream_t s) {
+                          int64_t n, int64_t planar_sn, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   h->launches++;
   switch (h->robot.dof) {
-    case 1: return launch_loglik_d<1>(h, in, squash, upstream, logp, d_in, n, s);
-    case 2: return launch_loglik_d<2>(h, in, squash, upstream, logp, d_in, n, s);
-    case 3: return launch_loglik_d<3>(h, in, squash, upstream, logp, d_in, n, s);
-    case 4: return launch_loglik_d<4>(h, in, squash, upstream, logp, d_in, n, s);
-    case 5: return launch_loglik_d<5>(h, in, squash, upstream, logp, d_in, n, s);
-    case 6: return launch_loglik_d<6>(h, in, squash, upstream, logp, d_in, n, s);
-    case 7: return launch_loglik_d<7>(h, in, squash, upstream, logp, d_in, n, s);
-    case 8: return launch_loglik_d<8>(h, in, squash, upstream, logp, d_in, n, s);
+    case 1: return launch_loglik_d<1>(h, in, squash, upstream, logp, d_in, n, planar_sn, s);
+    case 2: return launch_loglik_d<2>(h, in, squash, upstream, logp, d_in, n, planar_sn, s);
+    case 3: return launch_loglik_d<3>(h, in, squash, upstream, logp, d_in, n, planar_sn, s);
+    case 4: return launch_loglik_d<4>(h, in, squash, upstream, logp, d_in, n, planar_sn, s);
+    case 5: return launch_loglik_d<5>(h, in, squash, upstream, logp, d_in, n, planar_sn, s);
+    case 6: return launch_loglik_d<6>(h, in, squash, upstream, logp, d_in, n, planar_sn, s);
+    case 7: return launch_loglik_d<7>(h, in, squash, upstream, logp, d_in, n, planar_sn, s);
+    case 8: return launch_loglik_d<8>(h, in, squash, upstream, logp, d_in, n, planar_sn, s);
     default: return cudaErrorInvalidValue;
   }
 }
