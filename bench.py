@@ -114,27 +114,68 @@ def problem_queries(cfg_id, cfg, ps, robot, args):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML is polled in-process every
+    5 ms (the default timed region is ~15 ms: `nvidia-smi -lms 50` would see it once); without the NVML binding the
+    nvidia-smi loop of the recipe is used."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.rows, self.proc, self.idx, self.nvml, self.smax, self.stop_flag = [], None, gpu_index, None, None, False
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.idx < len(ids) and ids[self.idx].isdigit():
+                return int(ids[self.idx])
+        return self.idx
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "50"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self._physical_index()), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.dev, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.dev))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev))
+                self.rows.append((time.perf_counter(), mhz, mask))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self, t0, t1):
+        if self.nvml is not None:
+            self.stop_flag = True
+            rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+            reasons = sorted(k for k, bit in self.BITS.items() if any(r[2] & bit for r in rows))
+            return {"sm_mhz": statistics.median([r[1] for r in rows]) if rows else None, "sm_max_mhz": self.smax,
+                    "reasons": reasons, "samples": len(rows), "source": "nvml, 5 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.06)
@@ -148,7 +189,7 @@ class ClockSampler:
                     reasons.add(name)
         smax = float(rows[0][2]) if rows and rows[0][2].replace(".", "").isdigit() else None
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(rows)}
+                "samples": len(rows), "source": "nvidia-smi -lms 50"}
 
 
 def measured_peaks():

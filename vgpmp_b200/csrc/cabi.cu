@@ -430,9 +430,8 @@ int vgpmp_elbo_fwd_bwd(vgpmp_handle* h, const vgpmp_dims* dims, const vgpmp_para
   // Inside the step the samples and their cotangents are latent-major, [Bp,D,S,N]: the GP kernels (one CTA per problem and
   // latent) and the likelihood (lanes = consecutive timesteps) then read and write contiguous runs.  A caller who asks for
   // the samples (aux->f) gets the reference's [Bp,S,N,D].
-  static const int planar_env = getenv("VGPMP_F_PLANAR") ? atoi(getenv("VGPMP_F_PLANAR")) : 1;   // experiment switch
-  const int planar = (aux && aux->f) ? 0 : planar_env;
-  double* f = planar ? g.f : aux->f;
+  const int planar = (aux && aux->f) ? 0 : 1;
+  double* f = (aux && aux->f) ? aux->f : g.f;
   double* logp = (aux && aux->logp) ? aux->logp : g.logp;
   const bool bwd = gr != nullptr;
   {

@@ -1743,22 +1743,26 @@ __global__ void __launch_bounds__(256, 2) gp_backward_samples_kernel(BackwardArg
   for (int s0 = s_begin; s0 < s_end; s0 += kBS) {
     const int ns = min(kBS, s_end - s0);
     __syncthreads();                                    // previous tile fully consumed
+    // (staging DF one tile ahead with cp.async changed nothing here: 2758 vs 2792 us at 1024 problems x 256 samples, and its
+    // second buffer costs the second CTA per SM once N > 64)
+#pragma unroll 2
     for (int idx = tid; idx < kBS * NP; idx += nt) {    // DF[s][n], zero padded; its share of the prior path rides along
       const int i = idx / NP, n = idx - i * NP;           // (d f0(X) = df: the f0 / h0 loads overlap with the df loads)
       double dv = 0.0;
       if (i < ns && n < N) {
-        dv = dfp[((size_t)(s0 + i) * N + n) * dfs];
+        dv = __ldg(dfp + ((size_t)(s0 + i) * N + n) * dfs);
         const size_t o = ((size_t)pl * S + s0 + i) * A + n;
-        acc_f0 += dv * a.f0[o];
-        acc_ls += dv * a.h0[o];
+        acc_f0 += dv * __ldg(a.f0 + o);
+        acc_ls += dv * __ldg(a.h0 + o);
       }
       DF[i * ldN + n] = dv;
     }
+#pragma unroll 2
     for (int idx = tid; idx < kBS * 32; idx += nt) {    // VT[m][s], ET[m][s]
       const int i = idx >> 5, m = idx & 31;
       const bool ok = i < ns && m < Mp;
-      VT[m * kLD + i] = ok ? a.v[((size_t)pl * S + s0 + i) * Mp + m] : 0.0;
-      ET[m * kLD + i] = ok ? a.eps_u[((size_t)pl * S + s0 + i) * Mp + m] : 0.0;
+      VT[m * kLD + i] = ok ? __ldg(a.v + ((size_t)pl * S + s0 + i) * Mp + m) : 0.0;
+      ET[m * kLD + i] = ok ? __ldg(a.eps_u + ((size_t)pl * S + s0 + i) * Mp + m) : 0.0;
     }
     __syncthreads();
     // GV = DF KT^T: 4 x 4 output tiles, 2 per warp
@@ -1813,8 +1817,8 @@ __global__ void __launch_bounds__(256, 2) gp_backward_samples_kernel(BackwardArg
       if (lane < Mp) {
         const double gg = -B1[i * kLD + lane];
         const size_t o = ((size_t)pl * S + s0 + i) * A + N + lane;
-        acc_f0 += gg * a.f0[o];
-        acc_ls += gg * a.h0[o];
+        acc_f0 += gg * __ldg(a.f0 + o);
+        acc_ls += gg * __ldg(a.h0 + o);
       }
   }
   acc_var += acc_f0 / (2.0 * s2);
@@ -1900,11 +1904,23 @@ __global__ void __launch_bounds__(256, 2) pathwise_update_mma_kernel(PathwiseArg
   for (int s0 = s_begin + warp * 8; s0 < s_end; s0 += nw * 8) {
     const int ns = min(8, s_end - s0);
     const size_t ps0 = (size_t)pl * S + s0;
+    // This tile's inputs are requested up front through the read-only path (nothing in this kernel writes them): one round
+    // trip for EPS, F0(Zy) and EPSJ instead of one per 8-column block behind the shared-memory stores.
+    double e8[8], fz[4][2], ej[4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e8[i] = (i < ns && lane < Mp) ? __ldg(a.eps_u + (ps0 + i) * Mp + lane) : 0.0;
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int e2 = 0; e2 < 2; ++e2) {
+        const int m = ni * 8 + 2 * t + e2;
+        const bool ok = g < ns && m < Mp;
+        fz[ni][e2] = ok ? __ldg(a.f0 + (ps0 + g) * A + Nq + m) : 0.0;
+        ej[ni][e2] = ok ? __ldg(a.eps_j + (ps0 + g) * Mp + m) : 0.0;
+      }
     // T0 <- EPS tile [8 samples][32]
-    for (int idx = lane; idx < 8 * 32; idx += 32) {
-      const int i = idx >> 5, m = idx & 31;
-      T0[i * kLD + m] = (i < ns && m < Mp) ? a.eps_u[(ps0 + i) * Mp + m] : 0.0;
-    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) T0[i * kLD + lane] = e8[i];
     __syncwarp();
     // R = mu + EPS S^T - F0(Zy) - sqrt(jitter) EPSJ  -> T1      (right operand element (k, n) = S[n][k]: Ss is n-major)
 #pragma unroll
@@ -1914,12 +1930,21 @@ __global__ void __launch_bounds__(256, 2) pathwise_update_mma_kernel(PathwiseArg
       const int m0 = ni * 8 + 2 * t;
       double r0 = 0.0, r1 = 0.0;
       if (g < ns) {
-        if (m0 < Mp) r0 = mu[m0] + c0 - a.f0[(ps0 + g) * A + Nq + m0] - sqrtj * a.eps_j[(ps0 + g) * Mp + m0];
-        if (m0 + 1 < Mp) r1 = mu[m0 + 1] + c1 - a.f0[(ps0 + g) * A + Nq + m0 + 1] - sqrtj * a.eps_j[(ps0 + g) * Mp + m0 + 1];
+        if (m0 < Mp) r0 = mu[m0] + c0 - fz[ni][0] - sqrtj * ej[ni][0];
+        if (m0 + 1 < Mp) r1 = mu[m0 + 1] + c1 - fz[ni][1] - sqrtj * ej[ni][1];
       }
       *reinterpret_cast<double2*>(T1 + g * kLD + m0) = make_double2(r0, r1);
     }
     __syncwarp();
+    // F0(X) of this tile: requested now, needed after the two triangular products
+    double fx[NTILES][2];
+#pragma unroll
+    for (int ni = 0; ni < NTILES; ++ni)
+#pragma unroll
+      for (int e2 = 0; e2 < 2; ++e2) {
+        const int n = ni * 8 + 2 * t + e2;
+        fx[ni][e2] = (g < ns && n < Nq) ? __ldg(a.f0 + (ps0 + g) * A + n) : 0.0;
+      }
     // Y = R Li^T -> T0
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) {
@@ -1948,8 +1973,8 @@ __global__ void __launch_bounds__(256, 2) pathwise_update_mma_kernel(PathwiseArg
       wmma_rn<8>(c0, c1, T1, kLD, KF + ni * 8 * kLD, kLD, g, t);
       const int n0 = ni * 8 + 2 * t;
       if (g < ns) {
-        if (n0 < Nq) a.f[f_index(a.f_planar, p, s0 + g, n0, l, S, Nq, D)] = c0 + a.f0[(ps0 + g) * A + n0];
-        if (n0 + 1 < Nq) a.f[f_index(a.f_planar, p, s0 + g, n0 + 1, l, S, Nq, D)] = c1 + a.f0[(ps0 + g) * A + n0 + 1];
+        if (n0 < Nq) a.f[f_index(a.f_planar, p, s0 + g, n0, l, S, Nq, D)] = c0 + fx[ni][0];
+        if (n0 + 1 < Nq) a.f[f_index(a.f_planar, p, s0 + g, n0 + 1, l, S, Nq, D)] = c1 + fx[ni][1];
       }
     }
     __syncwarp();
