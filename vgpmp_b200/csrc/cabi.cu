@@ -250,6 +250,7 @@ int vgpmp_set_option(vgpmp_handle* h, const char* name, int value) {
   if (std::strcmp(name, "step_graph") == 0) { h->allow_step_graph = value != 0; return VGPMP_OK; }
   if (std::strcmp(name, "rrm_min_ctas") == 0) { h->rrm_min_ctas = value; return VGPMP_OK; }
   if (std::strcmp(name, "tc_sampler") == 0) { h->allow_tc_path = value != 0; return VGPMP_OK; }
+  if (std::strcmp(name, "tc_min_samples") == 0) { h->tc_min_samples = value < 1 ? 1 : value; return VGPMP_OK; }
   return fail(h, VGPMP_ERR_INVALID, std::string("set_option: unknown option ") + name);
 }
 
@@ -657,7 +658,8 @@ int vgpmp_train_step_host_begin(vgpmp_handle* h, const vgpmp_dims* dims, vgpmp_a
                             (uint64_t)(uintptr_t)elbo_dev, (uint64_t)(uintptr_t)loss_host, (uint64_t)(uintptr_t)ws,
                             (uint64_t)ws_bytes, (uint64_t)(uintptr_t)s, (uint64_t)st->train_q_mu, (uint64_t)st->train_q_sqrt,
                             (uint64_t)st->train_lengthscales, (uint64_t)st->train_variances,
-                            (uint64_t)(h->allow_tc_path | (h->allow_rr_path << 1) | (h->allow_dmma_path << 2) | (h->allow_grid_path << 3)),
+                            (uint64_t)(h->allow_tc_path | (h->allow_rr_path << 1) | (h->allow_dmma_path << 2) | (h->allow_grid_path << 3)) |
+                                ((uint64_t)h->tc_min_samples << 8),
                             (uint64_t)(int64_t)h->rrm_min_ctas};
   for (uint64_t wv : words) sig = mix64(sig, wv);
   double dw[6] = {st->learning_rate, st->beta1, st->beta2, st->eps, st->variance_lower, 0.0};

@@ -69,6 +69,7 @@ struct vgpmp_handle {
   uint64_t prefetched_seed = 0;
   // stage profiling (bench.py): event pairs recorded on the launching stream
   bool allow_tc_path = true;    // tcgen05 / TMEM 3xTF32 sampler for large sample counts (sampler_tc.cu)
+  int tc_min_samples = 64;      // ... from this many samples per problem on (below: the float64 DMMA samplers)
   bool allow_dmma_path = true;  // shared-memory DMMA sampler (N + M + 2 <= 192), else the general kernel
   bool allow_rr_path = true;    // register-resident warp-specialised DMMA sampler (<= 12 point tiles), else the shared-memory one
   // CUDA-graph replay of vgpmp_train_step_host (one captured graph per argument signature)

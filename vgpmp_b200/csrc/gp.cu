@@ -2220,7 +2220,7 @@ enum SamplerKind { SAMPLER_GENERAL = 0, SAMPLER_DMMA, SAMPLER_RR, SAMPLER_TC };
 static SamplerKind pick_sampler(const vgpmp_handle* h, const PathwiseArgs& a) {
   const int A = a.Nq + a.M + 2;
   if (!h->allow_grid_path || a.Nq < 2 || a.M < 2) return SAMPLER_GENERAL;
-  if (h->allow_tc_path && pathwise_tc_supported(a)) return SAMPLER_TC;
+  if (h->allow_tc_path && a.S >= h->tc_min_samples && pathwise_tc_supported(a)) return SAMPLER_TC;
   if (h->allow_rr_path && (a.Nq + 2 + 7) / 8 + (a.M + 7) / 8 <= kRT) return SAMPLER_RR;
   if (h->allow_dmma_path && A <= 192) return SAMPLER_DMMA;
   return SAMPLER_GENERAL;

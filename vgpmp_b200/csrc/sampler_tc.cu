@@ -52,7 +52,8 @@ struct TcShape {
   int perx, perz;  // rows per segment
   int blocks;      // sample blocks per pair
   int items;       // pairs * blocks
-  int ablate;      // experiments only (VGPMP_TC_ABLATE): 1 no MMAs, 2 no weight draws, 4 no features, 8 no table math, 16 no fold
+  int ablate;      // experiments only (VGPMP_TC_ABLATE): 1 no MMAs, 2 no weight draws, 4 no features, 8 no table math, 16 no fold,
+                   // 32 MMA thread spins without nanosleep, 64 no proxy fence, 128 no fold hand-shake, 256 no write-out
 };
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes) {
@@ -275,14 +276,14 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
             Fhi[fcol + (AP + Nq + endpoint) * 4] = hi; Flo[fcol + (AP + Nq + endpoint) * 4] = lo;
           }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+        if (!(sh.ablate & 64)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
         __syncwarp();
         if (lane == 0) { mbar_arrive(tab_empty + tslot); mbar_arrive(full + slot); }
         // ---- fold the partial sum that finished one group ago (its MMAs were issued >= 2 stages back) ----
         const int gl = t / kGroup;
-        if ((t % kGroup == kGroup - 1 || t == T - 1) && gl >= 1 && folded < gl) fold_next();
+        if (!(sh.ablate & 128) && (t % kGroup == kGroup - 1 || t == T - 1) && gl >= 1 && folded < gl) fold_next();
       }
-      while (folded < G) fold_next();
+      while (!(sh.ablate & 128) && folded < G) fold_next();
       gg += G;
       // ---- write-out through shared memory: every MMA of this item has been folded, so the stages are idle.  The
       // transposes live in the weight areas only (rewritten in full by every stage; the zero padding rows of the feature
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
       __syncwarp();
       const int hf = cp * CW >= AP ? 1 : 0;                     // cos columns -> f0, sin columns -> h0
       double* dst = hf == 0 ? a.f0 : a.h0;
-      if (dst != nullptr) {
+      if (dst != nullptr && !(sh.ablate & 256)) {
         for (int xl = lane; xl < CW; xl += 32) {
           const int x = cp * CW + xl - hf * AP;                 // point index
           if (x >= A) continue;
@@ -396,13 +397,14 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NROW >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
       constexpr uint32_t lbo_w = kWChunk * 4, lbo_f = FChunk * 4;
-      auto wait_sleepy = [](uint64_t* b, uint32_t parity) {     // one thread polling: leave the issue slots to the workers
+      const int ab = sh.ablate;
+      auto wait_sleepy = [ab](uint64_t* b, uint32_t parity) {     // one thread polling: leave the issue slots to the workers
         uint32_t ok;
         for (;;) {
           asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                        : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
           if (ok) break;
-          __nanosleep(40);
+          if (!(ab & 32)) __nanosleep(40);
         }
       };
       for (int item = blockIdx.x; item < sh.items; item += gridDim.x) {
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
           const int gl = t / kGroup;
           const int gi = gg + gl;
           const bool first = t % kGroup == 0;
-          if (first) wait_sleepy(grp_empty + (gi & 1), ((gi >> 1) & 1) ^ 1);   // the partial two groups back has been folded
+          if (first && !(ab & 128)) wait_sleepy(grp_empty + (gi & 1), ((gi >> 1) & 1) ^ 1);   // the partial two groups back has been folded
           wait_sleepy(full + slot, use & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t base = smem_u32(stage0 + (size_t)slot * kStage);
@@ -428,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
             umma_tf32(dcol, dwh, dfh, idesc, 1u);
           }
           umma_commit(empty + slot);
-          if (t % kGroup == kGroup - 1 || t == T - 1) umma_commit(grp_full + (gi & 1));
+          if (!(ab & 128) && (t % kGroup == kGroup - 1 || t == T - 1)) umma_commit(grp_full + (gi & 1));
         }
         gg += G;
       }
@@ -462,7 +464,7 @@ cudaError_t launch_nc(vgpmp_handle* h, const PathwiseArgs& a, const TcShape& sh,
 
 bool pathwise_tc_supported(const PathwiseArgs& a) {
   const int A = a.Nq + a.M + 2;
-  return a.S >= 64 && A <= 112 && a.Nq >= 2 && a.M >= 2 && a.B >= 64;
+  return a.S >= 1 && A <= 112 && a.Nq >= 2 && a.M >= 2 && a.B >= 64;   // the sample-count threshold is the caller's (tc_min_samples)
 }
 
 cudaError_t launch_pathwise_tc(vgpmp_handle* h, const PathwiseArgs& a, int pairs, const double* meta, cudaStream_t s) {
