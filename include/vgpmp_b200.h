@@ -290,6 +290,8 @@ double vgpmp_probe_fp64_tflops(int device);
  *   "tc_sampler"      num_samples >= 64 and N + M + 2 <= 112: the Fourier contraction runs on the 5th-generation tensor cores
  *                     (tcgen05.mma kind::tf32 as a 3-pass hi/lo split, FP32 partial sums in TMEM folded every 64 bases);
  *                     float32-class accuracy, gated by the tolerance tests (ELBO 1e-4, gradients 1e-3).  0 = float64 DMMA.
+ *   "tc_min_samples"  the sample count from which "tc_sampler" applies (default 64; measured cross-over with the float64
+ *                     DMMA samplers is between 20 and 32 samples, profiles/r2_tc_sampler_ablations.txt).
  *   "rr_sampler"      register-resident warp-specialised DMMA sampler (points must fit 12 tiles of 8 rows, e.g. N=70, M=24);
  *                     0 = the variant that passes the features through shared memory.
  *   "step_graph"      vgpmp_train_step_host[_begin] captures the step's launches into a CUDA graph once per argument signature
