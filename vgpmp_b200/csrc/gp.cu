@@ -1190,6 +1190,20 @@ __global__ void __launch_bounds__(128, 7) gp_prepare_update_kernel(PathwiseArgs 
   const int pl = blockIdx.x / a.nchunk, chunk = blockIdx.x % a.nchunk, p = pl / D, l = pl % D;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
   const bool first = chunk == 0;                      // chunk 0 publishes the factors for the reverse pass
+  {
+    // the update's inputs are requested from DRAM before the Cholesky (which needs none of them) instead of after it
+    const int sb = chunk * a.chunk, se = min(S, sb + a.chunk);
+    auto l2_prefetch = [&](const double* base, size_t count) {
+      const char* b0 = reinterpret_cast<const char*>(base);
+      for (size_t off = (size_t)tid * 128; off < count * sizeof(double); off += (size_t)nt * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + off));
+    };
+    if (se > sb) {
+      l2_prefetch(a.eps_u + ((size_t)pl * S + sb) * Mp, (size_t)(se - sb) * Mp);
+      l2_prefetch(a.eps_j + ((size_t)pl * S + sb) * Mp, (size_t)(se - sb) * Mp);
+      l2_prefetch(a.f0 + ((size_t)pl * S + sb) * A, (size_t)(se - sb) * A);
+    }
+  }
   gp_prepare_body(D, M, a.jitter, P, pl, first ? Lc_out : nullptr, first ? S_out : nullptr, first ? kl_l : nullptr,
                   first ? kvec : nullptr, first ? Linv_out : nullptr, prep, prep);
   if (meta[0] == 0.0) return;                         // general sampler runs after this kernel and does its own update
@@ -1385,6 +1399,23 @@ __global__ void __launch_bounds__(256, 4) gp_backward_kernel(BackwardArgs a) {
   double* red = gd + 32;               // [8]
   double* dft = red + 8;               // [kBT][N]  this tile's slice of d ELBO / d f
 
+  if (MODE == 0) {
+    // Everything this CTA will read is requested from DRAM now (the phases below meet their inputs one dependent round trip
+    // at a time otherwise: a third of the stall samples of this latency-bound kernel were first-touch loads).
+    auto l2_prefetch = [&](const double* base, size_t count) {
+      const char* b0 = reinterpret_cast<const char*>(base);
+      for (size_t off = (size_t)tid * 128; off < count * sizeof(double); off += (size_t)nt * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + off));
+    };
+    l2_prefetch(a.Linv + (size_t)pl * Mp * Mp, (size_t)Mp * Mp);
+    l2_prefetch(a.Lc + (size_t)pl * Mp * Mp, (size_t)Mp * Mp);
+    l2_prefetch(a.q_sqrt + (size_t)pl * M * M, (size_t)M * M);
+    l2_prefetch(a.v + (size_t)pl * S * Mp, (size_t)S * Mp);
+    l2_prefetch(a.eps_u + (size_t)pl * S * Mp, (size_t)S * Mp);
+    l2_prefetch(a.f0 + (size_t)pl * S * A, (size_t)S * A);
+    l2_prefetch(a.h0 + (size_t)pl * S * A, (size_t)S * A);
+    if (a.df_planar) l2_prefetch(a.df + ((size_t)p * D + l) * S * N, (size_t)S * N);
+  }
   const double ell = a.ls[pl], s2 = a.var[pl], inv_ell = 1.0 / ell;
   if (tid < 32) {
     zy[tid] = tid < Mp ? zy_at(a.Z, D, l, tid) : 0.0;
