@@ -1190,20 +1190,6 @@ __global__ void __launch_bounds__(128, 7) gp_prepare_update_kernel(PathwiseArgs 
   const int pl = blockIdx.x / a.nchunk, chunk = blockIdx.x % a.nchunk, p = pl / D, l = pl % D;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
   const bool first = chunk == 0;                      // chunk 0 publishes the factors for the reverse pass
-  {
-    // the update's inputs are requested from DRAM before the Cholesky (which needs none of them) instead of after it
-    const int sb = chunk * a.chunk, se = min(S, sb + a.chunk);
-    auto l2_prefetch = [&](const double* base, size_t count) {
-      const char* b0 = reinterpret_cast<const char*>(base);
-      for (size_t off = (size_t)tid * 128; off < count * sizeof(double); off += (size_t)nt * 128)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + off));
-    };
-    if (se > sb) {
-      l2_prefetch(a.eps_u + ((size_t)pl * S + sb) * Mp, (size_t)(se - sb) * Mp);
-      l2_prefetch(a.eps_j + ((size_t)pl * S + sb) * Mp, (size_t)(se - sb) * Mp);
-      l2_prefetch(a.f0 + ((size_t)pl * S + sb) * A, (size_t)(se - sb) * A);
-    }
-  }
   gp_prepare_body(D, M, a.jitter, P, pl, first ? Lc_out : nullptr, first ? S_out : nullptr, first ? kl_l : nullptr,
                   first ? kvec : nullptr, first ? Linv_out : nullptr, prep, prep);
   if (meta[0] == 0.0) return;                         // general sampler runs after this kernel and does its own update
