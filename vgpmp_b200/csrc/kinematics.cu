@@ -272,10 +272,6 @@ __device__ __forceinline__ double stable_sigmoid(double x) {
   return (x >= 0.0 ? 1.0 : e) * r;
 }
 
-// Fused likelihood: squash -> FK -> spheres -> SDF stencil -> hinge -> logp, plus the reverse pass to the input.
-// Spheres of a frame are handled NB at a time: all NB record loads (one 256-bit load per sphere) are issued before the first
-// one is consumed.  The joint axes needed by the reverse pass (7 doubles per
-// joint) are parked in shared memory, [value][thread] so that a warp's accesses are contiguous.
 // Where the D joint inputs of configuration c live: [n,D] (planar_sn = 0), or latent-major per problem,
 // [n / planar_sn][D][planar_sn] (the fused step's layout: a warp's lanes then read consecutive doubles).
 struct JointLayout {
@@ -298,23 +294,20 @@ struct SphereBatch {
   double4 r[NB];  // {value, gx, gy, gz}
 };
 
-template <int D, bool BWD, int NB>
+// Forward-only likelihood (prediction, best-sample selection, clearance-style queries): squash -> FK -> spheres -> SDF value
+// -> hinge -> logp.  Spheres of a frame are handled NB at a time: all NB value loads are issued before the first is consumed.
+template <int D, int NB>
 __global__ void __launch_bounds__(kThreads, 3) loglik_kernel(RobotDev rb, SdfDev sdf, LikDev lk,
-                                                         const double* __restrict__ in, int squash, double upstream,
-                                                         double* __restrict__ logp, double* __restrict__ d_in,
-                                                         int64_t n, int64_t planar_sn) {
-  extern __shared__ double axes[];  // BWD only: [D][8][kThreads]  (axis z, axis x point n, prefix term, d theta/d in)
-  const int tid = threadIdx.x;
-  const int64_t c = (int64_t)blockIdx.x * kThreads + tid;
+                                                         const double* __restrict__ in, int squash,
+                                                         double* __restrict__ logp, int64_t n, int64_t planar_sn) {
+  const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (c >= n) return;
   const JointLayout jl = joint_layout(c, D, planar_sn);   // joint k of this configuration: in[jl.base + k * jl.stride]
 
   Frame A;
   frame_from_base(rb, A);
-  double Fw[3] = {0.0, 0.0, 0.0}, Tw[3] = {0.0, 0.0, 0.0};  // running wrench of the spheres seen so far
   double lp = 0.0;
   const double inv_sigma = 1.0 / lk.sigma_obs;
-  int p = 0;
   double xnext = in[jl.base];   // joint inputs are fetched one joint ahead of their use
 
 #pragma unroll 1
@@ -324,82 +317,38 @@ __global__ void __launch_bounds__(kThreads, 3) loglik_kernel(RobotDev rb, SdfDev
       const double xin = xnext;
       if (k < D) xnext = in[jl.base + k * jl.stride];
       lp += xin - xin;     // 0 for a finite input; NaN / Inf inputs must not vanish in the voxel clip and the hinge's fmax
-      double thj = xin, dsq = 1.0;
-      if (squash) {
-        const double sg = stable_sigmoid(xin), span = rb.hi[j] - rb.lo[j];
-        thj = rb.lo[j] + span * sg;
-        dsq = span * sg * (1.0 - sg);
-      }
-      double zx, zy, zz, ox, oy, oz;
-      if (BWD && !rb.craig) {  // Spong: joint j turns about z of frame j-1, through its origin
-        zx = A.r[2]; zy = A.r[5]; zz = A.r[8]; ox = A.t[0]; oy = A.t[1]; oz = A.t[2];
-      }
+      double thj = xin;
+      if (squash) thj = rb.lo[j] + (rb.hi[j] - rb.lo[j]) * stable_sigmoid(xin);
       frame_step(rb, j, thj, A);
-      if (BWD) {
-        if (rb.craig) {        // Craig: joint j turns about z of frame j (its own frame), through its origin
-          zx = A.r[2]; zy = A.r[5]; zz = A.r[8]; ox = A.t[0]; oy = A.t[1]; oz = A.t[2];
-        }
-        const double nx = zy * oz - zz * oy, ny = zz * ox - zx * oz, nz = zx * oy - zy * ox;
-        double* slot = axes + (size_t)j * 8 * kThreads + tid;
-        slot[7 * kThreads] = dsq;
-        slot[0] = zx; slot[kThreads] = zy; slot[2 * kThreads] = zz;
-        slot[3 * kThreads] = nx; slot[4 * kThreads] = ny; slot[5 * kThreads] = nz;
-        slot[6 * kThreads] = zx * Tw[0] + zy * Tw[1] + zz * Tw[2] - (nx * Fw[0] + ny * Fw[1] + nz * Fw[2]);
-      }
     }
     const int pend = rb.frame_end[k];
-    for (p = (k == 0 ? 0 : rb.frame_end[k - 1]); p < pend; p += NB) {
-      SphereBatch<NB> sb;
-      // stage 1: positions, voxel indices, all loads
+    for (int p = (k == 0 ? 0 : rb.frame_end[k - 1]); p < pend; p += NB) {
+      double val[NB];
 #pragma unroll
       for (int i = 0; i < NB; ++i) {
-        const int q = min(p + i, pend - 1);  // tail lanes of the batch repeat the last sphere (weight 0 below)
+        const int q = min(p + i, pend - 1);  // tail lanes of the batch repeat the last sphere (not counted below)
         const double ox = rb.sphere_off[q][0], oy = rb.sphere_off[q][1], oz = rb.sphere_off[q][2];
-        sb.x[i] = A.r[0] * ox + A.r[1] * oy + A.r[2] * oz + A.t[0];
-        sb.y[i] = A.r[3] * ox + A.r[4] * oy + A.r[5] * oz + A.t[1];
-        sb.z[i] = A.r[6] * ox + A.r[7] * oy + A.r[8] * oz + A.t[2];
-        const Voxel v = sdf_voxel(sdf, sb.x[i] - lk.offset[0], sb.y[i] - lk.offset[1], sb.z[i] - lk.offset[2]);
-        if (BWD) sb.r[i] = sdf_record(sdf, v);
-        else sb.r[i].x = sdf_value(sdf, v);
+        const double x = A.r[0] * ox + A.r[1] * oy + A.r[2] * oz + A.t[0];
+        const double y = A.r[3] * ox + A.r[4] * oy + A.r[5] * oz + A.t[1];
+        const double z = A.r[6] * ox + A.r[7] * oy + A.r[8] * oz + A.t[2];
+        val[i] = sdf_value(sdf, sdf_voxel(sdf, x - lk.offset[0], y - lk.offset[1], z - lk.offset[2]));
       }
-      // stage 2: hinge, log-probability, wrench
 #pragma unroll
       for (int i = 0; i < NB; ++i) {
         if (p + i < pend) {
-          const double dist = sb.r[i].x - rb.sphere_rad[p + i];
-          const double hinge = fmax(lk.epsilon - dist, 0.0);
+          const double hinge = fmax(lk.epsilon - (val[i] - rb.sphere_rad[p + i]), 0.0);
           lp -= 0.5 * (hinge * inv_sigma) * hinge;
-          if (BWD && hinge > 0.0) {
-            // d logp / d dist = hinge / sigma; the custom gradient defines d dist / d x := stencil gradient
-            double gx = sb.r[i].y, gy = sb.r[i].z, gz = sb.r[i].w;
-            const double w = hinge * inv_sigma;
-            gx *= w; gy *= w; gz *= w;
-            Fw[0] += gx; Fw[1] += gy; Fw[2] += gz;
-            Tw[0] += sb.y[i] * gz - sb.z[i] * gy;
-            Tw[1] += sb.z[i] * gx - sb.x[i] * gz;
-            Tw[2] += sb.x[i] * gy - sb.y[i] * gx;
-          }
         }
       }
     }
   }
   logp[c] = lp;
-  if (BWD) {
-#pragma unroll
-    for (int j = 0; j < D; ++j) {
-      const double* slot = axes + (size_t)j * 8 * kThreads + tid;
-      const double dth = slot[0] * Tw[0] + slot[kThreads] * Tw[1] + slot[2 * kThreads] * Tw[2] -
-                         (slot[3 * kThreads] * Fw[0] + slot[4 * kThreads] * Fw[1] + slot[5 * kThreads] * Fw[2]) -
-                         slot[6 * kThreads];
-      d_in[jl.base + j * jl.stride] = upstream * dth * slot[7 * kThreads];
-    }
-  }
 }
 
-// Fused likelihood WITH its reverse pass, two sweeps over the kinematic chain.  (The one-sweep form above parks 8 doubles per
+// Fused likelihood WITH its reverse pass, two sweeps over the kinematic chain.  (A one-sweep form has to park 8 doubles per
 // joint and thread in shared memory for the final joint-gradient formula: 56 KB per CTA, i.e. 3 CTAs per SM and, with the
 // carve-out that takes, little L1 left for the record loads - which matters once the grid lives in HBM.)
-//   sweep 1  joints + spheres in chain order, as above: log-probability, total wrench (F, T), and per joint the prefix term
+//   sweep 1  joints + spheres in chain order: log-probability, total wrench (F, T), and per joint the prefix term
 //            p_j = z_j . T_{<j} - (z_j x o_j) . F_{<j} in REGISTERS (the joint loop is unrolled); sin / cos of the joint angle
 //            and the squash derivative go to shared memory (3 doubles per joint: 21 KB per CTA at D = 7);
 //   sweep 2  the chain again from the stored sin / cos (frame products only, no transcendental, no sphere):
@@ -558,8 +507,7 @@ cudaError_t launch_loglik_d(vgpmp_handle* h, const double* in, int squash, doubl
     if (e != cudaSuccess) return e;
     kern<<<blocks, kThreads, smem, s>>>(h->robot, h->sdf, h->lik, in, squash, upstream, logp, d_in, n, planar_sn);
   } else {
-    loglik_kernel<D, false, kSphereBatch><<<blocks, kThreads, 0, s>>>(h->robot, h->sdf, h->lik, in, squash, upstream,
-                                                                     logp, d_in, n, planar_sn);
+    loglik_kernel<D, kSphereBatch><<<blocks, kThreads, 0, s>>>(h->robot, h->sdf, h->lik, in, squash, logp, n, planar_sn);
   }
   return cudaGetLastError();
 }
