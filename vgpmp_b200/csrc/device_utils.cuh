@@ -73,6 +73,13 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint64_t iter, uint32_t s
 
 
 
+// L2 prefetch of `count` doubles starting at `base`, one 128-byte line per participating thread and round
+__device__ __forceinline__ void l2_prefetch_span(const double* base, size_t count, int tid, int nthreads) {
+  const char* b0 = reinterpret_cast<const char*>(base);
+  for (size_t off = (size_t)tid * 128; off < count * sizeof(double); off += (size_t)nthreads * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + off));
+}
+
 // shared-memory mbarrier helpers (producer/consumer hand-over without coupling the consumers to each other)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {

@@ -1388,11 +1388,7 @@ __global__ void __launch_bounds__(256, 4) gp_backward_kernel(BackwardArgs a) {
   if (MODE == 0) {
     // Everything this CTA will read is requested from DRAM now (the phases below meet their inputs one dependent round trip
     // at a time otherwise: a third of the stall samples of this latency-bound kernel were first-touch loads).
-    auto l2_prefetch = [&](const double* base, size_t count) {
-      const char* b0 = reinterpret_cast<const char*>(base);
-      for (size_t off = (size_t)tid * 128; off < count * sizeof(double); off += (size_t)nt * 128)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + off));
-    };
+    auto l2_prefetch = [&](const double* base, size_t count) { l2_prefetch_span(base, count, tid, nt); };
     l2_prefetch(a.Linv + (size_t)pl * Mp * Mp, (size_t)Mp * Mp);
     l2_prefetch(a.Lc + (size_t)pl * Mp * Mp, (size_t)Mp * Mp);
     l2_prefetch(a.q_sqrt + (size_t)pl * M * M, (size_t)M * M);
@@ -1732,6 +1728,17 @@ __global__ void __launch_bounds__(256, 2) gp_backward_samples_kernel(BackwardArg
   double* gmu = B2 + 32 * kLD;           // [32]
   double* zy = gmu + 32;                 // [32]
   double* red = zy + 32;                 // [8]
+  {                                                   // first tile's inputs: DRAM -> L2 while the operands are set up
+    const int n1 = min(kBS, s_end - s_begin);
+    const size_t ps1 = (size_t)pl * S + s_begin;
+    if (n1 > 0) {
+      if (a.df_planar) l2_prefetch_span(a.df + ((size_t)p * D + l) * S * N + (size_t)s_begin * N, (size_t)n1 * N, tid, nt);
+      l2_prefetch_span(a.f0 + ps1 * A, (size_t)n1 * A, tid, nt);
+      l2_prefetch_span(a.h0 + ps1 * A, (size_t)n1 * A, tid, nt);
+      l2_prefetch_span(a.v + ps1 * Mp, (size_t)n1 * Mp, tid, nt);
+      l2_prefetch_span(a.eps_u + ps1 * Mp, (size_t)n1 * Mp, tid, nt);
+    }
+  }
   const double ell = a.ls[pl], s2 = a.var[pl], inv_ell = 1.0 / ell;
   for (int idx = tid; idx < 2 * 32 * kLD + 32 * ldN; idx += nt) sm[idx] = 0.0;     // Li, LiT, KT (padding must be zero)
   if (tid < 32) { zy[tid] = tid < Mp ? zy_at(a.Z, D, l, tid) : 0.0; gmu[tid] = 0.0; }
@@ -1760,6 +1767,15 @@ __global__ void __launch_bounds__(256, 2) gp_backward_samples_kernel(BackwardArg
   for (int s0 = s_begin; s0 < s_end; s0 += kBS) {
     const int ns = min(kBS, s_end - s0);
     __syncthreads();                                    // previous tile fully consumed
+    if (s0 + kBS < s_end) {                             // next tile's inputs: DRAM -> L2 while this tile computes
+      const int s1 = s0 + kBS, n1 = min(kBS, s_end - s1);
+      const size_t ps1 = (size_t)pl * S + s1;
+      if (a.df_planar) l2_prefetch_span(dfp + (size_t)s1 * N, (size_t)n1 * N, tid, nt);
+      l2_prefetch_span(a.f0 + ps1 * A, (size_t)n1 * A, tid, nt);
+      l2_prefetch_span(a.h0 + ps1 * A, (size_t)n1 * A, tid, nt);
+      l2_prefetch_span(a.v + ps1 * Mp, (size_t)n1 * Mp, tid, nt);
+      l2_prefetch_span(a.eps_u + ps1 * Mp, (size_t)n1 * Mp, tid, nt);
+    }
     // (staging DF one tile ahead with cp.async changed nothing here: 2758 vs 2792 us at 1024 problems x 256 samples, and its
     // second buffer costs the second CTA per SM once N > 64)
 #pragma unroll 2
@@ -1890,6 +1906,15 @@ __global__ void __launch_bounds__(256, 2) pathwise_update_mma_kernel(PathwiseArg
   const int s_begin = (blockIdx.x % nchunk) * chunk, s_end = min(S, s_begin + chunk);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
   const int g = lane >> 2, t = lane & 3;
+  {                                                   // the chunk's first tiles: DRAM -> L2 while the operands are set up
+    const int n1 = min(nw * 8, s_end - s_begin);
+    const size_t ps1 = (size_t)pl * S + s_begin;
+    if (n1 > 0) {
+      l2_prefetch_span(a.eps_u + ps1 * Mp, (size_t)n1 * Mp, tid, nt);
+      l2_prefetch_span(a.eps_j + ps1 * Mp, (size_t)n1 * Mp, tid, nt);
+      l2_prefetch_span(a.f0 + ps1 * A, (size_t)n1 * A, tid, nt);
+    }
+  }
   double* Ss = sm;                                    // [32][kLD]  q_sqrt_full, n-major for U = EPS S^T
   double* Li = Ss + 32 * kLD;                         // [32][kLD]  L^-1
   double* LiT = Li + 32 * kLD;                        // [32][kLD]
@@ -1921,6 +1946,13 @@ __global__ void __launch_bounds__(256, 2) pathwise_update_mma_kernel(PathwiseArg
   for (int s0 = s_begin + warp * 8; s0 < s_end; s0 += nw * 8) {
     const int ns = min(8, s_end - s0);
     const size_t ps0 = (size_t)pl * S + s0;
+    if (s0 + nw * 8 < s_end) {                          // this warp's next tile: DRAM -> L2 while this one computes
+      const int s1 = s0 + nw * 8, n1 = min(8, s_end - s1);
+      const size_t ps1 = (size_t)pl * S + s1;
+      l2_prefetch_span(a.eps_u + ps1 * Mp, (size_t)n1 * Mp, lane, 32);
+      l2_prefetch_span(a.eps_j + ps1 * Mp, (size_t)n1 * Mp, lane, 32);
+      l2_prefetch_span(a.f0 + ps1 * A, (size_t)n1 * A, lane, 32);
+    }
     // This tile's inputs are requested up front through the read-only path (nothing in this kernel writes them): one round
     // trip for EPS, F0(Zy) and EPSJ instead of one per 8-column block behind the shared-memory stores.
     double e8[8], fz[4][2], ej[4][2];
