@@ -781,8 +781,8 @@ def test_device_rng_key_layout_is_pinned():
 
 
 def test_host_step_guards():
-    """the host-buffer step must refuse a sample-sharded model (it has no all-reduce), refuse a second
-    begin while a step is in flight, return losses that do not alias the pinned buffer, and its wait must be idempotent."""
+    """the host-buffer step must not silently skip the all-reduce of a sample-sharded model, must refuse a
+    second begin while a step is in flight, return losses that do not alias the pinned buffer, and its wait is idempotent."""
     case = H.make_case(num_problems=2, S=6, N=16, M=6, B=64, seed=12)
     Xh = torch.from_numpy(case["X"].copy()).pin_memory()
     model = H.make_model(case, seed=3)
@@ -795,10 +795,17 @@ def test_host_step_guards():
     a = model.train_step_host_wait()
     b = model.train_step_host_wait()                                            # idempotent (the loss was negated on the device)
     assert torch.equal(a, b)
-    sharded = H.make_model(case, seed=3)
-    sharded.enable_sample_sharding(0, 2)
-    with pytest.raises(NotImplementedError):
-        sharded.train_step_host(Xh)
+    # a sample-sharded model steps through train_step (which owns the all-reduce) with the host copies around it: the
+    # host-buffer step and the device step of two identical shards must agree bit for bit
+    dev, host = H.make_model(case, seed=3), H.make_model(case, seed=3)
+    for m in (dev, host):
+        m.enable_sample_sharding(1, 2)
+    for _ in range(2):
+        ld = dev.train_step(case["X"])
+        lh = host.train_step_host(Xh)
+        assert torch.equal(ld.cpu().reshape(-1), lh.reshape(-1))
+    assert torch.equal(dev._q_mu, host._q_mu) and torch.equal(dev._q_sqrt, host._q_sqrt)
+    assert torch.equal(host.train_step_host_wait(), lh)                         # idempotent here too
 
 
 @pytest.mark.parametrize("S", [7, 96])

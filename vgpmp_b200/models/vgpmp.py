@@ -381,6 +381,8 @@ class VGPMP:
 
         The steady state is ONE ctypes call: the argument block is cached per (host buffer, stream, optimiser settings)."""
         hs = getattr(self, "_host_state", None)
+        if self._shard is not None or (hs is not None and hs.get("generic_numel") == X_host.numel()):
+            return self._train_step_host_generic(X_host, wait, stream, loss_out)
         o, t = self.optimizer, self.trainable
         sid = stream if stream is not None else torch.cuda.current_stream(self._eng.device).cuda_stream
         key = (X_host.data_ptr(), X_host.numel(), sid, self.seed, self.problem_offset, o.learning_rate, o.beta_1, o.beta_2,
@@ -389,6 +391,8 @@ class VGPMP:
         call = hs["call"] if hs is not None else None
         if call is None or call["key"] != key:
             call = self._host_call(X_host, sid, loss_out, key)
+            if call is None:
+                return self._train_step_host_generic(X_host, wait, stream, loss_out)
         if hs is None:
             hs = self._host_state
         if hs["pending"]:
@@ -409,14 +413,17 @@ class VGPMP:
         """Slow path of `train_step_host`: checks the host tensor, (re)allocates the per-shape device state and builds the
         argument block of the C call."""
         eng, D = self._eng, self.num_latent_gps
-        if self._shard is not None:
-            raise NotImplementedError("train_step_host does not all-reduce: a sample-sharded model steps with train_step")
         if X_host.device.type != "cpu" or X_host.dtype != torch.float64 or not X_host.is_contiguous():
             raise TypeError("train_step_host expects a contiguous float64 CPU tensor (pinned for async copies)")
         N = X_host.numel() // D
         dims = self._dims(N)
         if len(self._plan(eng.dev(X_host.reshape(N, D)), False)[0]) != 1:
-            raise NotImplementedError("train_step_host serves batches that fit one workspace chunk; use train_step")
+            # more than one workspace chunk: the single C call (and its CUDA graph) covers one chunk, so this batch steps
+            # through train_step with the host copies around it
+            hs = getattr(self, "_host_state", None) or dict(N=-1, pending=False, call=None)
+            hs["generic_numel"] = X_host.numel()
+            self._host_state = hs
+            return None
         hs = getattr(self, "_host_state", None)
         if hs is None or hs["N"] != N:
             Xc = X_host.reshape(N, D)
@@ -453,10 +460,45 @@ class VGPMP:
         hs["call"] = call
         return call
 
+    def _train_step_host_generic(self, X_host, wait, stream, loss_out):
+        """Host-buffer step for models the one-call path does not cover (sample-sharded: the all-reduce sits between the
+        reverse pass and Adam; batches of several workspace chunks): pinned X -> device, `train_step`, loss -> pinned host."""
+        eng, D = self._eng, self.num_latent_gps
+        if X_host.device.type != "cpu" or X_host.dtype != torch.float64 or not X_host.is_contiguous():
+            raise TypeError("train_step_host expects a contiguous float64 CPU tensor (pinned for async copies)")
+        if stream is not None and stream != torch.cuda.current_stream(eng.device).cuda_stream:
+            raise NotImplementedError("the generic host step runs on torch's current stream")
+        N = X_host.numel() // D
+        hs = getattr(self, "_host_state", None) or dict(N=-1, pending=False, call=None)
+        self._host_state = hs
+        gs = hs.get("generic")
+        if gs is None or gs["N"] != N:
+            gs = dict(N=N, X_dev=eng.empty(N, D), loss=torch.empty(self.num_problems, dtype=torch.float64).pin_memory())
+            hs["generic"] = gs
+        if hs["pending"]:
+            raise RuntimeError("train_step_host(wait=False) was called twice without train_step_host_wait(): the pinned "
+                               "loss buffer of the step in flight would be overwritten")
+        gs["X_dev"].copy_(X_host.reshape(N, D), non_blocking=True)
+        loss = self.train_step(gs["X_dev"])
+        out = gs["loss"] if loss_out is None else loss_out
+        out.copy_(loss.reshape(-1), non_blocking=True)
+        hs["pending"], hs["generic_out"] = True, out
+        if not wait:
+            return None
+        return self.train_step_host_wait()
+
     def train_step_host_wait(self, copy: bool = True):
         """Second half of `train_step_host(..., wait=False)`: blocks until the loss of the step in flight is in host
         memory and returns a copy of it (the pinned buffer is re-used by the next step; `copy=False` returns the buffer)."""
         hs = self._host_state
+        if hs.get("generic_out") is not None:
+            torch.cuda.current_stream(self._eng.device).synchronize()
+            hs["pending"] = False
+            out, hs["generic_out"] = hs["generic_out"], None
+            hs["generic_last"] = out
+            return out.clone() if copy else out
+        if hs["call"] is None and hs.get("generic_last") is not None:      # a second wait after a generic step: idempotent
+            return hs["generic_last"].clone() if copy else hs["generic_last"]
         call = hs["call"]
         rc = call["end"](*call["end_args"])
         if rc:
