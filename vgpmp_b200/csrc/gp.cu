@@ -1527,17 +1527,19 @@ __global__ void __launch_bounds__(256, 4) gp_backward_kernel(BackwardArgs a) {
   if (MODE == 2) {  // fold the partial sums of all chunks, chunk 0 first
     for (int idx = tid; idx < 32 * 32; idx += nt) {
       double g = 0.0, gs = 0.0;
-      for (int c = 0; c < a.nchunk; ++c) {
+#pragma unroll 8
+      for (int c = 0; c < a.nchunk; ++c) {        // read-only loads, several chunks in flight; the sums stay in chunk order
         const double* part = a.partial + ((size_t)pl * a.nchunk + c) * kPartial;
-        g += part[idx];
-        gs += part[1024 + idx];
+        g += __ldg(part + idx);
+        gs += __ldg(part + 1024 + idx);
       }
       G[(idx >> 5) * LDM + (idx & 31)] = g;
       GS[(idx >> 5) * LDM + (idx & 31)] = gs;
     }
     if (tid < 32) {
       double t = 0.0;
-      for (int c = 0; c < a.nchunk; ++c) t += a.partial[((size_t)pl * a.nchunk + c) * kPartial + 2048 + tid];
+#pragma unroll 8
+      for (int c = 0; c < a.nchunk; ++c) t += __ldg(a.partial + ((size_t)pl * a.nchunk + c) * kPartial + 2048 + tid);
       gmu[tid] = t;
     }
     if (tid == 0)
@@ -2084,10 +2086,14 @@ __global__ void __launch_bounds__(256) elbo_reduce_kernel(int D, int SN, double 
 __global__ void elbo_finish_kernel(int D, int Bp, double scale, double klw, const double* __restrict__ partial, int nseg,
                                    const double* __restrict__ kl_l, double* __restrict__ elbo, double* __restrict__ kl_out,
                                    double* __restrict__ loss_out) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per problem: lane-strided sums of the segment partials, then a fixed shuffle tree (deterministic)
+  const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (p >= Bp) return;
   double lik = 0.0, kl = 0.0;
-  for (int i = 0; i < nseg; ++i) lik += partial[(size_t)p * nseg + i];
+  for (int i = lane; i < nseg; i += 32) lik += partial[(size_t)p * nseg + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lik += __shfl_xor_sync(kFull, lik, o);
+  if (lane != 0) return;
   for (int l = 0; l < D; ++l) kl += kl_l[(size_t)p * D + l];
   const double e = scale * lik - klw * kl;
   elbo[p] = e;
@@ -2565,7 +2571,7 @@ cudaError_t launch_elbo_reduce(vgpmp_handle* h, const vgpmp_dims& d, const doubl
   elbo_reduce_kernel<<<d.num_problems * nseg, 256, 0, s>>>(D, SN, scale, klw, logp, kl_l, elbo, kl_out, loss_out, nseg, partial);
   h->launches++;
   if (nseg > 1) {
-    elbo_finish_kernel<<<(d.num_problems + 127) / 128, 128, 0, s>>>(D, d.num_problems, scale, klw, partial, nseg, kl_l, elbo,
+    elbo_finish_kernel<<<(d.num_problems + 3) / 4, 128, 0, s>>>(D, d.num_problems, scale, klw, partial, nseg, kl_l, elbo,
                                                                     kl_out, loss_out);
     h->launches++;
   }
