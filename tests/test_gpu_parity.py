@@ -842,3 +842,19 @@ def test_tc_min_samples_option():
     assert np.all(np.abs(tc["elbo"] - f64["elbo"]) <= 1e-4 * np.abs(f64["elbo"]))
     for k in ("d_q_mu", "d_q_sqrt", "d_lengthscales", "d_variances"):
         assert H.rel_err(tc[k], f64[k]) < 1e-3, k
+
+
+def test_tc_training_steps_track_the_float64_sampler():
+    """Five optimisation steps at 64 samples with device draws: the run whose prior contraction goes through the tensor cores
+    (3xTF32) must stay within the north_star tolerances of the run that keeps it on the float64 DMMA path - same seed, same
+    Philox draws, Adam in the loop (errors are amplified from step to step, so this is the tight end of what the tolerance
+    allows: loss 1e-6 relative after five steps, parameters 1e-5)."""
+    case = H.make_case(num_problems=2, S=64, N=24, M=8, B=128, seed=21)
+    tc, f64 = H.make_model(case, seed=9), H.make_model(case, seed=9)
+    f64._eng.set_option("tc_sampler", 0)
+    for step in range(5):
+        a, b = _np(tc.train_step(case["X"])), _np(f64.train_step(case["X"]))
+        assert np.all(np.abs(a - b) <= 1e-6 * np.abs(b)), (step, a, b)
+    for name in ("_q_mu", "_q_sqrt", "_lengthscales", "_variances"):
+        assert H.rel_err(_np(getattr(tc, name)), _np(getattr(f64, name))) < 1e-5, name
+    assert not torch.equal(tc._q_mu, f64._q_mu)            # two different samplers really ran
