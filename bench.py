@@ -115,7 +115,7 @@ def problem_queries(cfg_id, cfg, ps, robot, args):
 
 class ClockSampler:
     """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML is polled in-process every
-    5 ms (the default timed region is ~15 ms: `nvidia-smi -lms 50` would see it once); without the NVML binding the
+    2 ms (the default timed region is ~15 ms: `nvidia-smi -lms 50` would see it once); without the NVML binding the
     nvidia-smi loop of the recipe is used."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -163,7 +163,7 @@ class ClockSampler:
                 self.rows.append((time.perf_counter(), mhz, mask))
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.002)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -175,7 +175,7 @@ class ClockSampler:
             rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
             reasons = sorted(k for k, bit in self.BITS.items() if any(r[2] & bit for r in rows))
             return {"sm_mhz": statistics.median([r[1] for r in rows]) if rows else None, "sm_max_mhz": self.smax,
-                    "reasons": reasons, "samples": len(rows), "source": "nvml, 5 ms period"}
+                    "reasons": reasons, "samples": len(rows), "source": "nvml, 2 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.06)
@@ -492,7 +492,8 @@ def run_b200(args):
     clocks = ClockSampler(local)
     clocks.start()
     time.sleep(0.15)
-    ms, launches, t0, _ = head.timed(args.steps, args.warmup, barrier)
+    ms, launches, t0, t1 = head.timed(args.steps, args.warmup, barrier)
+    clk = clocks.stop(t0, t1)      # the poller stops here: its wake-ups would otherwise jitter the host-driven e2e loop below
 
     # ------------------------------------------------------------------ stage profile (untimed extra pass)
     stages = head.stage_profile(min(args.steps, 50))
@@ -516,7 +517,6 @@ def run_b200(args):
         ms_e2e = f0.elapsed_time(f1)
         assert np.all(np.isfinite(last.numpy()))
     t2 = time.perf_counter()
-    clk = clocks.stop(t0, t2)
     ms, ms_e2e_r = reduce_max([ms, ms_e2e if ms_e2e is not None else 0.0])
 
     # ------------------------------------------------------------------ the other BASELINE configs at this GPU count
