@@ -94,11 +94,21 @@ __device__ __forceinline__ uint32_t mbar_test(uint64_t* b, uint32_t parity) {   
                : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
   return ok;
 }
+#ifndef VGPMP_MBAR_HINT_NS
+#define VGPMP_MBAR_HINT_NS 1000000
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  // try_wait parks the thread until the phase completes or the suspend-time hint runs out; with the default (short) limit
+  // a waiting warp re-issued the probe ~100 times per stage of the tensor-core sampler: 22 % of that kernel's issue slots
   uint32_t ok;
   do {
+#if VGPMP_MBAR_HINT_NS > 0
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity), "r"((uint32_t)VGPMP_MBAR_HINT_NS) : "memory");
+#else
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                  : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+#endif
   } while (!ok);
 }
 

@@ -401,8 +401,8 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
       auto wait_sleepy = [ab](uint64_t* b, uint32_t parity) {     // one thread polling: leave the issue slots to the workers
         uint32_t ok;
         for (;;) {
-          asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                       : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+          asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                       : "=r"(ok) : "r"(smem_u32(b)), "r"(parity), "r"((uint32_t)VGPMP_MBAR_HINT_NS) : "memory");
           if (ok) break;
           if (!(ab & 32)) __nanosleep(40);
         }
