@@ -3,10 +3,17 @@
 #pragma once
 #include "common.cuh"
 
+// Philox4x32-10 round keys (seed_lo + r W0, seed_hi + r W1): computed on the host, read as constant-bank operands by the
+// in-kernel generators (bumping the key in registers cost 18 of the ~100 instructions of a block of four normals)
+struct PhiloxKeys {
+  uint32_t k[20];
+};
+
 struct PathwiseArgs {
   int D, M, Nq, S, B, XG, KS;
   int gen_draws;       // 1: omega / tau / w are not in memory, the register-resident sampler generates them from the key below
   uint64_t seed, iteration;
+  PhiloxKeys rk;       // round keys of `seed` (filled with gen_draws)
   const unsigned long long* iter_dev;   // CUDA-graph replay: the iteration lives in device memory and is ADDED to `iteration`
   int64_t problem_offset, sample_offset;
   int items;           // work items of the general sampler (pairs x nchunk)
@@ -42,6 +49,18 @@ __device__ __forceinline__ void philox4x32(uint32_t c[4], uint32_t k0, uint32_t 
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
 }
+__device__ __forceinline__ void philox4x32(uint32_t c[4], const PhiloxKeys& rk) {   // same block function, precomputed round keys
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ rk.k[2 * r], n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ rk.k[2 * r + 1];
+    c[1] = (uint32_t)p1; c[3] = (uint32_t)p0; c[0] = n0; c[2] = n2;
+  }
+}
+inline void philox_round_keys(uint64_t seed, PhiloxKeys& rk) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) { rk.k[2 * r] = k0; rk.k[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
 __device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {  // (0,1), 53 bits
   const uint64_t x = ((uint64_t)hi << 32 | lo) >> 11;
   return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
@@ -49,20 +68,40 @@ __device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {  // (0,1), 53 
 // Four independent N(0,1) from one Philox block.  The draws are random inputs, not arithmetic of the reference: the
 // Box-Muller transform runs in float32 on the SFU (32-bit uniforms, |z| < 6.7) and is widened to float64.  Parity
 // tests feed the *materialised* draws to the oracle, so this choice cannot leak into a parity result.
+__device__ __forceinline__ void box_muller4f(const uint32_t c[4], float z[4]);
 __device__ __forceinline__ void normal4f(uint64_t seed, uint64_t iter, uint32_t stream, uint64_t idx, float z[4]) {
   uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)iter, stream ^ ((uint32_t)(iter >> 32) << 8)};
   philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  box_muller4f(c, z);
+}
+__device__ __forceinline__ void normal4f(const PhiloxKeys& rk, uint64_t iter, uint32_t stream, uint64_t idx, float z[4]) {
+  uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)iter, stream ^ ((uint32_t)(iter >> 32) << 8)};
+  philox4x32(c, rk);
+  box_muller4f(c, z);
+}
+__device__ __forceinline__ void box_muller4f(const uint32_t c[4], float z[4]) {
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const float u1 = ((float)c[2 * k] + 0.5f) * 2.3283064365386963e-10f;       // (0,1]
     const float u2 = ((float)c[2 * k + 1] + 0.5f) * 2.3283064365386963e-10f;
-    const float t = -2.0f * __logf(fminf(u1, 0.99999994f));     // > 1e-7
-    const float r = t * rsqrtf(t);                              // sqrt by one MUFU.RSQ (the IEEE sqrtf sequence was ~10 % of the sampler's instructions)
+    // t = -2 ln u1 > 1e-7 and r = sqrt(t) = t rsqrt(t), each ONE SFU instruction: the .ftz forms drop the denormal pre-scaling
+    // of __logf / rsqrtf (4 instructions each; u1 >= 1.2e-10 and t >= 1.2e-7 are never denormal, so every bit is unchanged)
+    float l2, rs;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fminf(u1, 0.99999994f)));
+    const float t = l2 * -1.3862943649291992f;                  // -2 * float(ln 2), the constant __logf multiplies by
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(t));
+    const float r = t * rs;
     float sn, cs;
     __sincosf(6.283185307179586f * u2, &sn, &cs);
     z[2 * k] = r * cs;
     z[2 * k + 1] = r * sn;
   }
+}
+__device__ __forceinline__ void normal4(const PhiloxKeys& rk, uint64_t iter, uint32_t stream, uint64_t idx, double z[4]) {
+  float zf[4];
+  normal4f(rk, iter, stream, idx, zf);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) z[k] = (double)zf[k];
 }
 __device__ __forceinline__ void normal4(uint64_t seed, uint64_t iter, uint32_t stream, uint64_t idx, double z[4]) {
   float zf[4];

@@ -736,14 +736,14 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
             const int ncall = (5 + D + 3) / 4;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              if (k < ncall) normal4(a.seed, a.iteration, 1u, key * 4 + k, z + 4 * k);
+              if (k < ncall) normal4(a.rk, a.iteration, 1u, key * 4 + k, z + 4 * k);
             const double gam = (z[0] * z[0] + z[1] * z[1] + z[2] * z[2] + z[3] * z[3] + z[4] * z[4]) / 5.0;
             const double rs = rsqrt(gam);
 #pragma unroll
             for (int d = 0; d < VGPMP_MAX_DOF; ++d)
               if (d < D) c = __dadd_rn(c, __dmul_rn(z[5 + d], rs));   // as stored then summed by the load path: no FMA
             uint32_t cc[4] = {(uint32_t)key, (uint32_t)(key >> 32), (uint32_t)a.iteration, 3u};
-            philox4x32(cc, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+            philox4x32(cc, a.rk);
             taub = 6.283185307179586476925 * u01(cc[0], cc[1]);
           }
           // weights: lane (quad, r) draws the two blocks (quad of 4 bases, samples r and r + 4) and later stores each
@@ -755,7 +755,7 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
             double z4[4] = {0.0, 0.0, 0.0, 0.0};
             if (i < ns && 4 * b4 < (uint32_t)B) {
               const uint64_t sg = (uint64_t)(s0 + i) + (uint64_t)a.sample_offset;
-              normal4(a.seed, a.iteration, 4u, (pairkey * (uint64_t)(1u << 24) + sg) * B4 + b4, z4);
+              normal4(a.rk, a.iteration, 4u, (pairkey * (uint64_t)(1u << 24) + sg) * B4 + b4, z4);
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) wcur[4 * hh + k] = z4[k];
@@ -972,14 +972,14 @@ __global__ void __launch_bounds__(256, 2) pathwise_rrm_kernel(PathwiseArgs a, co
           const int ncall = (5 + D + 3) / 4;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (k < ncall) normal4(a.seed, a.iteration, 1u, key * 4 + k, z + 4 * k);
+            if (k < ncall) normal4(a.rk, a.iteration, 1u, key * 4 + k, z + 4 * k);
           const double gam = (z[0] * z[0] + z[1] * z[1] + z[2] * z[2] + z[3] * z[3] + z[4] * z[4]) / 5.0;
           const double rs = rsqrt(gam);
 #pragma unroll
           for (int d = 0; d < VGPMP_MAX_DOF; ++d)
             if (d < D) c = __dadd_rn(c, __dmul_rn(z[5 + d], rs));   // as stored then summed by the load path: no FMA
           uint32_t cc[4] = {(uint32_t)key, (uint32_t)(key >> 32), (uint32_t)a.iteration, 3u};
-          philox4x32(cc, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+          philox4x32(cc, a.rk);
           taub = 6.283185307179586476925 * u01(cc[0], cc[1]);
         }
       } else if (live) {
@@ -1049,7 +1049,7 @@ __global__ void __launch_bounds__(256, 2) pathwise_rrm_kernel(PathwiseArgs a, co
           double z4[4] = {0.0, 0.0, 0.0, 0.0};
           if (i < ns && 4 * b4 < (uint32_t)B) {
             const uint64_t sg = (uint64_t)(s0 + i) + (uint64_t)a.sample_offset;
-            normal4(a.seed, a.iteration, 4u, (pairkey * (uint64_t)(1u << 24) + sg) * B4 + b4, z4);
+            normal4(a.rk, a.iteration, 4u, (pairkey * (uint64_t)(1u << 24) + sg) * B4 + b4, z4);
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -2161,6 +2161,7 @@ struct RngArgs {
   int D, B, S, Mp, Bp;
   int64_t problem_offset, sample_offset;
   uint64_t seed, iteration;
+  PhiloxKeys rk;                         // round keys of `seed`
   const unsigned long long* iter_dev;   // CUDA-graph replay: added to `iteration`
   double *omega, *tau, *w, *eps_u, *eps_j;
 };
@@ -2189,14 +2190,14 @@ __global__ void __launch_bounds__(256) rng_fill_kernel(RngArgs a, uint32_t bpp, 
     const int ncall = (5 + a.D + 3) / 4;                    // <= 4 for D <= 8
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (k < ncall) normal4(a.seed, a.iteration, 1u, key * 4 + k, z + 4 * k);
+      if (k < ncall) normal4(a.rk, a.iteration, 1u, key * 4 + k, z + 4 * k);
     const double gam = (z[0] * z[0] + z[1] * z[1] + z[2] * z[2] + z[3] * z[3] + z[4] * z[4]) / 5.0;
     const double rs = rsqrt(gam);
 #pragma unroll
     for (int d = 0; d < VGPMP_MAX_DOF; ++d)
       if (d < a.D) a.omega[gid * a.D + d] = z[5 + d] * rs;
     uint32_t c[4] = {(uint32_t)key, (uint32_t)(key >> 32), (uint32_t)a.iteration, 3u};
-    philox4x32(c, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    philox4x32(c, a.rk);
     a.tau[gid] = 6.283185307179586476925 * u01(c[0], c[1]);
     continue;
   }
@@ -2206,7 +2207,7 @@ __global__ void __launch_bounds__(256) rng_fill_kernel(RngArgs a, uint32_t bpp, 
     const uint64_t s = (uint64_t)sl + (uint64_t)a.sample_offset;
     const uint64_t key = ((p * D + l) * (uint64_t)(1u << 24) + s) * B4 + b4;  // sample index < 2^24
     double z[4];
-    normal4(a.seed, a.iteration, 4u, key, z);
+    normal4(a.rk, a.iteration, 4u, key, z);
     double* dst = a.w + ((size_t)pair * S + sl) * B + (size_t)b4 * 4;
     if (b4 * 4 + 4 <= B && (B & 1) == 0) {
       reinterpret_cast<double2*>(dst)[0] = make_double2(z[0], z[1]);
@@ -2223,7 +2224,7 @@ __global__ void __launch_bounds__(256) rng_fill_kernel(RngArgs a, uint32_t bpp, 
     const uint64_t s = (uint64_t)sl + (uint64_t)a.sample_offset;
     const uint64_t key = ((p * D + l) * (uint64_t)(1u << 24) + s) * 16 + m2;
     double z[4];
-    normal4(a.seed, a.iteration, 5u, key, z);
+    normal4(a.rk, a.iteration, 5u, key, z);
     const size_t o = ((size_t)pair * S + sl) * Mp + (size_t)m2 * 2;
     a.eps_u[o] = z[0];
     a.eps_j[o] = z[2];
@@ -2334,6 +2335,7 @@ cudaError_t launch_pathwise(vgpmp_handle* h, const vgpmp_dims& d, const vgpmp_pa
   if (lazy && (tc_path || rr_path)) {
     a.gen_draws = 1;
     a.seed = lz.seed; a.iteration = lz.iteration; a.problem_offset = lz.problem_offset; a.sample_offset = lz.sample_offset;
+    philox_round_keys(a.seed, a.rk);
   } else if (lazy) {
     if (!have_buffers) return cudaErrorInvalidValue;          // no in-kernel generator for this shape: the caller must provide buffers
     if ((e = launch_rng_fill(h, d, lz.seed, lz.iteration, lz.problem_offset, lz.sample_offset, const_cast<double*>(r.omega),
@@ -2602,6 +2604,7 @@ cudaError_t launch_rng_fill(vgpmp_handle* h, const vgpmp_dims& d, uint64_t seed,
   RngArgs a;
   a.D = h->robot.dof; a.B = d.num_bases; a.S = d.num_samples; a.Mp = d.num_inducing + 2; a.Bp = d.num_problems;
   a.problem_offset = problem_offset; a.sample_offset = sample_offset; a.seed = seed; a.iteration = iteration;
+  philox_round_keys(seed, a.rk);
   a.iter_dev = h->capture_iter_dev;
   a.omega = omega; a.tau = tau; a.w = w; a.eps_u = eps_u; a.eps_j = eps_j;
   const size_t per_pair = (omega ? (size_t)a.B : 0) + (w ? (size_t)a.S * ((a.B + 3) / 4) : 0) +

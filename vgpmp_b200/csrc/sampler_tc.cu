@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
           float z[4] = {0.f, 0.f, 0.f, 0.f};
           if (srow < S && 4 * b4g < (uint32_t)B && !(sh.ablate & 2)) {
             if (GEN) {
-              normal4f(a.seed, a.iteration, 4u, wkey + b4g, z);
+              normal4f(a.rk, a.iteration, 4u, wkey + b4g, z);
             } else {
               const double* src = wp + (size_t)srow * B + 4 * b4g;
 #pragma unroll
@@ -334,14 +334,14 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
             const int ncall = (5 + D + 3) / 4;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              if (k < ncall) normal4(a.seed, a.iteration, 1u, key * 4 + k, z + 4 * k);
+              if (k < ncall) normal4(a.rk, a.iteration, 1u, key * 4 + k, z + 4 * k);
             const double gam = (z[0] * z[0] + z[1] * z[1] + z[2] * z[2] + z[3] * z[3] + z[4] * z[4]) / 5.0;
             const double rs = rsqrt(gam);
 #pragma unroll
             for (int d = 0; d < VGPMP_MAX_DOF; ++d)
               if (d < D) c = __dadd_rn(c, __dmul_rn(z[5 + d], rs));
             uint32_t cc[4] = {(uint32_t)key, (uint32_t)(key >> 32), (uint32_t)a.iteration, 3u};
-            philox4x32(cc, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+            philox4x32(cc, a.rk);
             taub = 6.283185307179586476925 * u01(cc[0], cc[1]);
           } else {
             for (int d = 0; d < D; ++d) c += om[(size_t)b * D + d];
