@@ -40,7 +40,11 @@ constexpr int kGroup = 2;         // stages per TMEM partial sum (64 bases)
 #define VGPMP_TC_WORKERS 16
 #endif
 constexpr int kWorkers = VGPMP_TC_WORKERS;   // worker warps (8 or 16)
-constexpr int kTabWarps = 4;      // table producer warps, one table slot each (stage t is produced by warp t mod 4)
+#ifndef VGPMP_TC_TABWARPS
+#define VGPMP_TC_TABWARPS 3
+#endif
+constexpr int kTabWarps = VGPMP_TC_TABWARPS;   // table producer warps, one table slot each (stage t is produced by warp t mod kTabWarps).
+                                                // 16 + 3 + 1 = 20 warps: five per scheduler, so ptxas may use 96 registers (21 warps: 80, with spills)
 constexpr int kThreads = (kWorkers + kTabWarps + 1) * 32;
 constexpr int kTE = 2 * kWorkers + 10;   // doubles per basis in a table slot: segment starts [16][2] | Ex | Ez | e0 | e1 | cl | pad
 constexpr int kEx = 2 * kWorkers, kEz = kEx + 2, kE0 = kEx + 4, kE1 = kEx + 6, kCl = kEx + 8;
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
         float* Flo = Fhi + kFOp;
         // probe the two barriers this stage needs now, consume the answers after the weight draws: the try_wait round
         // trips (~hundreds of cycles each) then overlap with the Philox / Box-Muller chains instead of preceding them
-        const int tslot = tg & (kTabWarps - 1), tuse = tg / kTabWarps;
+        const int tslot = tg % kTabWarps, tuse = tg / kTabWarps;
         const uint32_t ok_empty = mbar_test(empty + slot, (use & 1) ^ 1);
         const uint32_t ok_tab = mbar_test(tab_full + tslot, tuse & 1);
         // ---- weights first (they need nothing but the key): 128 samples x 8 quads of 4 bases ----
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
     }
   } else if (warp < kWorkers + kTabWarps) {
     // =========================================== table producers ===========================================
-    // warp j owns table slot j and produces the stages with (global stage counter) mod 4 == j: one warp alone needs
+    // warp j owns table slot j and produces the stages with (global stage counter) mod kTabWarps == j: one warp alone needs
     // ~8 000 cycles per table (a serial chain of ~1 200 mostly float64 instructions), four in flight keep ahead of the workers
     const int tw = warp - kWorkers;
     for (int item = blockIdx.x; item < sh.items; item += gridDim.x) {
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
       const double* om = GEN ? nullptr : a.omega + (size_t)pl * B * D;
       const double* ta = GEN ? nullptr : a.tau + (size_t)pl * B;
       for (int t = 0; t < T; ++t, ++tg) {
-        if ((tg & (kTabWarps - 1)) != tw) continue;
+        if (tg % kTabWarps != tw) continue;
         const int slot = tw, use = tg / kTabWarps;
         const int b = t * kTB + lane;
         const bool live = b < B;
