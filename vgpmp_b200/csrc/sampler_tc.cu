@@ -40,6 +40,9 @@ constexpr int kGroup = 2;         // stages per TMEM partial sum (64 bases)
 #define VGPMP_TC_WORKERS 16
 #endif
 constexpr int kWorkers = VGPMP_TC_WORKERS;   // worker warps (8 or 16)
+#ifndef VGPMP_TC_MMA_SLEEP_NS
+#define VGPMP_TC_MMA_SLEEP_NS 200   // the issuing thread polls its barriers this often: a stage lasts ~2 us and two are in flight
+#endif
 #ifndef VGPMP_TC_TABWARPS
 #define VGPMP_TC_TABWARPS 3
 #endif
@@ -305,10 +308,11 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
           if (x >= A) continue;
           double scale = 1.0;
           if (hf == 1) scale = x < Nq ? t0 + dt * x : (x < Nq + 2 ? (double)(x - Nq) : z0 + dz * (x - Nq - 2));
-          for (int r = 0; r < 32; ++r) {
-            const int s = s0 + q * 32 + r;
-            if (s < S) dst[((size_t)pl * S + s) * A + x] = (double)tr[r * (CW + 1) + xl] * scale;
-          }
+          const int sbase = s0 + q * 32, rmax = min(32, S - sbase);
+          double* outp = dst + ((size_t)pl * S + sbase) * A + x;
+          const float* trp = tr + xl;
+#pragma unroll 4
+          for (int r = 0; r < rmax; ++r) outp[(size_t)r * A] = (double)trp[r * (CW + 1)] * scale;
         }
       }
       asm volatile("bar.sync 1, %0;" ::"r"(kWorkers * 32) : "memory");   // transposes read: the stages may be refilled
@@ -408,7 +412,7 @@ __global__ void __launch_bounds__(kThreads, 1) pathwise_tc_kernel(PathwiseArgs a
           asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
                        : "=r"(ok) : "r"(smem_u32(b)), "r"(parity), "r"((uint32_t)VGPMP_MBAR_HINT_NS) : "memory");
           if (ok) break;
-          if (!(ab & 32)) __nanosleep(40);
+          if (!(ab & 32)) __nanosleep(VGPMP_TC_MMA_SLEEP_NS);
         }
       };
       for (int item = blockIdx.x; item < sh.items; item += gridDim.x) {
