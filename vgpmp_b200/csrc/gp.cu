@@ -804,6 +804,7 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
         *reinterpret_cast<double2*>(e + 36) = make_double2(ab * ce0, ab * se0);
         *reinterpret_cast<double2*>(e + 38) = make_double2(ab * ce1, ab * se1);
         *reinterpret_cast<double2*>(e + 40) = make_double2(cb * inv_ell, 0.0);
+        *reinterpret_cast<double2*>(e + 50) = make_double2(0.0, 0.0);     // the consumers' zero pair (padding rows)
         if (gen) {
           double* eq = tab + ((size_t)slot * kRB + (lane & ~3)) * kRE + 42 + (lane & 3);   // row of basis 4*quad, column of sample r
 #pragma unroll
@@ -826,55 +827,51 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
       double acc[kRT][2][2];
 #pragma unroll
       for (int j = 0; j < kRT; ++j) acc[j][0][0] = acc[j][0][1] = acc[j][1][0] = acc[j][1][1] = 0.0;
-      const int Q = T * (kRB / 4);
-      int cur = -1;                                         // slot number (within this sample tile) this warp holds
-      // rows Nq and Nq+1 (the conditioned endpoints) live in tile JX-1, or JX-2 and JX-1; this lane's role there:
-      const int xa = 8 * (JX - 2) + g, xb = 8 * (JX - 1) + g;       // its row index in those two tiles
-      const int ea = xa - Nq, eb = xb - Nq;                        // < 0: chain value, 0 / 1: endpoint, > 1: padding
-      for (int q = warp; q < Q; q += kRC) {
-        const int n = q / (kRB / 4);
-        if (n != cur) {
-          if (cur >= 0) {                                                // done with the previous slot
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + (it * T + cur) % kRS);
-          }
-          const int N = it * T + n;
-          mbar_wait(full + N % kRS, (N / kRS) & 1);                     // this slot is filled (acquire)
-          cur = n;
-        }
-        const double* e = tab + ((size_t)((it * T + n) % kRS) * kRB + (q % (kRB / 4)) * 4 + t4) * kRE;
-        const double wk = e[42 + g];                                        // w[sample g][basis], staged by the producer
-        double2 ph = *reinterpret_cast<const double2*>(e + 2 * g);          // chain state: (cos, sin) of row g, amplitude in
-        double2 st = *reinterpret_cast<const double2*>(e + 16);             // E^8 of the query grid
-        const double wq = wk * e[40];                                       // w c / l for the d/dlengthscale contraction
+      // rows Nq and Nq+1 (the conditioned endpoints) live in tile JX-1, or JX-2 and JX-1.  This lane's role there is loop
+      // invariant: -1 = its chain value, else the offset of the (cos, sin) pair to use instead - endpoint 0 / 1 at 36 / 38,
+      // padding rows at 50 (a pair the producers keep at zero).  (Deciding this inside the basis loop cost ~35 of the ~165
+      // instructions of a step; the slot / quad index arithmetic below another ~20.)
+      const int ea = 8 * (JX - 2) + g - Nq, eb = 8 * (JX - 1) + g - Nq;
+      const int offa = (JX >= 2 && ea >= 0) ? (ea < 2 ? 36 + 2 * ea : 50) : -1;
+      const int offb = eb >= 0 ? (eb < 2 ? 36 + 2 * eb : 50) : -1;
+      unsigned roles = (offa >= 0 ? (unsigned)offa : 63u) | ((offb >= 0 ? (unsigned)offb : 63u) << 6);   // 63 = chain value
+      asm volatile("" : "+r"(roles));      // one opaque register: otherwise the compiler re-derives both in every step
+      const double* ebase = tab + (size_t)(warp * 4 + t4) * kRE;            // this warp's first quad of a slot, this lane's basis
+      for (int n = 0; n < T; ++n) {
+        const int N = it * T + n, slot = N % kRS;
+        mbar_wait(full + slot, (N / kRS) & 1);                             // this slot is filled (acquire)
+        const double* e = ebase + (size_t)slot * kRB * kRE;
+#pragma unroll 1
+        for (int hq = 0; hq < (kRB / 4) / kRC; ++hq, e += (size_t)kRC * 4 * kRE) {   // quads warp, warp + kRC of the slot
+          const double wk = e[42 + g];                                        // w[sample g][basis], staged by the producer
+          double2 ph = *reinterpret_cast<const double2*>(e + 2 * g);          // chain state: (cos, sin) of row g, amplitude in
+          double2 st = *reinterpret_cast<const double2*>(e + 16);             // E^8 of the query grid
+          const double wq = wk * e[40];                                       // w c / l for the d/dlengthscale contraction
 #pragma unroll
-        for (int j = 0; j < kRT; ++j) {
-          if (j == JX) {                                                    // inducing grid starts here
-            ph = *reinterpret_cast<const double2*>(e + 18 + 2 * g);
-            st = *reinterpret_cast<const double2*>(e + 34);
-          }
-          double ac = ph.x, as = ph.y;
-          if (j == JX - 2 && JX >= 2) {
-            if (ea >= 0) {
-              const double2 ep = ea < 2 ? *reinterpret_cast<const double2*>(e + 36 + 2 * ea) : make_double2(0.0, 0.0);
-              ac = ep.x; as = ep.y;
+          for (int j = 0; j < kRT; ++j) {
+            if (j == JX) {                                                    // inducing grid starts here
+              ph = *reinterpret_cast<const double2*>(e + 18 + 2 * g);
+              st = *reinterpret_cast<const double2*>(e + 34);
             }
-          }
-          if (j == JX - 1) {
-            if (eb >= 0) {
-              const double2 ep = eb < 2 ? *reinterpret_cast<const double2*>(e + 36 + 2 * eb) : make_double2(0.0, 0.0);
-              ac = ep.x; as = ep.y;
+            double ac = ph.x, as = ph.y;
+            if (j == JX - 2 && JX >= 2) {
+              const unsigned o = roles & 63u;
+              if (o != 63u) { const double2 ep = *reinterpret_cast<const double2*>(e + o); ac = ep.x; as = ep.y; }
             }
+            if (j == JX - 1) {
+              const unsigned o = roles >> 6;
+              if (o != 63u) { const double2 ep = *reinterpret_cast<const double2*>(e + o); ac = ep.x; as = ep.y; }
+            }
+            dmma884(acc[j][0][0], acc[j][0][1], ac, wk);
+            dmma884(acc[j][1][0], acc[j][1][1], as, wq);
+            const double c2 = ph.x * st.x - ph.y * st.y;
+            ph.y = ph.y * st.x + ph.x * st.y;
+            ph.x = c2;
           }
-          dmma884(acc[j][0][0], acc[j][0][1], ac, wk);
-          dmma884(acc[j][1][0], acc[j][1][1], as, wq);
-          const double c2 = ph.x * st.x - ph.y * st.y;
-          ph.y = ph.y * st.x + ph.x * st.y;
-          ph.x = c2;
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + slot);                          // done with the slot
       }
-      __syncwarp();
-      if (cur >= 0 && lane == 0) mbar_arrive(empty + (it * T + cur) % kRS);
       // the ring is dead only after ALL consumers left the loop: consumer-only barrier, then the partial sums of this
       // warp go to red[warp][feature][sample][row] over it
       asm volatile("bar.sync 1, %0;" ::"r"(kRC * 32) : "memory");
