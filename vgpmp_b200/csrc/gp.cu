@@ -1453,6 +1453,7 @@ __global__ void __launch_bounds__(256, 4) gp_backward_kernel(BackwardArgs a) {
       double t = 0.0;
       if (i < ns && m < Mp) {
         const double* dfs = dft + (size_t)i * N;
+#pragma unroll 4
         for (int n = 0; n < N; ++n) t += Kfu[n * Mp + m] * dfs[n];
       }
       gv[idx] = t;
@@ -1472,6 +1473,7 @@ __global__ void __launch_bounds__(256, 4) gp_backward_kernel(BackwardArgs a) {
     for (int n = warp; n < N; n += nw) {
       if (lane < Mp) {
         double t = 0.0;
+#pragma unroll 4
         for (int i = 0; i < ns; ++i) t += dft[(size_t)i * N + n] * vsm[i * 32 + lane];
         // k = s2 (1 + a + a^2/3) e^-a is in Kfu; dk/dr = -(5/3) r (1 + a) e^-a follows from it by a division (no second exp)
         const double r = fabs(a.X[(size_t)n * D + l] - zy[lane]) * inv_ell, av = VG_SQRT5 * r;
@@ -1484,6 +1486,7 @@ __global__ void __launch_bounds__(256, 4) gp_backward_kernel(BackwardArgs a) {
     for (int i = warp; i < Mp; i += nw) {
       if (lane < Mp) {
         double t = 0.0, u = 0.0;
+#pragma unroll 4
         for (int k = 0; k < ns; ++k) {
           const double g = gr[k * 32 + i];
           t += g * vsm[k * 32 + lane];
@@ -1562,6 +1565,7 @@ __global__ void __launch_bounds__(256, 4) gp_backward_kernel(BackwardArgs a) {
       const int c_ = lane;
       double t = 0.0;
       if (c_ <= r_) {
+#pragma unroll 4
         for (int i = r_ + 2; i < Mp; ++i) t += Lsm[i * LDM + r_ + 2] * GS[i * LDM + c_ + 2];
         const double qv = q[r_ * M + c_];
         t -= a.klw * (qv - (r_ == c_ ? 1.0 / qv : 0.0));  // - d KL / d q_sqrt
@@ -1573,6 +1577,7 @@ __global__ void __launch_bounds__(256, 4) gp_backward_kernel(BackwardArgs a) {
     const int k = lane;
     if (k >= 2 && k <= i) {
       double t = 0.0;
+#pragma unroll 4
       for (int j = 2; j <= k; ++j) t += GS[i * LDM + j] * q[(k - 2) * M + (j - 2)];
       GL[i * LDM + k] += t;
     }
@@ -1626,6 +1631,7 @@ __global__ void __launch_bounds__(256, 4) gp_backward_kernel(BackwardArgs a) {
     const int j = lane;
     double t = 0.0;
     if (j <= i) {
+#pragma unroll 4
       for (int k = i; k < Mp; ++k) t += Lsm[k * LDM + i] * GL[k * LDM + j];
       if (i == j) t *= 0.5;
     }
@@ -1637,6 +1643,7 @@ __global__ void __launch_bounds__(256, 4) gp_backward_kernel(BackwardArgs a) {
     const int j = lane;
     double t = 0.0;
     if (j <= i)
+#pragma unroll 4
       for (int k = j; k <= i; ++k) t += Pm[i * LDM + k] * Lism[k * LDM + j];
     T1[i * LDM + j] = t;
   }
@@ -1645,6 +1652,7 @@ __global__ void __launch_bounds__(256, 4) gp_backward_kernel(BackwardArgs a) {
     const int j = lane;
     if (j < Mp) {
       double t = 0.0;
+#pragma unroll 4
       for (int k = max(i, j); k < Mp; ++k) t += Lism[k * LDM + i] * T1[k * LDM + j];
       G[i * LDM + j] += t;
     }
