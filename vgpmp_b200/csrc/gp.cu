@@ -1018,6 +1018,7 @@ __global__ void __launch_bounds__(256, 2) pathwise_rrm_kernel(PathwiseArgs a, co
       *reinterpret_cast<double2*>(e + 36) = make_double2(ab * cv[4], ab * sv[4]);
       *reinterpret_cast<double2*>(e + 38) = make_double2(ab * cv[5], ab * sv[5]);
       *reinterpret_cast<double2*>(e + 40) = make_double2(cb * inv_ell, 0.0);
+      *reinterpret_cast<double2*>(e + kRMW + 8 * NT) = make_double2(0.0, 0.0);     // the consumers' zero pair
       // group phasors: consumer warp w starts at tile 3 w, i.e. E8x^(3w) on the query grid or E8z^(3w - JX) on the inducing grid
       {
         double px = 1.0, qx = 0.0, pz = 1.0, qz = 0.0;
@@ -1074,12 +1075,14 @@ __global__ void __launch_bounds__(256, 2) pathwise_rrm_kernel(PathwiseArgs a, co
     // sw: the inducing grid starts at this tile (reload the row start, no group offset)
     // (packed into one word: 2 bits of role + 1 bit of sw per tile - kept as arrays the compiler re-derived them in every
     // step of the basis loop, 12 % of the kernel's instructions)
-    unsigned roles = 0;
-#pragma unroll
+    constexpr int kZero = kRMW + 8 * NT;          // a pair the producers keep at zero (padding rows read it)
+    static_assert(kZero + 2 <= kEM && kZero < 127, "slot entry has no room for the zero pair");
+    unsigned roles = 0;                           // per tile: 7 bits = offset of the pair used instead of the chain value (127: none),
+#pragma unroll                                    //           bit 7 = the inducing grid starts at this tile
     for (int jj = 0; jj < kTPW; ++jj) {
       const int j = j0 + jj, ex = 8 * j + g - Nq;
-      const unsigned md = (j < JX && ex >= 0) ? (ex < 2 ? 1u + ex : 3u) : 0u;
-      roles |= (md | ((jj > 0 && j == JX) ? 4u : 0u)) << (3 * jj);
+      const unsigned off = (j < JX && ex >= 0) ? (ex < 2 ? 36u + 2u * ex : (unsigned)kZero) : 127u;
+      roles |= (off | ((jj > 0 && j == JX) ? 128u : 0u)) << (8 * jj);
     }
     asm volatile("" : "+r"(roles));                // opaque from here on: one register, extracted by shifts
     const bool startx = j0 < JX;
@@ -1114,17 +1117,14 @@ __global__ void __launch_bounds__(256, 2) pathwise_rrm_kernel(PathwiseArgs a, co
 #pragma unroll
       for (int jj = 0; jj < kTPW; ++jj) {
         if (jj >= tpw) break;
-        const unsigned role = (roles >> (3 * jj)) & 7u;
-        if (role & 4u) {
+        const unsigned role = (roles >> (8 * jj)) & 255u;
+        if (role & 128u) {
           ph = *reinterpret_cast<const double2*>(e + 18 + 2 * g);
           st = *reinterpret_cast<const double2*>(e + 34);
         }
         double ac = ph.x, as = ph.y;
-        if (role & 3u) {
-          const unsigned md = role & 3u;
-          const double2 ep = md < 3u ? *reinterpret_cast<const double2*>(e + 36 + 2 * (md - 1)) : make_double2(0.0, 0.0);
-          ac = ep.x; as = ep.y;
-        }
+        const unsigned o = role & 127u;
+        if (o != 127u) { const double2 ep = *reinterpret_cast<const double2*>(e + o); ac = ep.x; as = ep.y; }
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
           dmma884(acc[jj][0][i][0], acc[jj][0][i][1], ac, wk[i]);
