@@ -277,9 +277,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "franka/bookshelves planner_params S=7 N=70 M=24 B=1024, bounded sample of the 275-problem batch",
+        # the B200 arm's config 2 (same workload string, same shape keys); what was actually timed is in cpu_baseline.sample
+        "config": {"workload": CONFIGS[2]["what"], "baseline_config": 2, "problems_total": 275 * max(args.gpus, 1),
+                   "problems_this_gpu": 275, "S": 7, "N": 70, "M": 24, "B": 1024, "dof": 7, "spheres": 37,
                    "sdf": "bookshelves_center.obj -> float64 SDF on the host (oracle mesh producer), delta=0.01, padding=20: "
-                          "the grid of the GPU arm", "note": note},
+                          "the grid of the GPU arm", "sample": sample, "note": note},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
