@@ -844,14 +844,24 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
 #pragma unroll 1
         for (int hq = 0; hq < (kRB / 4) / kRC; ++hq, e += (size_t)kRC * 4 * kRE) {   // quads warp, warp + kRC of the slot
           const double wk = e[42 + g];                                        // w[sample g][basis], staged by the producer
-          double2 ph = *reinterpret_cast<const double2*>(e + 2 * g);          // chain state: (cos, sin) of row g, amplitude in
+          // Chain state: (cos, sin) of row g (amplitude in), advanced from tile to tile by the three-term recurrence
+          //   x_{j+1} = 2 cos(theta8) x_j - x_{j-1}      (theta8 = phase step of 8 rows)
+          // - one DFMA per value instead of the DMUL + DFMA of a complex product, and a one-deep dependency in front of the
+          // next tile's DMMA.  x_{-1} comes from one inverse rotation per grid.  Rounding errors grow like sin(m theta)/sin(theta)
+          // <= m <= 8 and the rounding of 2 cos(theta8) shifts the phase by <= 8 eps / theta8: far below the 1e-7 the samples
+          // are checked to, for any step a Student-t frequency produces.
+          double2 ph = *reinterpret_cast<const double2*>(e + 2 * g);
           double2 st = *reinterpret_cast<const double2*>(e + 16);             // E^8 of the query grid
+          double2 pm = make_double2(ph.x * st.x + ph.y * st.y, ph.y * st.x - ph.x * st.y);   // x_{-1} = x_0 E^-8
+          double k2 = 2.0 * st.x;
           const double wq = wk * e[40];                                       // w c / l for the d/dlengthscale contraction
 #pragma unroll
           for (int j = 0; j < kRT; ++j) {
             if (j == JX) {                                                    // inducing grid starts here
               ph = *reinterpret_cast<const double2*>(e + 18 + 2 * g);
               st = *reinterpret_cast<const double2*>(e + 34);
+              pm = make_double2(ph.x * st.x + ph.y * st.y, ph.y * st.x - ph.x * st.y);
+              k2 = 2.0 * st.x;
             }
             double ac = ph.x, as = ph.y;
             if (j == JX - 2 && JX >= 2) {
@@ -864,9 +874,9 @@ __global__ void __launch_bounds__(256, 2) pathwise_rr_kernel(PathwiseArgs a, con
             }
             dmma884(acc[j][0][0], acc[j][0][1], ac, wk);
             dmma884(acc[j][1][0], acc[j][1][1], as, wq);
-            const double c2 = ph.x * st.x - ph.y * st.y;
-            ph.y = ph.y * st.x + ph.x * st.y;
-            ph.x = c2;
+            const double nc = fma(k2, ph.x, -pm.x), ns_ = fma(k2, ph.y, -pm.y);
+            pm = ph;
+            ph = make_double2(nc, ns_);
           }
         }
         __syncwarp();
