@@ -16,15 +16,16 @@
 // TMEM accumulator only ever holds the partial sum of 64 bases: two TMEM regions alternate, and the worker warps fold
 // every finished partial into FP32 registers with round-to-nearest adds (16 folds per output) while the next 64 bases run.
 //
-// Warp roles (576 threads, 1 CTA per SM, persistent over work items):
+// Warp roles (640 threads = five warps per scheduler, so that ptxas may use 96 registers; 1 CTA per SM, persistent):
 //   warps 0-15 workers.  Per stage of 32 bases: features by complex rotation along the two grids in float64 (warp =
-//              segment of rows, lane = basis; start / step phasors come from the table warp), split into hi / lo and
+//              segment of rows, lane = basis; start / step phasors come from the table warps), split into hi / lo and
 //              stored in the UMMA canonical K-major no-swizzle layout [basis / 4][row][4]; the stage's 128 x 32 weights
 //              from Philox4x32-10 (same keys as rng_fill_kernel: the trajectory is the one materialised draws give) or
 //              from memory; every second stage the fold described above (warp = TMEM lane quarter x column quarter).
 //              The producer side is issue / latency bound (Philox and Box-Muller are serial chains), hence 16 warps.
-//   warp 16    table producer: lane = basis; omega / tau draws, 6 lock-step sincos, segment start phasors by powers.
-//   warp 17    lane 0 issues the MMAs (12 per stage) and commits them to the mbarriers that free the stage / publish the
+//   warps 16-18 table producers, one table slot each (stage t belongs to warp t mod 3): lane = basis; omega / tau draws,
+//              6 lock-step sincos, segment start phasors by powers (a serial chain of ~1 200 instructions per table).
+//   warp 19    lane 0 issues the MMAs (12 per stage) and commits them to the mbarriers that free the stage / publish the
 //              group; the warp also owns the TMEM allocation.
 #include <algorithm>
 #include <cstdlib>

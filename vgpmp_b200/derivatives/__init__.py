@@ -4,9 +4,9 @@ In the reference `gpflow_vgpmp/derivatives/` holds kernel-derivative covariances
 branch `VGPMP.initialize` never builds; the gradient of the ELBO itself comes from TF
 autodiff (utils/miscellaneous.py:68-84).  Here the name is kept for the hand-written reverse pass:
 
-    d ELBO / d f              loglik_kernel<D, true>   (SDF custom gradient -> sphere wrenches -> joint axes -> sigmoid)
+    d ELBO / d f              loglik_bwd_kernel<D>     (SDF custom gradient -> sphere wrenches -> joint axes -> sigmoid)
     d ELBO / d {_q_mu, _q_sqrt, lengthscales, variances}
-                              gp_backward_kernel       (pathwise update, Cholesky reverse, KL)
+                              gp_backward_kernel, gp_backward_samples_kernel   (pathwise update, Cholesky reverse, KL)
 """
 from __future__ import annotations
 
